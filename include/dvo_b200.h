@@ -1,0 +1,174 @@
+/* dvo_b200.h -- C-ABI of the B200-native direct-alignment hot path (libdvo_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of mpkuse/rgbd_odometry: plain pointers and sizes only, no
+ * torch / Eigen / OpenCV types.  The reference has no FFI of its own -- its interface is the C++ class API of
+ * SolveDVO / EPoseEstimator / PyramidalStorageStruct / GOP (include/SolveDVO.h:148-360,
+ * include/EPoseEstimator.h:33-106, include/PyramidalStorage.h:37-78, include/GOP.h:67-95).  Each entry point
+ * below cites the reference member(s) it replaces; rgbd_odometry_b200/host/ re-creates those classes on top of
+ * this ABI, and INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - images are row-major, tightly packed; gray is u8, depth is u16 millimetres, BGR is u8 HWC;
+ *   - a context owns device memory for `max_batch` independent frame pairs ("slots"); every call that takes
+ *     (first, count) addresses slots [first, first+count);
+ *   - rotation matrices are row-major double[9]; a pose record is R[9] followed by T[3] (12 doubles) with the
+ *     reference's convention  p_now = R^T (P_ref - T)   (src/SolveDVO.cpp:330);
+ *   - `mem` arguments: DVO_MEM_HOST (pageable or pinned host memory) or DVO_MEM_DEVICE (device pointers);
+ *   - every function returns 0 on success, <0 on error (see dvo_last_error()); work is enqueued on the
+ *     context's CUDA stream and is asynchronous unless the call returns data to host memory.
+ *   - There is NO CPU fallback: every entry point fails with DVO_ERR_CUDA when no CUDA device is usable.
+ */
+#ifndef DVO_B200_H_
+#define DVO_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DVO_MAX_LEVELS 6
+
+enum { DVO_OK = 0, DVO_ERR_ARG = -1, DVO_ERR_CUDA = -2, DVO_ERR_STATE = -3, DVO_ERR_NOMEM = -4 };
+enum { DVO_MEM_HOST = 0, DVO_MEM_DEVICE = 1 };
+enum { DVO_FRAME_REF = 0, DVO_FRAME_NOW = 1 };
+
+/* solver (runIterations, src/SolveDVO.cpp:619-1017).  SUBGRAD_REF is the shipped projected sub-gradient
+ * method; GN / LM solve the 6x6 normal equations the same kernels accumulate (north_star extension). */
+enum { DVO_SOLVER_SUBGRAD_REF = 0, DVO_SOLVER_GN = 1, DVO_SOLVER_LM = 2 };
+/* Jacobian: REFERENCE = computeJacobianOfNowFrame as written (normalised coordinates, src/SolveDVO.cpp:383-406);
+ * EXACT = analytic derivative of the residual wrt the right-multiplicative pose update. */
+enum { DVO_JAC_REFERENCE = 0, DVO_JAC_EXACT = 1 };
+/* weights: REF_CAUCHY = getWeightOf (src/SolveDVO.cpp:1047-1053); HUBER; NONE. */
+enum { DVO_WEIGHT_REF_CAUCHY = 0, DVO_WEIGHT_HUBER = 1, DVO_WEIGHT_NONE = 2 };
+/* per-point fp32 arithmetic: EXACT reproduces the oracle's IEEE operation order bit for bit (no FMA
+ * contraction, IEEE division); FAST lets the compiler contract and uses approximate reciprocals. */
+enum { DVO_ARITH_EXACT = 0, DVO_ARITH_FAST = 1 };
+/* pyramid flavour: NEAREST = camTopic2PublisherPyD (src/camTopic2PublisherPyD.cpp:338-348);
+ * AREA = EPoseEstimator (src/EPoseEstimator.cpp:251-253, 284-286). */
+enum { DVO_PYR_NEAREST = 0, DVO_PYR_AREA = 1 };
+
+/* which = selector for dvo_get_level_buffer */
+enum {
+    DVO_BUF_GRAY = 0,   /* u8   [h][w]   pyramid level of the gray image                                  */
+    DVO_BUF_DEPTH = 1,  /* u16  [h][w]   pyramid level of depth (mm, zeros replaced by 1, SolveDVO.cpp:512) */
+    DVO_BUF_EDGE = 2,   /* u8   [h][w]   Canny edge map, 0 / 255                                          */
+    DVO_BUF_D2 = 3,     /* i32  [h][w]   exact squared Euclidean distance to the nearest edge pixel       */
+    DVO_BUF_DTN = 4,    /* f32  [h][w]   normalised distance transform (0..255)                           */
+    DVO_BUF_GX = 5,     /* f32  [h][w]   d(DTn)/dx, central difference * 0.5                              */
+    DVO_BUF_GY = 6      /* f32  [h][w]   d(DTn)/dy                                                        */
+};
+
+typedef struct dvo_ctx dvo_ctx;
+
+typedef struct dvo_config {
+    int width, height;      /* level-0 resolution                                              */
+    int levels;             /* pyramid levels, 1..DVO_MAX_LEVELS (reference ships 4)            */
+    int max_batch;          /* frame pairs resident on the device per launch                    */
+    int device;             /* CUDA device ordinal                                              */
+    int keep_now_depth;     /* 1: store the now frame's depth pyramid too (needed only so a now frame can
+                               later become the reference, SolveDVO::setPrevFrameAsRefFrame :561-584)   */
+    int trace_iters;        /* >0: keep a per-iteration trace (g, H, energy, pose) of this many iterations
+                               per level for parity tests; 0 in production                              */
+} dvo_config;
+
+typedef struct dvo_solver_params {
+    int solver;             /* DVO_SOLVER_*   */
+    int jacobian;           /* DVO_JAC_*      */
+    int weight;             /* DVO_WEIGHT_*   */
+    int arithmetic;         /* DVO_ARITH_*    */
+    float huber_k;
+    double lm_lambda0;
+    int iters[DVO_MAX_LEVELS];  /* iterationsConfig (src/SolveDVO.cpp:30-33); 0 skips the level */
+} dvo_solver_params;
+
+/* per pair result record (what runIterations returns besides the pose, src/SolveDVO.cpp:997-1005, plus the
+ * quiet-path residual statistic of processResidueHistogram :1398-1483) */
+typedef struct dvo_pair_info {
+    int status;                          /* 0 ok; bit0: a level had no reference points or no now edges   */
+    int npts[DVO_MAX_LEVELS];            /* selected reference edge points per level                      */
+    int best_index[DVO_MAX_LEVELS];      /* bestEnergyIndex per level                                     */
+    int iterations_run[DVO_MAX_LEVELS];  /* iterations actually executed per level                        */
+    float best_energy[DVO_MAX_LEVELS];   /* ||eps||_2 of the best iterate                                 */
+    float visible_ratio[DVO_MAX_LEVELS]; /* finalVisibleRatio                                             */
+    float laplacian_b;                   /* mean(eps_best) at the finest executed level                   */
+} dvo_pair_info;
+
+const char* dvo_last_error(void);
+int dvo_device_count(void);
+
+/* lifetime: replaces the SolveDVO / EPoseEstimator constructors' state (src/SolveDVO.cpp:5-70) */
+int dvo_create(const dvo_config* cfg, dvo_ctx** out);
+int dvo_destroy(dvo_ctx* ctx);
+/* run on a caller-owned CUDA stream (cudaStream_t as void*); NULL restores the context's own stream */
+int dvo_set_stream(dvo_ctx* ctx, void* cuda_stream);
+int dvo_synchronize(dvo_ctx* ctx);
+
+/* SolveDVO::setCameraMatrix (src/SolveDVO.cpp:88-126): intrinsics of level 0 */
+int dvo_set_intrinsics(dvo_ctx* ctx, float fx, float fy, float cx, float cy);
+
+/* frame ingest: SolveDVO::imageArrivedCallBack + setRcvdFrameAsRefFrame / setRcvdFrameAsNowFrame
+ * (src/SolveDVO.cpp:490-614).  Full-resolution images; the pyramid is built by dvo_build_pyramids.
+ * depth may be NULL for the now frame (the edge solver never reads it). */
+int dvo_set_frames(dvo_ctx* ctx, int frame, int first, int count, const uint8_t* gray, const uint16_t* depth, int mem);
+/* SolveDVO::setPrevFrameAsRefFrame (src/SolveDVO.cpp:561-584): the now frame of every slot becomes its
+ * reference frame (pyramid, edges and depth are moved on the device; needs keep_now_depth). */
+int dvo_promote_now_to_ref(dvo_ctx* ctx, int first, int count);
+
+/* pyramid construction (src/camTopic2PublisherPyD.cpp:338-348): levels 1.. from level 0, both frames */
+int dvo_build_pyramids(dvo_ctx* ctx, int first, int count, int frames_mask /* bit0 ref, bit1 now */);
+
+/* computeDistTransfrmOfRef/Now + preProcessRefFrame (src/SolveDVO.cpp:1679-1799, 269-303):
+ * Canny, exact EDT, normalise, gradient for the now frame; Canny + edge-point back-projection for the
+ * reference frame. */
+int dvo_prepare(dvo_ctx* ctx, int first, int count, int frames_mask);
+
+/* initial pose per slot (cR_64, cT_64 of src/SolveDVO.cpp:1931-1932); NULL = identity */
+int dvo_set_initial_pose(dvo_ctx* ctx, int first, int count, const double* R9T3, int mem);
+
+/* the coarse-to-fine solve (src/SolveDVO.cpp:2097-2104 calling runIterations :619-1017) */
+int dvo_run(dvo_ctx* ctx, int first, int count, const dvo_solver_params* params);
+
+/* read back poses (12 doubles per slot) and optional info records */
+int dvo_get_poses(dvo_ctx* ctx, int first, int count, double* R9T3, dvo_pair_info* info, int mem);
+
+/* One call for a whole batch with host buffers: upload, pyramids, prepare, run, download (the end-to-end path
+ * SolveDVO::loop executes per frame, src/SolveDVO.cpp:2017-2104).  count may exceed max_batch; the batch is
+ * processed in chunks.  now_depth may be NULL. */
+int dvo_align_batch(dvo_ctx* ctx, int count, const uint8_t* ref_gray, const uint16_t* ref_depth,
+                    const uint8_t* now_gray, const uint16_t* now_depth, const dvo_solver_params* params,
+                    double* R9T3, dvo_pair_info* info);
+
+/* ---- inspection (parity tests; not on the hot path) ---- */
+int dvo_level_dims(dvo_ctx* ctx, int level, int* w, int* h);
+int dvo_get_level_buffer(dvo_ctx* ctx, int slot, int frame, int level, int which, void* host_dst, size_t bytes);
+/* reference edge points of one slot/level in enumeration order (SpaceCordList _3d, src/SolveDVO.cpp:287-289) */
+int dvo_get_points(dvo_ctx* ctx, int slot, int level, float* X, float* Y, float* Z, int capacity, int* n);
+/* one evaluation of the normal equations at a given pose: H = J^T W J (row-major 6x6), g = J^T W eps,
+ * sumsq = sum eps^2, nvis; optional per-point outputs (capacity = npts): eps, w, reprojection u, v, J (N x 6) */
+int dvo_eval_normal_equations(dvo_ctx* ctx, int slot, int level, const double* R9T3, int jacobian, int weight,
+                              int arithmetic, float huber_k, double* H36, double* g6, double* sumsq, int* nvis,
+                              float* eps, float* w, float* u, float* v, float* J);
+/* per-iteration trace of the last dvo_run (needs cfg.trace_iters > 0): for level `level`, `trace_iters` records of
+ * 56 doubles: g[6], H[36], energy, nvis, R[9], T[3] (zero where not executed) */
+int dvo_get_trace(dvo_ctx* ctx, int slot, int level, double* trace);
+
+/* per-stage device time of the most recent calls, CUDA events on the context stream (ms); enable first */
+enum { DVO_STAGE_H2D = 0, DVO_STAGE_PYRAMID, DVO_STAGE_CANNY, DVO_STAGE_EDT_ROWS, DVO_STAGE_NORMGRAD, DVO_STAGE_SOLVE,
+       DVO_STAGE_D2H, DVO_STAGE_COUNT };
+int dvo_enable_timing(dvo_ctx* ctx, int on);
+int dvo_get_stage_ms(dvo_ctx* ctx, float* ms /* DVO_STAGE_COUNT */);
+/* number of kernel launches issued by this context since creation */
+long long dvo_launch_count(dvo_ctx* ctx);
+
+/* ---- GOP<double> (src/GOP.cpp:138-196): batched composition on the device ----
+ * For `nseq` independent sequences of `nframes` relative poses each (12 doubles, relative to the sequence's last
+ * key frame) and kind[] (0 ordinary, 1 key frame, 2 ordinary then updateMostRecentToKeyFrame), write global poses
+ * out[nseq][nframes][19] = R[9], T[3], px py pz qx qy qz qw. */
+int dvo_gop_compose(dvo_ctx* ctx, int nseq, int nframes, const int* kind, const double* rel, double* out, int mem);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DVO_B200_H_ */

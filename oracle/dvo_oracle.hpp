@@ -1,0 +1,699 @@
+// dvo_oracle.hpp -- CPU restatement of the reference's direct-alignment hot path.
+//
+// TEST INFRASTRUCTURE ONLY.  Nothing under rgbd_odometry_b200/ (the product) includes, links or calls this.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use it.
+//
+// PARITY STATUS: "parity unpinned" by the reference's own tests -- mpkuse/rgbd_odometry ships no tests, no
+// golden vectors and no data files, and it cannot be compiled here (needs ROS, Eigen, OpenCV
+// C++, Sophus, libigl).  This file restates the reference's arithmetic line by line, each
+// function citing the reference file:line it follows (paths relative to the reference checkout).  The
+// OpenCV-defined stages (Canny, distanceTransform, normalize, filter2D, resize, cvtColor) are pinned against
+// cv2 4.13 by tests/test_oracle_vs_cv2.py and by the committed fixtures under tests/golden/.
+//
+// Build: g++ -O3 -ffp-contract=off (no -ffast-math): every float expression below is evaluated exactly in
+// the written order with one IEEE rounding per operation, which is what the CUDA "exact" arithmetic mirrors.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace orc {
+
+// ------------------------------------------------------------------------------------------------------
+// Pyramid construction (R1, R12)
+// ------------------------------------------------------------------------------------------------------
+
+// cv::resize(..., Size(), s, s, ...) output size: cvRound(dim * s), round-half-to-even
+// (reference call sites: src/camTopic2PublisherPyD.cpp:344-345).
+inline int level_dim(int dim, int level) { return (int)std::nearbyint((double)dim * std::ldexp(1.0, -level)); }
+
+// INTER_NEAREST from full resolution: dst(y,x) = src(min(y*2^k, H-1), min(x*2^k, W-1))
+// (src/camTopic2PublisherPyD.cpp:338-345, src/publisherPyD.cpp:230-239).
+template <typename T>
+void pyr_nearest(const T* src, int W, int H, int level, T* dst, int channels = 1) {
+    const int w = level_dim(W, level), h = level_dim(H, level), s = 1 << level;
+    for (int y = 0; y < h; ++y) {
+        int sy = y * s; if (sy > H - 1) sy = H - 1;
+        for (int x = 0; x < w; ++x) {
+            int sx = x * s; if (sx > W - 1) sx = W - 1;
+            for (int c = 0; c < channels; ++c)
+                dst[((size_t)y * w + x) * channels + c] = src[((size_t)sy * W + sx) * channels + c];
+        }
+    }
+}
+
+// INTER_AREA from full resolution with integer scale 2^k (src/EPoseEstimator.cpp:251-253, 284-286):
+// k=1 -> (sum4 + 2) >> 2 ; k>=2 -> rint_half_even((float)sum * (float)(1/area))  (SURVEY Appendix B.5).
+// Requires W, H divisible by 2^k (true for every BASELINE config level that EPoseEstimator builds).
+template <typename T>
+void pyr_area(const T* src, int W, int H, int level, T* dst, int channels = 1) {
+    const int s = 1 << level, w = W / s, h = H / s;
+    if (level == 0) { std::memcpy(dst, src, sizeof(T) * (size_t)W * H * channels); return; }
+    const float inv_area = (float)(1.0 / (double)(s * s));
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x)
+            for (int c = 0; c < channels; ++c) {
+                int sum = 0;
+                for (int dy = 0; dy < s; ++dy)
+                    for (int dx = 0; dx < s; ++dx)
+                        sum += (int)src[((size_t)(y * s + dy) * W + (x * s + dx)) * channels + c];
+                T out;
+                if (level == 1) out = (T)((sum + 2) >> 2);
+                else out = (T)(int)std::nearbyintf((float)sum * inv_area);
+                dst[((size_t)y * w + x) * channels + c] = out;
+            }
+}
+
+// cvtColor BGR2GRAY, u8, OpenCV 4.x 15-bit fixed point (src/camTopic2PublisherPyD.cpp:347,
+// src/EPoseEstimator.cpp:71,120).
+inline void bgr2gray(const uint8_t* bgr, size_t npix, uint8_t* gray) {
+    for (size_t i = 0; i < npix; ++i)
+        gray[i] = (uint8_t)((bgr[3 * i] * 3735 + bgr[3 * i + 1] * 19235 + bgr[3 * i + 2] * 9798 + (1 << 14)) >> 15);
+}
+
+// Depth ingest: metres f32 -> millimetres u16 (src/camTopic2PublisherPyD.cpp:72-80): fp32 multiply by 1000,
+// saturate_cast<ushort>(cvRound) (half-even), then 0 -> 1.
+inline void depth_m_to_mm(const float* m, size_t n, uint16_t* mm) {
+    for (size_t i = 0; i < n; ++i) {
+        float v = m[i] * 1000.0f;
+        int r = std::isfinite(v) ? (int)std::nearbyintf(v > 1e9f ? 1e9f : (v < -1e9f ? -1e9f : v)) : 0;
+        r = r < 0 ? 0 : (r > 65535 ? 65535 : r);
+        mm[i] = (uint16_t)(r == 0 ? 1 : r);
+    }
+}
+// SolveDVO ingest: dframe.setTo(1, dframe==0) (src/SolveDVO.cpp:512).
+inline void depth_fix_zero(uint16_t* d, size_t n) { for (size_t i = 0; i < n; ++i) if (d[i] == 0) d[i] = 1; }
+
+// ------------------------------------------------------------------------------------------------------
+// Canny (R3; cv::Canny(img, 150, 100, 3, true) at src/SolveDVO.cpp:1705,1767)
+// ------------------------------------------------------------------------------------------------------
+inline void canny(const uint8_t* img, int W, int H, uint8_t* edge, double t1 = 150.0, double t2 = 100.0) {
+    double lo_d = t1 < t2 ? t1 : t2, hi_d = t1 < t2 ? t2 : t1;
+    lo_d = lo_d > 32767.0 ? 32767.0 : lo_d; hi_d = hi_d > 32767.0 ? 32767.0 : hi_d;
+    if (lo_d > 0) lo_d *= lo_d; if (hi_d > 0) hi_d *= hi_d;           // L2gradient: thresholds are squared
+    const int low = (int)std::floor(lo_d), high = (int)std::floor(hi_d);
+    const size_t P = (size_t)W * H;
+    std::vector<int> dx(P), dy(P);
+    // magnitude with a 1-pixel zero border
+    const int MW = W + 2;
+    std::vector<int> mag((size_t)MW * (H + 2), 0);
+    auto px = [&](int y, int x) -> int {                               // BORDER_REPLICATE
+        y = y < 0 ? 0 : (y >= H ? H - 1 : y); x = x < 0 ? 0 : (x >= W ? W - 1 : x);
+        return (int)img[(size_t)y * W + x];
+    };
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            int gx = (px(y - 1, x + 1) + 2 * px(y, x + 1) + px(y + 1, x + 1)) -
+                     (px(y - 1, x - 1) + 2 * px(y, x - 1) + px(y + 1, x - 1));
+            int gy = (px(y + 1, x - 1) + 2 * px(y + 1, x) + px(y + 1, x + 1)) -
+                     (px(y - 1, x - 1) + 2 * px(y - 1, x) + px(y - 1, x + 1));
+            dx[(size_t)y * W + x] = gx; dy[(size_t)y * W + x] = gy;
+            mag[(size_t)(y + 1) * MW + (x + 1)] = gx * gx + gy * gy;
+        }
+    // non-maximum suppression: 0 = none, 1 = weak candidate, 2 = strong
+    const int CANNY_SHIFT = 15;
+    const int TG22 = (int)(0.4142135623730950488016887242097 * (1 << CANNY_SHIFT) + 0.5);
+    std::vector<uint8_t> cls(P, 0);
+    std::vector<int> stack;
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            const int* m0 = &mag[(size_t)(y + 1) * MW + (x + 1)];
+            const int m = *m0;
+            if (m <= low) continue;
+            int xs = dx[(size_t)y * W + x], ys = dy[(size_t)y * W + x];
+            int ax = std::abs(xs), ay = std::abs(ys) << CANNY_SHIFT;
+            int tg22x = ax * TG22;
+            bool keep;
+            if (ay < tg22x) keep = (m > m0[-1]) && (m >= m0[1]);
+            else {
+                int tg67x = tg22x + (ax << (CANNY_SHIFT + 1));
+                if (ay > tg67x) keep = (m > m0[-MW]) && (m >= m0[MW]);
+                else { int s = ((xs ^ ys) < 0) ? -1 : 1; keep = (m > m0[-MW - s]) && (m > m0[MW + s]); }
+            }
+            if (!keep) continue;
+            if (m > high) { cls[(size_t)y * W + x] = 2; stack.push_back(y * W + x); }
+            else cls[(size_t)y * W + x] = 1;
+        }
+    // hysteresis: grow strong pixels through 8-connected weak candidates
+    while (!stack.empty()) {
+        int p = stack.back(); stack.pop_back();
+        int y = p / W, x = p % W;
+        for (int dy2 = -1; dy2 <= 1; ++dy2)
+            for (int dx2 = -1; dx2 <= 1; ++dx2) {
+                int yy = y + dy2, xx = x + dx2;
+                if (yy < 0 || yy >= H || xx < 0 || xx >= W) continue;
+                size_t q = (size_t)yy * W + xx;
+                if (cls[q] == 1) { cls[q] = 2; stack.push_back((int)q); }
+            }
+    }
+    for (size_t i = 0; i < P; ++i) edge[i] = cls[i] == 2 ? 255 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Exact squared Euclidean distance transform (R3; cv::distanceTransform(255-E, L2, PRECISE) at
+// src/SolveDVO.cpp:1709,1771).  Integer arithmetic only (Meijster et al. 2000).
+// d2(y,x) = min over edge pixels (edge != 0) of dy^2 + dx^2.  Returns the number of edge pixels; if there
+// are none every d2 is EDT_INF (the reference's DT is undefined there and it later asserts, :282).
+// ------------------------------------------------------------------------------------------------------
+constexpr int EDT_INF_1D = 1 << 14;                   // "no edge in this column" marker (> any image dim)
+constexpr int EDT_INF = EDT_INF_1D * EDT_INF_1D;      // 2^28
+
+inline size_t edt_d2(const uint8_t* edge, int W, int H, int32_t* d2) {
+    std::vector<int> g((size_t)W * H);
+    size_t nedge = 0;
+    for (int x = 0; x < W; ++x) {                      // phase 1: vertical distance to nearest edge in column
+        int d = EDT_INF_1D;
+        for (int y = 0; y < H; ++y) {
+            if (edge[(size_t)y * W + x]) { d = 0; ++nedge; } else if (d < EDT_INF_1D) ++d;
+            g[(size_t)y * W + x] = d;
+        }
+        d = EDT_INF_1D;
+        for (int y = H - 1; y >= 0; --y) {
+            if (edge[(size_t)y * W + x]) d = 0; else if (d < EDT_INF_1D) ++d;
+            if (d < g[(size_t)y * W + x]) g[(size_t)y * W + x] = d;
+        }
+    }
+    std::vector<int> s(W), t(W);
+    for (int y = 0; y < H; ++y) {                      // phase 2: lower envelope of parabolas per row
+        const int* gr = &g[(size_t)y * W];
+        auto f = [&](int x, int i) -> long long { long long dx = x - i; return dx * dx + (long long)gr[i] * gr[i]; };
+        auto sep = [&](int i, int u) -> long long {   // first x where parabola u beats parabola i (i < u)
+            long long num = (long long)u * u - (long long)i * i + (long long)gr[u] * gr[u] - (long long)gr[i] * gr[i];
+            long long den = 2LL * (u - i);
+            // floor division (num may be negative)
+            long long q = num / den; if ((num % den != 0) && ((num < 0) != (den < 0))) --q;
+            return q;
+        };
+        int q = 0; s[0] = 0; t[0] = 0;
+        for (int u = 1; u < W; ++u) {
+            while (q >= 0 && f(t[q], s[q]) > f(t[q], u)) --q;
+            if (q < 0) { q = 0; s[0] = u; }
+            else {
+                long long w = 1 + sep(s[q], u);
+                if (w < W) { ++q; s[q] = u; t[q] = (int)w; }
+            }
+        }
+        for (int u = W - 1; u >= 0; --u) {
+            long long v = f(u, s[q]);
+            d2[(size_t)y * W + u] = (int32_t)(v > EDT_INF ? EDT_INF : v);
+            if (u == t[q]) --q;
+        }
+    }
+    return nedge;
+}
+
+// DT := correctly rounded sqrtf(d2); normalize(DT, 0, 255, NORM_MINMAX) (src/SolveDVO.cpp:1712,1774):
+// OpenCV computes scale = (dmax-dmin) * (1/(smax-smin)) in double, narrows it to float for a 32F output, and
+// shift = (float)dmin - (float)(smin*scale); dst = src*scale + shift in fp32.
+inline void dt_normalize(const int32_t* d2, size_t n, float* dtn, float* scale_out = nullptr) {
+    float mn = INFINITY, mx = -INFINITY;
+    for (size_t i = 0; i < n; ++i) { float v = std::sqrt((float)d2[i]); if (v < mn) mn = v; if (v > mx) mx = v; }
+    double smin = mn, smax = mx;
+    double scale = (255.0 - 0.0) * ((smax - smin > 2.220446049250313e-16) ? 1.0 / (smax - smin) : 0.0);
+    float fscale = (float)scale;
+    float shift = (float)0.0 - (float)(smin * (double)fscale);
+    if (scale_out) *scale_out = fscale;
+    for (size_t i = 0; i < n; ++i) { float v = std::sqrt((float)d2[i]); float p = v * fscale; dtn[i] = p + shift; }
+}
+
+// imageGradient (R4; src/SolveDVO.cpp:1063-1098): filter2D with [-.5 0 .5] and its transpose,
+// BORDER_REFLECT_101 => exactly 0 on the first/last column (gx) and row (gy)  (SURVEY Appendix B.6).
+inline void gradient(const float* img, int W, int H, float* gx, float* gy) {
+    for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) {
+            int xl = x - 1 < 0 ? 1 : x - 1, xr = x + 1 >= W ? W - 2 : x + 1;
+            int yu = y - 1 < 0 ? 1 : y - 1, yd = y + 1 >= H ? H - 2 : y + 1;
+            if (W == 1) xl = xr = 0; if (H == 1) yu = yd = 0;
+            float a = 0.5f * img[(size_t)y * W + xr], b = -0.5f * img[(size_t)y * W + xl];
+            gx[(size_t)y * W + x] = b + a;
+            float c = 0.5f * img[(size_t)yd * W + x], d = -0.5f * img[(size_t)yu * W + x];
+            gy[(size_t)y * W + x] = d + c;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Camera + reference point list (R5)
+// ------------------------------------------------------------------------------------------------------
+struct Intrinsics { float fx, fy, cx, cy; };   // of level 0 (src/SolveDVO.cpp:103-106, include/SolveDVO.h:179)
+
+struct PointList { std::vector<float> X, Y, Z, u, v; size_t size() const { return X.size(); } };
+
+// selectedPts (src/SolveDVO.cpp:1230-1264) + enlistRefEdgePts (:224-264): column-major enumeration
+// (xx outer, yy inner); mask = edge > 0 && depth > 100.0f (mm).
+inline void select_points(const uint8_t* edge, const uint16_t* depth_mm, int W, int H, int level, Intrinsics K,
+                          PointList& out) {
+    out.X.clear(); out.Y.clear(); out.Z.clear(); out.u.clear(); out.v.clear();
+    const float scaleFac = (float)std::pow(2.0, -level);            // :231
+    const float tmpfx = (float)(1. / (double)(scaleFac * K.fx));    // :232 (double division, narrowed)
+    const float tmpfy = (float)(1. / (double)(scaleFac * K.fy));    // :233
+    const float tmpcx = scaleFac * K.cx, tmpcy = scaleFac * K.cy;   // :234-235
+    for (int xx = 0; xx < W; ++xx)
+        for (int yy = 0; yy < H; ++yy) {
+            float d = (float)depth_mm[(size_t)yy * W + xx];
+            if (edge[(size_t)yy * W + xx] > 0 && d > 100.0f) {
+                float Z = d / 1000.0f;                               // :248
+                float X = Z * ((float)xx - tmpcx) * tmpfx;           // :249  ((Z*(xx-cx))*tmpfx)
+                float Y = Z * ((float)yy - tmpcy) * tmpfy;           // :250
+                out.X.push_back(X); out.Y.push_back(Y); out.Z.push_back(Z);
+                out.u.push_back((float)xx); out.v.push_back((float)yy);
+            }
+        }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Small fp64 linear algebra / Lie group helpers (Eigen + Sophus are absent; closed forms)
+// All 3x3 matrices are row-major double[9].
+// ------------------------------------------------------------------------------------------------------
+inline void mat3_mul(const double* A, const double* B, double* C) {
+    double r[9];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+    std::memcpy(C, r, sizeof(r));
+}
+inline void mat3_vec(const double* A, const double* v, double* o) {
+    double r[3];
+    for (int i = 0; i < 3; ++i) r[i] = A[3 * i] * v[0] + A[3 * i + 1] * v[1] + A[3 * i + 2] * v[2];
+    o[0] = r[0]; o[1] = r[1]; o[2] = r[2];
+}
+inline void mat3_identity(double* A) { for (int i = 0; i < 9; ++i) A[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+
+// Eigen::Quaternion(Matrix3) (src/GOP.cpp:105).  q = (x, y, z, w).
+inline void rot_to_quat(const double* R, double* q) {
+    double t = R[0] + R[4] + R[8];
+    if (t > 0) {
+        double s = std::sqrt(t + 1.0);
+        q[3] = 0.5 * s; s = 0.5 / s;
+        q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+    } else {
+        int i = 0; if (R[4] > R[0]) i = 1; if (R[8] > R[4 * i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        double s = std::sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        q[i] = 0.5 * s; s = 0.5 / s;
+        q[3] = (R[3 * k + j] - R[3 * j + k]) * s;
+        q[j] = (R[3 * j + i] + R[3 * i + j]) * s;
+        q[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+    }
+}
+
+// Sophus::SE3d::exp(psi) (src/SolveDVO.cpp:905-907): psi = (upsilon, omega), translation part first.
+inline void se3_exp(const double* psi, double* R, double* t) {
+    const double* u = psi; const double* w = psi + 3;
+    double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = std::sqrt(th2);
+    double O[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0}, O2[9];
+    mat3_mul(O, O, O2);
+    double A, B, C;                                        // sin(th)/th, (1-cos)/th^2, (th-sin)/th^3
+    if (th < 1e-5) { A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; C = 1.0 / 6.0 - th2 / 120.0; }
+    else { A = std::sin(th) / th; B = (1.0 - std::cos(th)) / th2; C = (th - std::sin(th)) / (th2 * th); }
+    double V[9];
+    for (int i = 0; i < 9; ++i) {
+        double I = (i % 4 == 0) ? 1.0 : 0.0;
+        R[i] = I + A * O[i] + B * O2[i];
+        V[i] = I + B * O[i] + C * O2[i];
+    }
+    mat3_vec(V, u, t);
+}
+
+// Sophus::SE3d::log(SE3(R,t)) (src/SolveDVO.cpp:736-739).  Rotation goes through a unit quaternion
+// (setRotationMatrix), theta = 2*atan2(|q_v|, q_w).
+inline void se3_log(const double* R, const double* t, double* psi) {
+    double q[4]; rot_to_quat(R, q);
+    double qn = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int i = 0; i < 4; ++i) q[i] /= qn;
+    if (q[3] < 0) for (int i = 0; i < 4; ++i) q[i] = -q[i];
+    double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2], n = std::sqrt(n2), w = q[3];
+    double k;                                              // omega = k * q_v
+    if (n < 1e-10) k = 2.0 / w - 2.0 * n2 / (3.0 * w * w * w);
+    else k = 2.0 * std::atan2(n, w) / n;
+    double om[3] = {k * q[0], k * q[1], k * q[2]};
+    double th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2], th = std::sqrt(th2);
+    double O[9] = {0, -om[2], om[1], om[2], 0, -om[0], -om[1], om[0], 0}, O2[9];
+    mat3_mul(O, O, O2);
+    double D;                                              // (1 - th*sin/(2(1-cos)))/th^2
+    if (th < 1e-5) D = 1.0 / 12.0 + th2 / 720.0;
+    else D = (1.0 - th * std::sin(th) / (2.0 * (1.0 - std::cos(th)))) / th2;
+    double Vi[9];
+    for (int i = 0; i < 9; ++i) Vi[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * O[i] + D * O2[i];
+    mat3_vec(Vi, t, psi);
+    psi[3] = om[0]; psi[4] = om[1]; psi[5] = om[2];
+}
+
+// 3x3 SVD by two-sided Jacobi on A^T A (symmetric eigen-decomposition), U from A*V.  Sufficient for
+// rotationize(): A is within ~1e-15 of orthonormal, so all singular values are ~1 and well separated from 0.
+inline void svd3(const double* A, double* U, double* S, double* V) {
+    double B[9];                                           // B = A^T A
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) B[3 * i + j] = A[i] * A[j] + A[3 + i] * A[3 + j] + A[6 + i] * A[6 + j];
+    mat3_identity(V);
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = std::fabs(B[1]) + std::fabs(B[2]) + std::fabs(B[5]);
+        if (off < 1e-300) break;
+        bool rotated = false;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                double bpq = B[3 * p + q];
+                if (std::fabs(bpq) <= 1e-17 * std::sqrt(std::fabs(B[4 * p] * B[4 * q]))) continue;
+                rotated = true;
+                double tau = (B[4 * q] - B[4 * p]) / (2.0 * bpq);
+                double tt = (tau >= 0 ? 1.0 : -1.0) / (std::fabs(tau) + std::sqrt(1.0 + tau * tau));
+                double c = 1.0 / std::sqrt(1.0 + tt * tt), s = tt * c;
+                for (int k = 0; k < 3; ++k) {              // B <- B * J
+                    double bkp = B[3 * k + p], bkq = B[3 * k + q];
+                    B[3 * k + p] = c * bkp - s * bkq; B[3 * k + q] = s * bkp + c * bkq;
+                }
+                for (int k = 0; k < 3; ++k) {              // B <- J^T * B
+                    double bpk = B[3 * p + k], bqk = B[3 * q + k];
+                    B[3 * p + k] = c * bpk - s * bqk; B[3 * q + k] = s * bpk + c * bqk;
+                }
+                for (int k = 0; k < 3; ++k) {              // V <- V * J
+                    double vkp = V[3 * k + p], vkq = V[3 * k + q];
+                    V[3 * k + p] = c * vkp - s * vkq; V[3 * k + q] = s * vkp + c * vkq;
+                }
+            }
+        if (!rotated) break;
+    }
+    for (int j = 0; j < 3; ++j) {                          // U_j = A v_j / |A v_j|
+        double col[3];
+        for (int i = 0; i < 3; ++i) col[i] = A[3 * i] * V[j] + A[3 * i + 1] * V[3 + j] + A[3 * i + 2] * V[6 + j];
+        double n = std::sqrt(col[0] * col[0] + col[1] * col[1] + col[2] * col[2]);
+        S[j] = n;
+        for (int i = 0; i < 3; ++i) U[3 * i + j] = n > 0 ? col[i] / n : (i == j ? 1.0 : 0.0);
+    }
+}
+
+// SolveDVO::rotationize (src/SolveDVO.cpp:1269-1282): R <- U * diag(sigma>0 ? 1 : -1) * V^T.
+inline void rotationize(double* R) {
+    double U[9], S[3], V[9], US[9];
+    svd3(R, U, S, V);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) US[3 * i + j] = U[3 * i + j] * (S[j] > 0 ? 1.0 : -1.0);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) R[3 * i + j] = US[3 * i] * V[3 * j] + US[3 * i + 1] * V[3 * j + 1] + US[3 * i + 2] * V[3 * j + 2];
+}
+
+// 6x6 SPD solve (Cholesky, fp64); reads the upper triangle of Hin.  Returns false if not positive definite.
+inline bool chol6_solve(const double* Hin, const double* b, double* x) {
+    double L[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = Hin[6 * j + i];
+            for (int k = 0; k < j; ++k) s -= L[6 * i + k] * L[6 * j + k];
+            if (i == j) { if (!(s > 0)) return false; L[6 * i + i] = std::sqrt(s); }
+            else L[6 * i + j] = s / L[6 * j + j];
+        }
+    double y[6];
+    for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= L[6 * i + k] * y[k]; y[i] = s / L[6 * i + i]; }
+    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= L[6 * k + i] * x[k]; x[i] = s / L[6 * i + i]; }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// The per-level "now" buffers the solver gathers from, and the per-iteration evaluation (R6, R7)
+// ------------------------------------------------------------------------------------------------------
+struct LevelImages { int W = 0, H = 0; std::vector<float> dtn, gx, gy; };
+
+enum JacobianMode { JAC_REFERENCE = 0, JAC_EXACT = 1 };
+enum WeightMode { W_REF_CAUCHY = 0, W_HUBER = 1, W_NONE = 2 };
+enum SolverMode { SOLVER_SUBGRAD_REF = 0, SOLVER_GN = 1, SOLVER_LM = 2 };
+
+struct EvalOut {
+    double g[6]; double H[36]; double sumsq; int nvis;
+    std::vector<float> eps, w, reproj_u, reproj_v, J;    // per point (J: N x 6 row-major), optional
+};
+
+// getWeightOf (src/SolveDVO.cpp:1047-1053): 6.0 / (6.0 + r*r/.25), r*r in float, the rest in double.
+inline float weight_ref(float r) { float rr = r * r; return (float)(6.0 / (6.0 + (double)rr / .25)); }
+// Huber weight (extension; north_star "Huber/sub-gradient weights"): w = 1 if |r|<=k else k/|r|.
+inline float weight_huber(float r, float k) { float a = std::fabs(r); return a <= k ? 1.0f : k / a; }
+
+// computeJacobianOfNowFrame (src/SolveDVO.cpp:306-414) + getReprojectedEpsilons (:425-462) + the normal
+// equation sums of runIterations (:714-720, :777).  cR, cT are the fp64 pose; they are narrowed to fp32
+// exactly as :673-674 does.  H = sum (double)(J_i w_i)^T (double)J_i is the oracle's GN extension.
+inline void evaluate(const PointList& pts, const LevelImages& now, int level, Intrinsics K, const double* cR,
+                     const double* cT, JacobianMode jm, WeightMode wm, float huber_k, bool keep_per_point,
+                     EvalOut& out) {
+    const size_t N = pts.size();
+    float R[9], T[3];
+    for (int i = 0; i < 9; ++i) R[i] = (float)cR[i];
+    for (int i = 0; i < 3; ++i) T[i] = (float)cT[i];
+    const float scaleFac = (float)std::pow(2.0, -level);            // :334
+    // scaleMatrix * K (3x3 product evaluated first, :344): M00 = sf*fx, M02 = sf*cx, M11 = sf*fy, M12 = sf*cy
+    const float M00 = scaleFac * K.fx, M02 = scaleFac * K.cx, M11 = scaleFac * K.fy, M12 = scaleFac * K.cy;
+    const int nCols = now.W, nRows = now.H;
+    for (int i = 0; i < 6; ++i) out.g[i] = 0; for (int i = 0; i < 36; ++i) out.H[i] = 0;
+    out.sumsq = 0; out.nvis = 0;
+    if (keep_per_point) {
+        out.eps.assign(N, 0.f); out.w.assign(N, 0.f); out.reproj_u.assign(N, 0.f); out.reproj_v.assign(N, 0.f);
+        out.J.assign(N * 6, 0.f);
+    }
+    for (size_t i = 0; i < N; ++i) {
+        // p' = cR^T (P - cT)   (:330), accumulated k = 0,1,2
+        float d0 = pts.X[i] - T[0], d1 = pts.Y[i] - T[1], d2 = pts.Z[i] - T[2];
+        float px = (R[0] * d0 + R[3] * d1) + R[6] * d2;
+        float py = (R[1] * d0 + R[4] * d1) + R[7] * d2;
+        float pz = (R[2] * d0 + R[5] * d1) + R[8] * d2;
+        float inv = 1.0f / pz;                                       // :339
+        float X = px * inv, Y = py * inv, Z = pz * inv;              // :340-341 (all three rows)
+        // (scaleMatrix*K) * p_n  (:344): row 0 = (M00*X + 0*Y) + M02*Z ; the 0*Y term is an exact no-op
+        float u = M00 * X + M02 * Z, v = M11 * Y + M12 * Z;
+        if (keep_per_point) { out.reproj_u[i] = u; out.reproj_v[i] = v; }
+        // visibility (:371, :435): '>' bounds; u == nCols / v == nRows would index out of range in the
+        // reference (UB) and NaN would pass its test -- both treated as invisible here (measure zero).
+        if (!(u >= 0.0f && u < (float)nCols && v >= 0.0f && v < (float)nRows)) continue;
+        int xx = (int)u, yy = (int)v;                                // :376-377
+        size_t idx = (size_t)yy * nCols + xx;
+        float G0 = now.gx[idx], G1 = now.gy[idx];                    // :384-385
+        float Jr[6];
+        if (jm == JAC_REFERENCE) {
+            float A00 = M00 / Z, A02 = -((M00 * X) / (Z * Z));       // :388-390  (scaleFac*fx == M00)
+            float A11 = M11 / Z, A12 = -((M11 * Y) / (Z * Z));       // :392-393
+            // tmp = cR^T * p_n (:399)
+            float w0 = (R[0] * X + R[3] * Y) + R[6] * Z;
+            float w1 = (R[1] * X + R[4] * Y) + R[7] * Z;
+            float w2 = (R[2] * X + R[5] * Y) + R[8] * Z;
+            // G*A1 (1x3): the products with A1's structural zeros are exact no-ops
+            float a = G0 * A00, b = G1 * A11, c = G0 * A02 + G1 * A12;
+            // (G*A1) * A2, A2 = [ -cR^T | hat(w) ] (:397-405, to_se_3 :1104-1114)
+            Jr[0] = -((a * R[0] + b * R[1]) + c * R[2]);
+            Jr[1] = -((a * R[3] + b * R[4]) + c * R[5]);
+            Jr[2] = -((a * R[6] + b * R[7]) + c * R[8]);
+            Jr[3] = b * w2 - c * w1;                                 // a*0 + b*w2 + c*(-w1)
+            Jr[4] = c * w0 - a * w2;                                 // a*(-w2) + b*0 + c*w0  == (-(a*w2)) + c*w0
+            Jr[5] = a * w1 - b * w0;                                 // a*w1 + b*(-w0) + c*0
+        } else {
+            // Exact Jacobian of eps wrt the right-multiplicative update (T += R*ups, R <- R*exp(om)):
+            // d p'/d ups = -I, d p'/d om = hat(p'), projection Jacobian at the un-normalised p'.
+            float iz = 1.0f / pz;
+            float a = (G0 * M00) * iz, b = (G1 * M11) * iz;
+            float c = -((a * px + b * py) * iz);
+            Jr[0] = -a; Jr[1] = -b; Jr[2] = -c;
+            Jr[3] = b * pz - c * py; Jr[4] = c * px - a * pz; Jr[5] = a * py - b * px;
+        }
+        float e = now.dtn[idx];                                      // :446
+        float w;
+        if (wm == W_REF_CAUCHY) w = weight_ref(e); else if (wm == W_HUBER) w = weight_huber(e, huber_k); else w = 1.0f;
+        out.nvis++;
+        out.sumsq += (double)e * (double)e;
+        double de = (double)e;
+        double Jw[6];
+        for (int k = 0; k < 6; ++k) { float jw = Jr[k] * w; Jw[k] = (double)jw; out.g[k] += Jw[k] * de; }   // :714-720,:777
+        for (int r = 0; r < 6; ++r)
+            for (int c2 = 0; c2 < 6; ++c2) out.H[6 * r + c2] += Jw[r] * (double)Jr[c2];
+        if (keep_per_point) { out.eps[i] = e; out.w[i] = w; for (int k = 0; k < 6; ++k) out.J[6 * i + k] = Jr[k]; }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// runIterations (R8; src/SolveDVO.cpp:619-1017) and the GN / LM extension
+// ------------------------------------------------------------------------------------------------------
+struct SolverConfig {
+    SolverMode solver = SOLVER_SUBGRAD_REF;
+    JacobianMode jac = JAC_REFERENCE;
+    WeightMode weight = W_REF_CAUCHY;
+    float huber_k = 1.345f;
+    double lm_lambda0 = 1e-3;
+    float trust_radius = 0.003f;            // trustRegionHyperSphereRadius (src/SolveDVO.cpp:25)
+    float psi_term = 1.0E-7f;               // psiNormTerminationThreshold (:24)
+};
+
+struct IterTrace { double g[6]; double H[36]; float energy; int nvis; double R[9], T[3]; };
+
+struct LevelResult {
+    int best_index = -1; float best_energy = 1.0E10f; float visible_ratio = 1.0f; int iterations_run = 0;
+    std::vector<float> energies;            // energyAtEachIteration
+    std::vector<float> best_eps, best_u, best_v;
+    std::vector<IterTrace> trace;
+};
+
+inline void run_iterations(const PointList& pts, const LevelImages& now, int level, int maxIterations,
+                           Intrinsics K, const SolverConfig& cfg, double* cR, double* cT, LevelResult& res,
+                           bool keep_trace = false, bool keep_per_point = true) {
+    res = LevelResult();
+    res.energies.assign(maxIterations, 0.f);
+    float bestTotalEpsilon = 1.0E10f; float bestRatio = 1.0f;
+    double bestcR[9], bestcT[3] = {0, 0, 0}; mat3_identity(bestcR);
+    int bestItr = -1;
+    double descent[6] = {0, 0, 0, 0, 0, 0};
+    const double BETA = 0.5;
+    // LM state: last accepted linearisation
+    double accR[9] = {0}, accT[3] = {0}, accH[36] = {0}, accg[6] = {0}; float accE = 0; bool have_acc = false; double lambda = cfg.lm_lambda0;
+    EvalOut ev;
+    const size_t N = pts.size();
+    for (int itr = 0; itr < maxIterations; ++itr) {
+        evaluate(pts, now, level, K, cR, cT, cfg.jac, cfg.weight, cfg.huber_k, keep_per_point, ev);
+        float ratio = N ? (float)ev.nvis / (float)N : 0.f;            // :457
+        float energy = (float)std::sqrt(ev.sumsq);                    // aggregateEpsilons :1310-1312
+        res.energies[itr] = energy; res.iterations_run = itr + 1;
+        if (keep_trace) {
+            IterTrace t; std::memcpy(t.g, ev.g, sizeof(t.g)); std::memcpy(t.H, ev.H, sizeof(t.H));
+            t.energy = energy; t.nvis = ev.nvis; std::memcpy(t.R, cR, sizeof(t.R)); std::memcpy(t.T, cT, sizeof(t.T));
+            res.trace.push_back(t);
+        }
+        if (energy <= bestTotalEpsilon) {                             // :696-705
+            bestTotalEpsilon = energy; bestRatio = ratio; std::memcpy(bestcR, cR, sizeof(bestcR));
+            std::memcpy(bestcT, cT, sizeof(bestcT)); bestItr = itr;
+            if (keep_per_point) { res.best_eps = ev.eps; res.best_u = ev.reproj_u; res.best_v = ev.reproj_v; }
+        }
+        double psi[6];
+        if (cfg.solver == SOLVER_SUBGRAD_REF) {
+            double g[6]; std::memcpy(g, ev.g, sizeof(g));
+            // L2 regulariser (:736-743, :796)
+            double cPsi[6]; se3_log(cR, cT, cPsi);
+            double cn = 0; for (int k = 0; k < 6; ++k) cn += cPsi[k] * cPsi[k]; cn = std::sqrt(cn);
+            if (cn > 0) for (int k = 0; k < 6; ++k) cPsi[k] = cPsi[k] / cn;
+            double stepLength = 9.0 * 1.0E-2 / ((itr > 5) ? (double)(itr - 4) : 1.0);     // :773
+            for (int k = 0; k < 6; ++k) g[k] += 0.05 * cPsi[k];                            // :796
+            for (int k = 0; k < 6; ++k) descent[k] = (1.0 - BETA) * g[k] + BETA * descent[k];   // :799
+            const double P[6] = {1.0, 1.0, 1.0, 0.5, 0.5, 0.5};                             // :729
+            for (int k = 0; k < 6; ++k) psi[k] = -stepLength * P[k] * descent[k];           // :821
+            double norm = 0; for (int k = 0; k < 6; ++k) norm += psi[k] * psi[k]; norm = std::sqrt(norm);
+            if (norm > (double)cfg.trust_radius) {                                          // :835-839
+                for (int k = 0; k < 6; ++k) psi[k] = psi[k] / norm * (double)cfg.trust_radius;
+            } else {
+                double n2 = 0; for (int k = 0; k < 6; ++k) n2 += psi[k] * psi[k];
+                if (std::sqrt(n2) < cfg.psi_term) break;                                    // :840 -> :872 (dangling else)
+            }
+        } else {
+            // GN / LM extension on H = J^T W J, g = J^T W eps (not in the reference)
+            bool accept = (cfg.solver == SOLVER_GN) || !have_acc || (energy <= accE);
+            if (accept) {
+                std::memcpy(accR, cR, sizeof(accR)); std::memcpy(accT, cT, sizeof(accT));
+                std::memcpy(accH, ev.H, sizeof(accH)); std::memcpy(accg, ev.g, sizeof(accg)); accE = energy;
+                if (cfg.solver == SOLVER_LM && have_acc) lambda = lambda * 0.1 < 1e-9 ? 1e-9 : lambda * 0.1;
+                have_acc = true;
+            } else {
+                lambda *= 10.0;
+                if (lambda > 1e8) break;
+                std::memcpy(cR, accR, sizeof(accR)); std::memcpy(cT, accT, sizeof(accT));
+            }
+            double A[36], nb[6];
+            for (int k = 0; k < 36; ++k) A[k] = accH[k];
+            double lam = (cfg.solver == SOLVER_LM) ? lambda : 0.0;
+            for (int k = 0; k < 6; ++k) { A[7 * k] += lam * accH[7 * k] + 1e-9; nb[k] = -accg[k]; }
+            if (!chol6_solve(A, nb, psi)) break;
+            double n2 = 0; for (int k = 0; k < 6; ++k) n2 += psi[k] * psi[k];
+            if (std::sqrt(n2) < cfg.psi_term) break;
+        }
+        // pose update (:905-920)
+        double xR[9], xt[3], Rt[3];
+        se3_exp(psi, xR, xt);
+        mat3_vec(cR, xt, Rt);
+        cT[0] += Rt[0]; cT[1] += Rt[1]; cT[2] += Rt[2];
+        mat3_mul(cR, xR, cR);
+        rotationize(cR);
+    }
+    std::memcpy(cR, bestcR, sizeof(bestcR)); rotationize(cR);          // :997-1001
+    std::memcpy(cT, bestcT, sizeof(bestcT));
+    res.best_index = bestItr; res.best_energy = bestTotalEpsilon; res.visible_ratio = bestRatio;
+}
+
+// processResidueHistogram quiet path (R10; src/SolveDVO.cpp:1398-1483): b_cap = mean(eps) in fp32.
+inline float laplacian_b(const std::vector<float>& eps) {
+    float b = 0; for (float e : eps) b += e; return eps.empty() ? 0.f : b / (float)eps.size();
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Whole-frame helpers: computeDistTransfrmOfNow/Ref (R3/R4; src/SolveDVO.cpp:1679-1799) for all levels
+// ------------------------------------------------------------------------------------------------------
+struct FramePyramid {
+    int levels = 0;
+    std::vector<int> W, H;
+    std::vector<std::vector<uint8_t>> gray, edge;
+    std::vector<std::vector<uint16_t>> depth;
+    std::vector<std::vector<int32_t>> d2;
+    std::vector<LevelImages> img;
+    std::vector<size_t> nedge;
+};
+
+inline void build_frame(const uint8_t* gray, const uint16_t* depth, int W, int H, int levels, bool want_dt,
+                        FramePyramid& f) {
+    f.levels = levels; f.W.resize(levels); f.H.resize(levels); f.gray.resize(levels); f.edge.resize(levels);
+    f.depth.resize(levels); f.d2.resize(levels); f.img.resize(levels); f.nedge.assign(levels, 0);
+    for (int l = 0; l < levels; ++l) {
+        int w = level_dim(W, l), h = level_dim(H, l);
+        f.W[l] = w; f.H[l] = h;
+        f.gray[l].resize((size_t)w * h); pyr_nearest(gray, W, H, l, f.gray[l].data());
+        if (depth) { f.depth[l].resize((size_t)w * h); pyr_nearest(depth, W, H, l, f.depth[l].data()); depth_fix_zero(f.depth[l].data(), f.depth[l].size()); }
+        f.edge[l].resize((size_t)w * h); canny(f.gray[l].data(), w, h, f.edge[l].data());
+        if (want_dt) {
+            f.d2[l].resize((size_t)w * h); f.nedge[l] = edt_d2(f.edge[l].data(), w, h, f.d2[l].data());
+            LevelImages& li = f.img[l]; li.W = w; li.H = h;
+            li.dtn.resize((size_t)w * h); li.gx.resize((size_t)w * h); li.gy.resize((size_t)w * h);
+            dt_normalize(f.d2[l].data(), (size_t)w * h, li.dtn.data());
+            gradient(li.dtn.data(), w, h, li.gx.data(), li.gy.data());
+        } else {
+            size_t n = 0; for (uint8_t e : f.edge[l]) n += e ? 1 : 0; f.nedge[l] = n;
+        }
+    }
+}
+
+struct PairResult {
+    double R[9], T[3];
+    std::vector<LevelResult> levels;       // indexed by pyramid level
+    std::vector<size_t> npts;
+    int status = 0;                          // 0 ok; 1 = some level had no reference points / no now edges
+};
+
+// One frame pair through the shipped schedule (R9; src/SolveDVO.cpp:2097-2104): levels (L-1)..0, pose carried.
+inline void align_pair(const uint8_t* ref_gray, const uint16_t* ref_depth, const uint8_t* now_gray, int W, int H,
+                       int levels, Intrinsics K, const int* iters, const SolverConfig& cfg, const double* R0,
+                       const double* T0, PairResult& out, bool keep_trace = false, bool keep_per_point = false) {
+    FramePyramid ref, now;
+    build_frame(ref_gray, ref_depth, W, H, levels, false, ref);
+    build_frame(now_gray, nullptr, W, H, levels, true, now);
+    if (R0) std::memcpy(out.R, R0, sizeof(out.R)); else mat3_identity(out.R);
+    if (T0) std::memcpy(out.T, T0, sizeof(out.T)); else out.T[0] = out.T[1] = out.T[2] = 0;
+    out.levels.assign(levels, LevelResult()); out.npts.assign(levels, 0); out.status = 0;
+    for (int l = levels - 1; l >= 0; --l) {
+        if (iters[l] <= 0) continue;
+        PointList pts;
+        select_points(ref.edge[l].data(), ref.depth[l].data(), ref.W[l], ref.H[l], l, K, pts);
+        out.npts[l] = pts.size();
+        if (pts.size() == 0 || now.nedge[l] == 0) { out.status = 1; continue; }   // reference asserts (:282)
+        run_iterations(pts, now.img[l], l, iters[l], K, cfg, out.R, out.T, out.levels[l], keep_trace, keep_per_point);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// GOP (R11; src/GOP.cpp:138-196)
+// ------------------------------------------------------------------------------------------------------
+struct GopElement { bool key; int frame, reason; double R[9], T[3], pose[7]; };   // pose = px py pz qx qy qz qw
+struct Gop {
+    std::vector<GopElement> v; double kR[9], kT[3];
+    Gop() { mat3_identity(kR); kT[0] = kT[1] = kT[2] = 0; }
+    void push(int frame, bool key, int reason, const double* cR, const double* cT) {
+        GopElement e; e.key = key; e.frame = frame; e.reason = key ? reason : -1;
+        double RT[3]; mat3_vec(kR, cT, RT);
+        for (int i = 0; i < 3; ++i) e.T[i] = kT[i] + RT[i];                 // :144, :172
+        mat3_mul(kR, cR, e.R);                                                // :145, :173
+        e.pose[0] = e.T[0]; e.pose[1] = e.T[1]; e.pose[2] = e.T[2]; rot_to_quat(e.R, e.pose + 3);
+        v.push_back(e);
+        if (key) { std::memcpy(kR, e.R, sizeof(kR)); std::memcpy(kT, e.T, sizeof(kT)); }   // :184-185
+    }
+    void update_most_recent_to_key(int reason) {                              // :189-196
+        GopElement& e = v.back(); std::memcpy(kR, e.R, sizeof(kR)); std::memcpy(kT, e.T, sizeof(kT));
+        e.key = true; e.reason = reason;
+    }
+};
+
+}  // namespace orc

@@ -1,0 +1,88 @@
+"""ctypes binding of the C-ABI in include/dvo_b200.h (libdvo_b200.so).  Fails loudly when the CUDA library is missing."""
+import ctypes as C
+import os
+
+from . import build as _build
+
+MAX_LEVELS = 6
+STAGES = ["h2d", "pyramid", "canny", "edt_rows", "normgrad", "solve", "d2h"]
+
+
+class Config(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("levels", C.c_int), ("max_batch", C.c_int), ("device", C.c_int),
+                ("keep_now_depth", C.c_int), ("trace_iters", C.c_int)]
+
+
+class SolverParams(C.Structure):
+    _fields_ = [("solver", C.c_int), ("jacobian", C.c_int), ("weight", C.c_int), ("arithmetic", C.c_int),
+                ("huber_k", C.c_float), ("lm_lambda0", C.c_double), ("iters", C.c_int * MAX_LEVELS)]
+
+
+class PairInfo(C.Structure):
+    _fields_ = [("status", C.c_int), ("npts", C.c_int * MAX_LEVELS), ("best_index", C.c_int * MAX_LEVELS),
+                ("iterations_run", C.c_int * MAX_LEVELS), ("best_energy", C.c_float * MAX_LEVELS),
+                ("visible_ratio", C.c_float * MAX_LEVELS), ("laplacian_b", C.c_float)]
+
+
+# every symbol include/dvo_b200.h declares
+SYMBOLS = [
+    "dvo_last_error", "dvo_device_count", "dvo_create", "dvo_destroy", "dvo_set_stream", "dvo_synchronize",
+    "dvo_set_intrinsics", "dvo_set_frames", "dvo_promote_now_to_ref", "dvo_build_pyramids", "dvo_prepare",
+    "dvo_set_initial_pose", "dvo_run", "dvo_get_poses", "dvo_align_batch", "dvo_level_dims", "dvo_get_level_buffer",
+    "dvo_get_points", "dvo_eval_normal_equations", "dvo_get_trace", "dvo_enable_timing", "dvo_get_stage_ms",
+    "dvo_launch_count", "dvo_gop_compose",
+]
+
+_lib = None
+
+
+def load(build_if_missing=True):
+    """Load libdvo_b200.so (building it in-tree with nvcc when absent).  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing:
+        path = _build.build_cuda()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m rgbd_odometry_b200.build` (no CPU fallback exists)")
+    lib = C.CDLL(path)
+    lib.dvo_last_error.restype = C.c_char_p
+    lib.dvo_launch_count.restype = C.c_longlong
+    lib.dvo_launch_count.argtypes = [C.c_void_p]
+    lib.dvo_create.argtypes = [C.POINTER(Config), C.POINTER(C.c_void_p)]
+    lib.dvo_destroy.argtypes = [C.c_void_p]
+    lib.dvo_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dvo_synchronize.argtypes = [C.c_void_p]
+    lib.dvo_set_intrinsics.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
+    lib.dvo_set_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.dvo_promote_now_to_ref.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.dvo_build_pyramids.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.dvo_prepare.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.dvo_set_initial_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+    lib.dvo_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SolverParams)]
+    lib.dvo_get_poses.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.dvo_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                    C.POINTER(SolverParams), C.c_void_p, C.c_void_p]
+    lib.dvo_level_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.dvo_get_level_buffer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    lib.dvo_get_points.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+    lib.dvo_eval_normal_equations.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                              C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dvo_get_trace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dvo_enable_timing.argtypes = [C.c_void_p, C.c_int]
+    lib.dvo_get_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dvo_gop_compose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    _lib = lib
+    return lib
+
+
+class DvoError(RuntimeError):
+    pass
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().dvo_last_error().decode(errors="replace")
+        raise DvoError(f"{what} failed ({rc}): {msg}")

@@ -1,0 +1,386 @@
+// capi.cu -- the extern "C" boundary declared in include/dvo_b200.h: context lifetime, device memory arena,
+// host<->device staging and the stage sequencing.  No CPU compute path exists here: every entry point either
+// launches the sm_100a kernels or fails.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void dvo_set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+
+// cv::resize output size: cvRound(dim * 2^-level), round half to even
+static int level_dim(int dim, int level) { return (int)nearbyint((double)dim * ldexp(1.0, -level)); }
+
+namespace {
+struct StageTimer {
+    dvo_ctx* c; int stage; bool on;
+    StageTimer(dvo_ctx* c_, int s) : c(c_), stage(s), on(c_->timing) { if (on) cudaEventRecord(c->ev_a, c->stream); }
+    ~StageTimer() {
+        if (!on) return;
+        cudaEventRecord(c->ev_b, c->stream); cudaEventSynchronize(c->ev_b);
+        float ms = 0.f; cudaEventElapsedTime(&ms, c->ev_a, c->ev_b); c->stage_ms[stage] += ms;
+    }
+};
+template <typename T> int dalloc(T** p, size_t n) {
+    if (n == 0) { *p = nullptr; return DVO_OK; }
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) { dvo_set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e)); return DVO_ERR_NOMEM; }
+    return DVO_OK;
+}
+bool range_ok(dvo_ctx* c, int first, int count) { return c && first >= 0 && count >= 0 && first + count <= c->cfg.max_batch; }
+}  // namespace
+
+extern "C" {
+
+const char* dvo_last_error(void) { return g_err; }
+
+int dvo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
+    if (!cfg || !out) { dvo_set_error("dvo_create: null argument"); return DVO_ERR_ARG; }
+    if (cfg->width < 8 || cfg->height < 8 || cfg->levels < 1 || cfg->levels > DVO_MAX_LEVELS || cfg->max_batch < 1 ||
+        cfg->width >= DVO_EDT_INF_1D || cfg->height >= DVO_EDT_INF_1D) {
+        dvo_set_error("dvo_create: bad config %dx%d levels=%d max_batch=%d", cfg->width, cfg->height, cfg->levels, cfg->max_batch);
+        return DVO_ERR_ARG;
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        dvo_set_error("dvo_create: no usable CUDA device (%s); this library has no CPU fallback", cudaGetErrorString(e));
+        cudaGetLastError();
+        return DVO_ERR_CUDA;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { dvo_set_error("dvo_create: device %d out of range (%d devices)", cfg->device, ndev); return DVO_ERR_ARG; }
+    DVO_CUDA(cudaSetDevice(cfg->device));
+    dvo_ctx* c = new (std::nothrow) dvo_ctx();
+    if (!c) return DVO_ERR_NOMEM;
+    memset(c, 0, sizeof(*c));
+    c->cfg = *cfg;
+    PyrGeom& g = c->geom;
+    g.L = cfg->levels; g.Bmax = cfg->max_batch;
+    long long acc = 0; int maxP = 0;
+    for (int l = 0; l < g.L; ++l) {
+        g.w[l] = level_dim(cfg->width, l); g.h[l] = level_dim(cfg->height, l);
+        if (g.w[l] < 2 || g.h[l] < 2) { dvo_set_error("dvo_create: level %d is %dx%d (too small)", l, g.w[l], g.h[l]); delete c; return DVO_ERR_ARG; }
+        g.P[l] = g.w[l] * g.h[l]; g.off[l] = acc * g.Bmax; acc += g.P[l];
+        if (g.P[l] > maxP) maxP = g.P[l];
+    }
+    g.total = acc * g.Bmax;
+    cudaDeviceProp prop;
+    DVO_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    DVO_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    DVO_CUDA(cudaEventCreate(&c->ev_a));
+    DVO_CUDA(cudaEventCreate(&c->ev_b));
+
+    const size_t T = (size_t)g.total, B = (size_t)g.Bmax;
+    int rc = DVO_OK;
+    auto A = [&](int r) { if (rc == DVO_OK) rc = r; };
+    for (int f = 0; f < 2; ++f) { A(dalloc(&c->gray[f], T)); A(dalloc(&c->edge[f], T)); }
+    A(dalloc(&c->depth[0], T));
+    if (cfg->keep_now_depth) A(dalloc(&c->depth[1], T));
+    A(dalloc(&c->gcol, T)); A(dalloc(&c->d2, T)); A(dalloc(&c->texel, T));
+    A(dalloc(&c->ptsX, T)); A(dalloc(&c->ptsY, T)); A(dalloc(&c->ptsZ, T));
+    A(dalloc(&c->npts, B * g.L)); A(dalloc(&c->nedge, 2 * B * g.L)); A(dalloc(&c->maxd2, B * g.L));
+    A(dalloc(&c->pose0, B * 12)); A(dalloc(&c->pose, B * 12)); A(dalloc(&c->info, B));
+    if (cfg->trace_iters > 0) A(dalloc(&c->trace, B * g.L * cfg->trace_iters * DVO_TRACE_DOUBLES));
+    // hysteresis bitmaps that do not fit in shared memory live in a global scratch (one pair of bitmaps per CTA)
+    {
+        const size_t words = (size_t)2 * (((g.w[0] + 31) >> 5) + 2) * (g.h[0] + 2);
+        if (words * 4 + 1024 > c->smem_optin) { c->bitmap_scratch_words = words; A(dalloc(&c->bitmap_scratch, words * B)); }
+    }
+    if (rc != DVO_OK) { dvo_destroy(c); return rc; }
+    DVO_CUDA(cudaMemsetAsync(c->npts, 0, sizeof(int) * B * g.L, c->stream));
+    DVO_CUDA(cudaMemsetAsync(c->nedge, 0, sizeof(unsigned) * 2 * B * g.L, c->stream));
+    DVO_CUDA(cudaMemsetAsync(c->maxd2, 0, sizeof(unsigned) * B * g.L, c->stream));
+    DVO_CUDA(cudaMemsetAsync(c->info, 0, sizeof(dvo_pair_info) * B, c->stream));
+    DVO_CUDA(cudaMallocHost((void**)&c->h_pose, sizeof(double) * 12 * B));
+    DVO_CUDA(cudaMallocHost((void**)&c->h_info, sizeof(dvo_pair_info) * B));
+    dvo_set_initial_pose(c, 0, g.Bmax, nullptr, DVO_MEM_HOST);
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c;
+    return DVO_OK;
+}
+
+int dvo_destroy(dvo_ctx* c) {
+    if (!c) return DVO_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    for (int f = 0; f < 2; ++f) { cudaFree(c->gray[f]); cudaFree(c->depth[f]); cudaFree(c->edge[f]); }
+    cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ);
+    cudaFree(c->npts); cudaFree(c->nedge); cudaFree(c->maxd2); cudaFree(c->pose0); cudaFree(c->pose); cudaFree(c->info);
+    cudaFree(c->trace); cudaFree(c->bitmap_scratch);
+    if (c->h_pose) cudaFreeHost(c->h_pose);
+    if (c->h_info) cudaFreeHost(c->h_info);
+    if (c->ev_a) cudaEventDestroy(c->ev_a);
+    if (c->ev_b) cudaEventDestroy(c->ev_b);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return DVO_OK;
+}
+
+int dvo_set_stream(dvo_ctx* c, void* s) {
+    if (!c) return DVO_ERR_ARG;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return DVO_OK;
+}
+
+int dvo_synchronize(dvo_ctx* c) {
+    if (!c) return DVO_ERR_ARG;
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    return DVO_OK;
+}
+
+int dvo_set_intrinsics(dvo_ctx* c, float fx, float fy, float cx, float cy) {
+    if (!c) return DVO_ERR_ARG;
+    c->K.fx = fx; c->K.fy = fy; c->K.cx = cx; c->K.cy = cy; c->haveK = true;
+    return DVO_OK;
+}
+
+int dvo_set_frames(dvo_ctx* c, int frame, int first, int count, const uint8_t* gray, const uint16_t* depth, int mem) {
+    if (!range_ok(c, first, count) || (frame != DVO_FRAME_REF && frame != DVO_FRAME_NOW) || !gray) { dvo_set_error("dvo_set_frames: bad argument"); return DVO_ERR_ARG; }
+    if (frame == DVO_FRAME_REF && !depth) { dvo_set_error("dvo_set_frames: the reference frame needs depth"); return DVO_ERR_ARG; }
+    StageTimer t(c, DVO_STAGE_H2D);
+    const size_t P0 = c->geom.P[0];
+    const cudaMemcpyKind k = mem == DVO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    DVO_CUDA(cudaMemcpyAsync(c->gray[frame] + lvl_at(c->geom, 0, first), gray, P0 * count, k, c->stream));
+    if (depth && c->depth[frame])
+        DVO_CUDA(cudaMemcpyAsync(c->depth[frame] + lvl_at(c->geom, 0, first), depth, P0 * count * sizeof(uint16_t), k, c->stream));
+    return DVO_OK;
+}
+
+int dvo_promote_now_to_ref(dvo_ctx* c, int first, int count) {
+    if (!range_ok(c, first, count)) return DVO_ERR_ARG;
+    return launch_promote(c, first, count);
+}
+
+int dvo_build_pyramids(dvo_ctx* c, int first, int count, int frames_mask) {
+    if (!range_ok(c, first, count)) { dvo_set_error("dvo_build_pyramids: bad range"); return DVO_ERR_ARG; }
+    if (count == 0) return DVO_OK;
+    StageTimer t(c, DVO_STAGE_PYRAMID);
+    return launch_pyramid(c, first, count, frames_mask);
+}
+
+int dvo_prepare(dvo_ctx* c, int first, int count, int frames_mask) {
+    if (!range_ok(c, first, count)) { dvo_set_error("dvo_prepare: bad range"); return DVO_ERR_ARG; }
+    if (!c->haveK) { dvo_set_error("dvo_prepare: intrinsics not set (SolveDVO asserts isCameraIntrinsicsAvailable)"); return DVO_ERR_STATE; }
+    if (count == 0) return DVO_OK;
+    int rc;
+    { StageTimer t(c, DVO_STAGE_CANNY); rc = launch_canny(c, first, count, frames_mask); if (rc) return rc; }
+    if (frames_mask & 2) {
+        { StageTimer t(c, DVO_STAGE_EDT_ROWS); rc = launch_edt_rows(c, first, count); if (rc) return rc; }
+        { StageTimer t(c, DVO_STAGE_NORMGRAD); rc = launch_normgrad(c, first, count); if (rc) return rc; }
+    }
+    return DVO_OK;
+}
+
+int dvo_set_initial_pose(dvo_ctx* c, int first, int count, const double* R9T3, int mem) {
+    if (!range_ok(c, first, count)) return DVO_ERR_ARG;
+    if (R9T3) {
+        DVO_CUDA(cudaMemcpyAsync(c->pose0 + 12 * (size_t)first, R9T3, sizeof(double) * 12 * count,
+                                 mem == DVO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+        if (mem != DVO_MEM_DEVICE) DVO_CUDA(cudaStreamSynchronize(c->stream));
+    } else {
+        std::vector<double> id((size_t)12 * count, 0.0);
+        for (int i = 0; i < count; ++i) { id[12 * (size_t)i] = 1.0; id[12 * (size_t)i + 4] = 1.0; id[12 * (size_t)i + 8] = 1.0; }
+        DVO_CUDA(cudaMemcpyAsync(c->pose0 + 12 * (size_t)first, id.data(), sizeof(double) * 12 * count, cudaMemcpyHostToDevice, c->stream));
+        DVO_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return DVO_OK;
+}
+
+int dvo_run(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
+    if (!range_ok(c, first, count) || !p) { dvo_set_error("dvo_run: bad argument"); return DVO_ERR_ARG; }
+    if (!c->haveK) { dvo_set_error("dvo_run: intrinsics not set"); return DVO_ERR_STATE; }
+    if (count == 0) return DVO_OK;
+    StageTimer t(c, DVO_STAGE_SOLVE);
+    return launch_solve(c, first, count, p);
+}
+
+int dvo_get_poses(dvo_ctx* c, int first, int count, double* R9T3, dvo_pair_info* info, int mem) {
+    if (!range_ok(c, first, count)) return DVO_ERR_ARG;
+    StageTimer t(c, DVO_STAGE_D2H);
+    const cudaMemcpyKind k = mem == DVO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (R9T3) DVO_CUDA(cudaMemcpyAsync(R9T3, c->pose + 12 * (size_t)first, sizeof(double) * 12 * count, k, c->stream));
+    if (info) DVO_CUDA(cudaMemcpyAsync(info, c->info + first, sizeof(dvo_pair_info) * count, k, c->stream));
+    if (mem != DVO_MEM_DEVICE) DVO_CUDA(cudaStreamSynchronize(c->stream));
+    return DVO_OK;
+}
+
+int dvo_align_batch(dvo_ctx* c, int count, const uint8_t* ref_gray, const uint16_t* ref_depth, const uint8_t* now_gray,
+                    const uint16_t* now_depth, const dvo_solver_params* p, double* R9T3, dvo_pair_info* info) {
+    if (!c || count < 0 || !ref_gray || !ref_depth || !now_gray || !p) { dvo_set_error("dvo_align_batch: bad argument"); return DVO_ERR_ARG; }
+    const size_t P0 = c->geom.P[0];
+    const int B = c->cfg.max_batch;
+    for (int done = 0; done < count; done += B) {
+        const int n = (count - done < B) ? count - done : B;
+        int rc;
+        if ((rc = dvo_set_frames(c, DVO_FRAME_REF, 0, n, ref_gray + P0 * done, ref_depth + P0 * done, DVO_MEM_HOST))) return rc;
+        if ((rc = dvo_set_frames(c, DVO_FRAME_NOW, 0, n, now_gray + P0 * done, now_depth ? now_depth + P0 * done : nullptr, DVO_MEM_HOST))) return rc;
+        if ((rc = dvo_set_initial_pose(c, 0, n, nullptr, DVO_MEM_HOST))) return rc;
+        if ((rc = dvo_build_pyramids(c, 0, n, 3))) return rc;
+        if ((rc = dvo_prepare(c, 0, n, 3))) return rc;
+        if ((rc = dvo_run(c, 0, n, p))) return rc;
+        if ((rc = dvo_get_poses(c, 0, n, R9T3 ? R9T3 + 12 * (size_t)done : nullptr, info ? info + done : nullptr, DVO_MEM_HOST))) return rc;
+    }
+    return DVO_OK;
+}
+
+int dvo_level_dims(dvo_ctx* c, int level, int* w, int* h) {
+    if (!c || level < 0 || level >= c->geom.L) return DVO_ERR_ARG;
+    if (w) *w = c->geom.w[level];
+    if (h) *h = c->geom.h[level];
+    return DVO_OK;
+}
+
+int dvo_get_level_buffer(dvo_ctx* c, int slot, int frame, int level, int which, void* dst, size_t bytes) {
+    if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || (frame != 0 && frame != 1) || !dst) { dvo_set_error("dvo_get_level_buffer: bad argument"); return DVO_ERR_ARG; }
+    const size_t P = c->geom.P[level];
+    const long long o = lvl_at(c->geom, level, slot);
+    const void* src = nullptr; size_t es = 0;
+    switch (which) {
+        case DVO_BUF_GRAY: src = c->gray[frame] + o; es = 1; break;
+        case DVO_BUF_DEPTH: if (!c->depth[frame]) { dvo_set_error("depth not stored for this frame"); return DVO_ERR_STATE; } src = c->depth[frame] + o; es = 2; break;
+        case DVO_BUF_EDGE: src = c->edge[frame] + o; es = 1; break;
+        case DVO_BUF_D2: if (frame != DVO_FRAME_NOW) { dvo_set_error("d2 exists for the now frame only"); return DVO_ERR_ARG; } src = c->d2 + o; es = 4; break;
+        case DVO_BUF_DTN: case DVO_BUF_GX: case DVO_BUF_GY:
+            if (frame != DVO_FRAME_NOW) { dvo_set_error("DT exists for the now frame only"); return DVO_ERR_ARG; } src = c->texel + o; es = 16; break;
+        default: dvo_set_error("dvo_get_level_buffer: unknown buffer %d", which); return DVO_ERR_ARG;
+    }
+    if (which >= DVO_BUF_DTN) {
+        if (bytes < P * 4) { dvo_set_error("dvo_get_level_buffer: destination too small"); return DVO_ERR_ARG; }
+        std::vector<float> tmp(P * 4);
+        DVO_CUDA(cudaMemcpyAsync(tmp.data(), src, P * 16, cudaMemcpyDeviceToHost, c->stream));
+        DVO_CUDA(cudaStreamSynchronize(c->stream));
+        const int comp = which - DVO_BUF_DTN;
+        float* d = (float*)dst;
+        for (size_t i = 0; i < P; ++i) d[i] = tmp[4 * i + comp];
+        return DVO_OK;
+    }
+    if (bytes < P * es) { dvo_set_error("dvo_get_level_buffer: destination too small"); return DVO_ERR_ARG; }
+    DVO_CUDA(cudaMemcpyAsync(dst, src, P * es, cudaMemcpyDeviceToHost, c->stream));
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    if (which == DVO_BUF_DEPTH && level == 0) {            // level-0 zero fix is applied at read-out (see preprocess.cu)
+        uint16_t* d = (uint16_t*)dst;
+        for (size_t i = 0; i < P; ++i) if (d[i] == 0) d[i] = 1;
+    }
+    return DVO_OK;
+}
+
+int dvo_get_points(dvo_ctx* c, int slot, int level, float* X, float* Y, float* Z, int capacity, int* n) {
+    if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !n) return DVO_ERR_ARG;
+    int cnt = 0;
+    DVO_CUDA(cudaMemcpyAsync(&cnt, c->npts + (size_t)slot * c->geom.L + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    *n = cnt;
+    const int m = cnt < capacity ? cnt : capacity;
+    const long long o = lvl_at(c->geom, level, slot);
+    if (m > 0) {
+        if (X) DVO_CUDA(cudaMemcpyAsync(X, c->ptsX + o, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+        if (Y) DVO_CUDA(cudaMemcpyAsync(Y, c->ptsY + o, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+        if (Z) DVO_CUDA(cudaMemcpyAsync(Z, c->ptsZ + o, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+        DVO_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    return DVO_OK;
+}
+
+int dvo_eval_normal_equations(dvo_ctx* c, int slot, int level, const double* R9T3, int jacobian, int weight, int arithmetic,
+                              float huber_k, double* H36, double* g6, double* sumsq, int* nvis, float* eps, float* w, float* u,
+                              float* v, float* J) {
+    if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !R9T3) return DVO_ERR_ARG;
+    if (!c->haveK) { dvo_set_error("intrinsics not set"); return DVO_ERR_STATE; }
+    int N = 0;
+    DVO_CUDA(cudaMemcpyAsync(&N, c->npts + (size_t)slot * c->geom.L + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    double* d_pose = nullptr; double* d_out = nullptr; float* d_pp = nullptr;
+    DVO_CUDA(cudaMalloc((void**)&d_pose, sizeof(double) * 12));
+    DVO_CUDA(cudaMalloc((void**)&d_out, sizeof(double) * 44));
+    const bool pp = eps || w || u || v || J;
+    const size_t n1 = (size_t)(N > 0 ? N : 1);
+    if (pp) DVO_CUDA(cudaMalloc((void**)&d_pp, sizeof(float) * n1 * 10));
+    DVO_CUDA(cudaMemcpyAsync(d_pose, R9T3, sizeof(double) * 12, cudaMemcpyHostToDevice, c->stream));
+    float *de = nullptr, *dw = nullptr, *du = nullptr, *dv = nullptr, *dJ = nullptr;
+    if (pp) { de = d_pp; dw = d_pp + n1; du = d_pp + 2 * n1; dv = d_pp + 3 * n1; dJ = d_pp + 4 * n1; }
+    int rc = launch_eval(c, slot, level, d_pose, jacobian, weight, arithmetic, huber_k, d_out, de, dw, du, dv, dJ);
+    if (rc == DVO_OK) {
+        double out[44];
+        cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(out), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && pp && N > 0) {
+            if (eps) cudaMemcpyAsync(eps, de, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
+            if (w) cudaMemcpyAsync(w, dw, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
+            if (u) cudaMemcpyAsync(u, du, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
+            if (v) cudaMemcpyAsync(v, dv, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
+            if (J) cudaMemcpyAsync(J, dJ, sizeof(float) * 6 * N, cudaMemcpyDeviceToHost, c->stream);
+        }
+        e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { dvo_set_error("dvo_eval_normal_equations: %s", cudaGetErrorString(e)); rc = DVO_ERR_CUDA; }
+        else {
+            if (g6) memcpy(g6, out, sizeof(double) * 6);
+            if (H36) memcpy(H36, out + 6, sizeof(double) * 36);
+            if (sumsq) *sumsq = out[42];
+            if (nvis) *nvis = (int)out[43];
+        }
+    }
+    cudaFree(d_pose); cudaFree(d_out); cudaFree(d_pp);
+    return rc;
+}
+
+int dvo_get_trace(dvo_ctx* c, int slot, int level, double* trace) {
+    if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !trace) return DVO_ERR_ARG;
+    if (!c->trace) { dvo_set_error("dvo_get_trace: context created with trace_iters = 0"); return DVO_ERR_STATE; }
+    const size_t n = (size_t)c->cfg.trace_iters * DVO_TRACE_DOUBLES;
+    DVO_CUDA(cudaMemcpyAsync(trace, c->trace + ((size_t)slot * c->geom.L + level) * n, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    return DVO_OK;
+}
+
+int dvo_enable_timing(dvo_ctx* c, int on) {
+    if (!c) return DVO_ERR_ARG;
+    c->timing = on != 0;
+    for (int i = 0; i < DVO_STAGE_COUNT; ++i) c->stage_ms[i] = 0.f;
+    return DVO_OK;
+}
+
+int dvo_get_stage_ms(dvo_ctx* c, float* ms) {
+    if (!c || !ms) return DVO_ERR_ARG;
+    for (int i = 0; i < DVO_STAGE_COUNT; ++i) { ms[i] = c->stage_ms[i]; c->stage_ms[i] = 0.f; }
+    return DVO_OK;
+}
+
+long long dvo_launch_count(dvo_ctx* c) { return c ? c->launches : 0; }
+
+int dvo_gop_compose(dvo_ctx* c, int nseq, int nframes, const int* kind, const double* rel, double* out, int mem) {
+    if (!c || nseq < 1 || nframes < 1 || !kind || !rel || !out) return DVO_ERR_ARG;
+    const size_t n = (size_t)nseq * nframes;
+    if (mem == DVO_MEM_DEVICE) return launch_gop(c, nseq, nframes, kind, rel, out);
+    int* d_kind = nullptr; double* d_rel = nullptr; double* d_out = nullptr;
+    DVO_CUDA(cudaMalloc((void**)&d_kind, sizeof(int) * n));
+    DVO_CUDA(cudaMalloc((void**)&d_rel, sizeof(double) * 12 * n));
+    DVO_CUDA(cudaMalloc((void**)&d_out, sizeof(double) * 19 * n));
+    DVO_CUDA(cudaMemcpyAsync(d_kind, kind, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    DVO_CUDA(cudaMemcpyAsync(d_rel, rel, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, c->stream));
+    int rc = launch_gop(c, nseq, nframes, d_kind, d_rel, d_out);
+    if (rc == DVO_OK) {
+        cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * 19 * n, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { dvo_set_error("dvo_gop_compose: %s", cudaGetErrorString(e)); rc = DVO_ERR_CUDA; }
+    }
+    cudaFree(d_kind); cudaFree(d_rel); cudaFree(d_out);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// common.cuh -- context layout, geometry helpers and arithmetic policies shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dvo_b200.h"
+
+#define DVO_EDT_INF_1D 16384             // "no edge pixel in this column" (larger than any image dimension)
+#define DVO_EDT_INF (1 << 28)            // DVO_EDT_INF_1D squared: d2 of an image without edges
+
+// Pyramid geometry.  Every per-level device array uses the same layout: level-major, then slot, then the
+// level's row-major pixels:   element(l, b, i) = base[ off[l] + b * P[l] + i ],  off[l] = Bmax * sum_{k<l} P[k].
+struct PyrGeom {
+    int L, Bmax;
+    int w[DVO_MAX_LEVELS], h[DVO_MAX_LEVELS], P[DVO_MAX_LEVELS];
+    long long off[DVO_MAX_LEVELS];
+    long long total;
+};
+__host__ __device__ inline long long lvl_at(const PyrGeom& g, int l, int b) { return g.off[l] + (long long)b * g.P[l]; }
+
+struct Intr { float fx, fy, cx, cy; };
+
+// One trace record per executed iteration: g[6], H[36], energy, nvis, R[9], T[3].
+#define DVO_TRACE_DOUBLES 56
+
+struct dvo_ctx {
+    dvo_config cfg;
+    PyrGeom geom;
+    Intr K;
+    bool haveK;
+    cudaStream_t own_stream, stream;
+    int sm_count;
+    size_t smem_optin;
+
+    uint8_t* gray[2];        // [frame] gray pyramid
+    uint16_t* depth[2];      // [frame] depth pyramid (now: only if keep_now_depth)
+    uint8_t* edge[2];        // [frame] Canny edge maps 0/255
+    uint16_t* gcol;          // now: EDT phase-1 column distances
+    int32_t* d2;             // now: exact squared distance
+    float4* texel;           // now: {DTn, gx, gy, 0}
+    float *ptsX, *ptsY, *ptsZ;   // ref: back-projected edge points, capacity P[l] per slot and level
+    int* npts;               // [Bmax][L]
+    unsigned* nedge;         // [2][Bmax][L]
+    unsigned* maxd2;         // [Bmax][L]
+    double* pose0;           // [Bmax][12]
+    double* pose;            // [Bmax][12]
+    dvo_pair_info* info;     // [Bmax]
+    double* trace;           // [Bmax][L][trace_iters][56] or null
+    uint32_t* bitmap_scratch;    // hysteresis bitmaps for images too large for shared memory, or null
+    size_t bitmap_scratch_words; // per CTA
+
+    // host staging for dvo_align_batch / dvo_get_poses
+    double* h_pose;          // pinned [Bmax][12]
+    dvo_pair_info* h_info;   // pinned [Bmax]
+
+    bool timing;
+    cudaEvent_t ev_a, ev_b;
+    float stage_ms[DVO_STAGE_COUNT];
+    long long launches;
+};
+
+void dvo_set_error(const char* fmt, ...);
+
+#define DVO_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            dvo_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return DVO_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// ---- stage launchers (each defined next to its kernels) ----
+int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask);
+int launch_canny(dvo_ctx* c, int first, int count, int frames_mask);
+int launch_edt_rows(dvo_ctx* c, int first, int count);
+int launch_normgrad(dvo_ctx* c, int first, int count);
+int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p);
+int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k,
+                double* d_out /* 6 + 36 + 1 + 1 doubles */, float* d_eps, float* d_w, float* d_u, float* d_v, float* d_J);
+int launch_gop(dvo_ctx* c, int nseq, int nframes, const int* d_kind, const double* d_rel, double* d_out);
+int launch_promote(dvo_ctx* c, int first, int count);
+
+// ---- arithmetic policies for the per-point fp32 math ----
+// EXACT: one IEEE rounding per written operation, never contracted -> bit-identical to the oracle compiled with
+// -ffp-contract=off.  FAST: plain expressions (nvcc contracts to FFMA) and approximate reciprocals.
+template <int ARITH> struct Ar;
+template <> struct Ar<DVO_ARITH_EXACT> {
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    // a*b + c*d and (a*b + c*d) + e*f in the oracle's order
+    static __device__ __forceinline__ float dot2(float a, float b, float c, float d) { return __fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+    static __device__ __forceinline__ float dot3(float a, float b, float c, float d, float e, float f) {
+        return __fadd_rn(__fadd_rn(__fmul_rn(a, b), __fmul_rn(c, d)), __fmul_rn(e, f));
+    }
+    static __device__ __forceinline__ float diff2(float a, float b, float c, float d) { return __fsub_rn(__fmul_rn(a, b), __fmul_rn(c, d)); }
+    // getWeightOf: 6.0 / (6.0 + (double)(r*r) / .25)
+    static __device__ __forceinline__ float weight_ref(float r) {
+        float rr = __fmul_rn(r, r);
+        return __double2float_rn(__ddiv_rn(6.0, __dadd_rn(6.0, __dmul_rn((double)rr, 4.0))));
+    }
+};
+template <> struct Ar<DVO_ARITH_FAST> {
+    static __device__ __forceinline__ float mul(float a, float b) { return a * b; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdividef(a, b); }
+    static __device__ __forceinline__ float dot2(float a, float b, float c, float d) { return fmaf(c, d, a * b); }
+    static __device__ __forceinline__ float dot3(float a, float b, float c, float d, float e, float f) { return fmaf(e, f, fmaf(c, d, a * b)); }
+    static __device__ __forceinline__ float diff2(float a, float b, float c, float d) { return fmaf(a, b, -(c * d)); }
+    static __device__ __forceinline__ float weight_ref(float r) { return __fdividef(1.5f, fmaf(r, r, 1.5f)); }
+};

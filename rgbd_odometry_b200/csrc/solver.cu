@@ -1,0 +1,522 @@
+// solver.cu -- the batched coarse-to-fine edge-alignment solve: one persistent CTA per frame pair runs every
+// level and iteration on the device (warp, gather, Jacobian, weights, fp64 reduction to g = J^T W eps and
+// H = J^T W J, the 6-vector step / 6x6 solve, SE(3) update, best-iterate tracking, termination) with no host
+// round trip.  Follows SolveDVO::runIterations (src/SolveDVO.cpp:619-1017), computeJacobianOfNowFrame
+// (:306-414) and getReprojectedEpsilons (:425-462); see SURVEY.md Appendix A for the restated arithmetic.
+#include "common.cuh"
+
+namespace {
+
+constexpr int SOLVE_THREADS = 256;
+constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
+
+// ------------------------------------------------------------------ fp64 3x3 / SE(3) helpers (device)
+__device__ __forceinline__ void m3_mul(const double* A, const double* B, double* C) {
+    double r[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) r[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) C[i] = r[i];
+}
+__device__ __forceinline__ void m3_vec(const double* A, const double* v, double* o) {
+    const double a = A[0] * v[0] + A[1] * v[1] + A[2] * v[2];
+    const double b = A[3] * v[0] + A[4] * v[1] + A[5] * v[2];
+    const double c = A[6] * v[0] + A[7] * v[1] + A[8] * v[2];
+    o[0] = a; o[1] = b; o[2] = c;
+}
+
+// SE(3) exponential, tangent = (upsilon, omega), translation first (Sophus::SE3d::exp, src/SolveDVO.cpp:905).
+__device__ __noinline__ void se3_exp_dev(const double* psi, double* R, double* t) {
+    const double wx = psi[3], wy = psi[4], wz = psi[5];
+    const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
+    double A, B, C;
+    if (th < 1e-5) { A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; C = 1.0 / 6.0 - th2 / 120.0; }
+    else { const double s = sin(th), c = cos(th); A = s / th; B = (1.0 - c) / th2; C = (th - s) / (th2 * th); }
+    const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
+    double O2[9]; m3_mul(O, O, O2);
+    double V[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double I = (i % 4 == 0) ? 1.0 : 0.0;
+        R[i] = I + A * O[i] + B * O2[i];
+        V[i] = I + B * O[i] + C * O2[i];
+    }
+    m3_vec(V, psi, t);
+}
+
+// rotation matrix -> unit quaternion (x,y,z,w), Shepperd's branches
+__device__ __forceinline__ void rot_to_quat_dev(const double* R, double* q) {
+    const double tr = R[0] + R[4] + R[8];
+    if (tr > 0) {
+        double s = sqrt(tr + 1.0); q[3] = 0.5 * s; s = 0.5 / s;
+        q[0] = (R[7] - R[5]) * s; q[1] = (R[2] - R[6]) * s; q[2] = (R[3] - R[1]) * s;
+    } else {
+        int i = 0; if (R[4] > R[0]) i = 1; if (R[8] > R[4 * i]) i = 2;
+        const int j = (i + 1) % 3, k = (j + 1) % 3;
+        double s = sqrt(R[4 * i] - R[4 * j] - R[4 * k] + 1.0);
+        q[i] = 0.5 * s; s = 0.5 / s;
+        q[3] = (R[3 * k + j] - R[3 * j + k]) * s;
+        q[j] = (R[3 * j + i] + R[3 * i + j]) * s;
+        q[k] = (R[3 * k + i] + R[3 * i + k]) * s;
+    }
+}
+
+// SE(3) logarithm (Sophus::SE3d::log of setRotationMatrix(cR), translation cT; src/SolveDVO.cpp:736-739)
+__device__ __noinline__ void se3_log_dev(const double* R, const double* t, double* psi) {
+    double q[4]; rot_to_quat_dev(R, q);
+    const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    double sgn = (q[3] < 0 ? -1.0 : 1.0) / qn;
+    const double x = q[0] * sgn, y = q[1] * sgn, z = q[2] * sgn, w = q[3] * sgn;
+    const double n2 = x * x + y * y + z * z, n = sqrt(n2);
+    const double k = (n < 1e-10) ? (2.0 / w - 2.0 * n2 / (3.0 * w * w * w)) : (2.0 * atan2(n, w) / n);
+    const double ox = k * x, oy = k * y, oz = k * z;
+    const double th2 = ox * ox + oy * oy + oz * oz, th = sqrt(th2);
+    const double O[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
+    double O2[9]; m3_mul(O, O, O2);
+    const double D = (th < 1e-5) ? (1.0 / 12.0 + th2 / 720.0) : ((1.0 - th * sin(th) / (2.0 * (1.0 - cos(th)))) / th2);
+    double Vi[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Vi[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * O[i] + D * O2[i];
+    m3_vec(Vi, t, psi);
+    psi[3] = ox; psi[4] = oy; psi[5] = oz;
+}
+
+// SolveDVO::rotationize (src/SolveDVO.cpp:1269-1282) returns U V^T of the SVD, i.e. the orthogonal polar factor.
+// Computed here by Newton's iteration X <- (X + X^-T)/2, which converges quadratically; the input is within
+// ~1e-15 of a rotation on every call the solver makes, so one or two steps suffice.
+__device__ __noinline__ void rotationize_dev(double* R) {
+    for (int it = 0; it < 40; ++it) {
+        const double c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
+        const double c10 = R[2] * R[7] - R[1] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[1] * R[6] - R[0] * R[7];
+        const double c20 = R[1] * R[5] - R[2] * R[4], c21 = R[2] * R[3] - R[0] * R[5], c22 = R[0] * R[4] - R[1] * R[3];
+        const double det = R[0] * c00 + R[1] * c01 + R[2] * c02;
+        if (fabs(det) < 1e-300) break;
+        const double id = 1.0 / det;
+        const double Xit[9] = {c00 * id, c01 * id, c02 * id, c10 * id, c11 * id, c12 * id, c20 * id, c21 * id, c22 * id};   // X^-T
+        double delta = 0.0;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) { const double nv = 0.5 * (R[i] + Xit[i]); delta = fmax(delta, fabs(nv - R[i])); R[i] = nv; }
+        if (delta < 4e-16) break;
+    }
+}
+
+// 6x6 SPD solve by Cholesky; reads the upper triangle of H (row-major).  Returns false if not positive definite.
+__device__ __noinline__ bool chol6_dev(const double* H, const double* b, double* x) {
+    double Lm[36];
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) {
+            double s = H[6 * j + i];
+            for (int k = 0; k < j; ++k) s -= Lm[6 * i + k] * Lm[6 * j + k];
+            if (i == j) { if (!(s > 0)) return false; Lm[6 * i + i] = sqrt(s); }
+            else Lm[6 * i + j] = s / Lm[6 * j + j];
+        }
+    double y[6];
+    for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= Lm[6 * i + k] * y[k]; y[i] = s / Lm[6 * i + i]; }
+    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= Lm[6 * k + i] * x[k]; x[i] = s / Lm[6 * i + i]; }
+    return true;
+}
+
+// ------------------------------------------------------------------ per-point evaluation
+struct PoseF { float R[9], T[3]; };
+struct LevelCam { float M00, M02, M11, M12; int w, h; };
+
+// Returns false when the reprojection falls outside the now image (J = eps = w = 0, src/SolveDVO.cpp:371-374).
+template <int ARITH, int JAC>
+__device__ __forceinline__ bool eval_point(float Xp, float Yp, float Zp, const PoseF& P, const LevelCam& cam,
+                                           const float4* __restrict__ tex, int weight_mode, float huber_k, float* Jr,
+                                           float& e, float& wgt, float& u, float& v) {
+    typedef Ar<ARITH> A;
+    typedef Ar<DVO_ARITH_EXACT> E;   // the reprojection is always IEEE-exact so that FAST gathers the same texel
+    const float* R = P.R;
+    // p' = cR^T (P - cT)                                                       (:330)
+    const float d0 = E::sub(Xp, P.T[0]), d1 = E::sub(Yp, P.T[1]), d2 = E::sub(Zp, P.T[2]);
+    const float px = E::dot3(R[0], d0, R[3], d1, R[6], d2);
+    const float py = E::dot3(R[1], d0, R[4], d1, R[7], d2);
+    const float pz = E::dot3(R[2], d0, R[5], d1, R[8], d2);
+    const float inv = E::div(1.0f, pz);                                          // :339
+    const float X = E::mul(px, inv), Y = E::mul(py, inv), Z = E::mul(pz, inv);   // :340-341
+    u = E::dot2(cam.M00, X, cam.M02, Z);                                         // :344
+    v = E::dot2(cam.M11, Y, cam.M12, Z);
+    if (!(u >= 0.0f && u < (float)cam.w && v >= 0.0f && v < (float)cam.h)) return false;
+    const int xx = __float2int_rz(u), yy = __float2int_rz(v);                    // :376-377
+    const float4 t = __ldg(tex + yy * cam.w + xx);                               // {DTn, gx, gy, 0}
+    const float G0 = t.y, G1 = t.z;
+    if (JAC == DVO_JAC_REFERENCE) {
+        const float ZZ = A::mul(Z, Z);
+        const float A00 = A::div(cam.M00, Z), A02 = -A::div(A::mul(cam.M00, X), ZZ);     // :388-390
+        const float A11 = A::div(cam.M11, Z), A12 = -A::div(A::mul(cam.M11, Y), ZZ);     // :392-393
+        const float w0 = A::dot3(R[0], X, R[3], Y, R[6], Z);                             // :399
+        const float w1 = A::dot3(R[1], X, R[4], Y, R[7], Z);
+        const float w2 = A::dot3(R[2], X, R[5], Y, R[8], Z);
+        const float a = A::mul(G0, A00), b = A::mul(G1, A11), c = A::dot2(G0, A02, G1, A12);
+        Jr[0] = -A::dot3(a, R[0], b, R[1], c, R[2]);                                     // :397-405
+        Jr[1] = -A::dot3(a, R[3], b, R[4], c, R[5]);
+        Jr[2] = -A::dot3(a, R[6], b, R[7], c, R[8]);
+        Jr[3] = A::diff2(b, w2, c, w1);
+        Jr[4] = A::diff2(c, w0, a, w2);
+        Jr[5] = A::diff2(a, w1, b, w0);
+    } else {
+        const float a = A::mul(A::mul(G0, cam.M00), inv), b = A::mul(A::mul(G1, cam.M11), inv);
+        const float c = -A::mul(A::dot2(a, px, b, py), inv);
+        Jr[0] = -a; Jr[1] = -b; Jr[2] = -c;
+        Jr[3] = A::diff2(b, pz, c, py);
+        Jr[4] = A::diff2(c, px, a, pz);
+        Jr[5] = A::diff2(a, py, b, px);
+    }
+    e = t.x;                                                                     // :446
+    if (weight_mode == DVO_WEIGHT_REF_CAUCHY) wgt = A::weight_ref(e);            // :450, :1051
+    else if (weight_mode == DVO_WEIGHT_HUBER) { const float ae = fabsf(e); wgt = ae <= huber_k ? 1.0f : A::div(huber_k, ae); }
+    else wgt = 1.0f;
+    return true;
+}
+
+// Accumulator layout: [0..5] g, [6] sum eps^2, [7] sum eps, then (NEED_H) 21 upper-triangle entries of H row by row.
+template <bool NEED_H> struct AccN { static constexpr int N = NEED_H ? 29 : 8; };
+
+template <int ARITH, int JAC, bool NEED_H>
+__device__ __forceinline__ void accumulate_points(const float* __restrict__ X, const float* __restrict__ Y,
+                                                  const float* __restrict__ Z, int N, const PoseF& P, const LevelCam& cam,
+                                                  const float4* __restrict__ tex, int weight_mode, float huber_k,
+                                                  double* acc, int& nvis, float* o_eps, float* o_w, float* o_u, float* o_v,
+                                                  float* o_J) {
+    typedef Ar<ARITH> A;
+    for (int i = threadIdx.x; i < N; i += SOLVE_THREADS) {
+        float Jr[6], e = 0.f, wgt = 0.f, u, v;
+        const bool vis = eval_point<ARITH, JAC>(__ldg(X + i), __ldg(Y + i), __ldg(Z + i), P, cam, tex, weight_mode, huber_k, Jr, e, wgt, u, v);
+        if (o_u) { o_u[i] = u; o_v[i] = v; }
+        if (vis) {
+            ++nvis;
+            const double de = (double)e;
+            acc[6] = fma(de, de, acc[6]);
+            acc[7] += de;
+            double Jw[6];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) { Jw[k] = (double)A::mul(Jr[k], wgt); acc[k] = fma(Jw[k], de, acc[k]); }   // :714-720, :777
+            if (NEED_H) {
+                int idx = 8;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int c = r; c < 6; ++c) { acc[idx] = fma(Jw[r], (double)Jr[c], acc[idx]); ++idx; }
+            }
+        } else { e = 0.f; wgt = 0.f;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Jr[k] = 0.f; }
+        if (o_eps) { o_eps[i] = e; o_w[i] = wgt; }
+        if (o_J) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) o_J[6 * i + k] = Jr[k]; }
+    }
+}
+
+// Deterministic block reduction: fixed shuffle tree inside each warp, then warp partials summed in warp order.
+template <int NACC>
+__device__ __forceinline__ void block_reduce(double* acc, int nvis, double (*s_red)[NACC], int* s_nv, double* s_tot, int* s_nvtot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][k] = v;
+    }
+    for (int o = 16; o > 0; o >>= 1) nvis += __shfl_down_sync(0xffffffffu, nvis, o);
+    if (lane == 0) s_nv[warp] = nvis;
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double v = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < SOLVE_WARPS; ++wv) v += s_red[wv][threadIdx.x];
+        s_tot[threadIdx.x] = v;
+    }
+    if (threadIdx.x == 32) { int n = 0; for (int wv = 0; wv < SOLVE_WARPS; ++wv) n += s_nv[wv]; *s_nvtot = n; }
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------ solver state (thread 0, in shared memory)
+struct SolverState {
+    double cR[9], cT[3], bestR[9], bestT[3], descent[6];
+    double accR[9], accT[3], accH[36], accg[6];
+    double lambda, bestSumEps;
+    float accE, bestE, bestRatio;
+    int have_acc, bestItr;
+};
+
+struct SolveArgs {
+    PyrGeom geom; Intr K;
+    const float *X, *Y, *Z; const int* npts; const unsigned* nedge_now; const float4* texel;
+    const double* pose0; double* pose; dvo_pair_info* info; double* trace; int trace_iters;
+    dvo_solver_params prm; int first;
+};
+
+// One iteration's serial tail (thread 0): best tracking, step computation, pose update.  Returns 1 to stop the level.
+__device__ __noinline__ int solver_step(SolverState& S, const double* tot, int nvis, int N, int itr, const dvo_solver_params& prm,
+                                        bool need_h, dvo_pair_info* info, int level, double* trace_rec) {
+    const float ratio = (float)nvis / (float)N;                                   // :457
+    const float energy = (float)sqrt(tot[6]);                                      // :1310-1312
+    info->iterations_run[level] = itr + 1;
+    double Hf[36];
+    if (need_h) {
+        int idx = 8;
+        for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { Hf[6 * r + c] = tot[idx]; Hf[6 * c + r] = tot[idx]; ++idx; }
+    } else { for (int k = 0; k < 36; ++k) Hf[k] = 0.0; }
+    if (trace_rec) {
+        for (int k = 0; k < 6; ++k) trace_rec[k] = tot[k];
+        for (int k = 0; k < 36; ++k) trace_rec[6 + k] = Hf[k];
+        trace_rec[42] = energy; trace_rec[43] = nvis;
+        for (int k = 0; k < 9; ++k) trace_rec[44 + k] = S.cR[k];
+        for (int k = 0; k < 3; ++k) trace_rec[53 + k] = S.cT[k];
+    }
+    if (energy <= S.bestE) {                                                      // :696-705
+        S.bestE = energy; S.bestRatio = ratio; S.bestItr = itr; S.bestSumEps = tot[7];
+        for (int k = 0; k < 9; ++k) S.bestR[k] = S.cR[k];
+        for (int k = 0; k < 3; ++k) S.bestT[k] = S.cT[k];
+    }
+    double psi[6];
+    if (prm.solver == DVO_SOLVER_SUBGRAD_REF) {
+        double g[6]; for (int k = 0; k < 6; ++k) g[k] = tot[k];
+        double cPsi[6]; se3_log_dev(S.cR, S.cT, cPsi);                            // :736-739
+        double cn = 0; for (int k = 0; k < 6; ++k) cn += cPsi[k] * cPsi[k]; cn = sqrt(cn);
+        if (cn > 0) for (int k = 0; k < 6; ++k) cPsi[k] = cPsi[k] / cn;           // :740-741
+        const double stepLength = 9.0 * 1.0E-2 / ((itr > 5) ? (double)(itr - 4) : 1.0);   // :773
+        for (int k = 0; k < 6; ++k) g[k] += 0.05 * cPsi[k];                       // :796
+        for (int k = 0; k < 6; ++k) S.descent[k] = 0.5 * g[k] + 0.5 * S.descent[k];      // :799
+        const double Pv[6] = {1.0, 1.0, 1.0, 0.5, 0.5, 0.5};                      // :729
+        double nrm = 0;
+        for (int k = 0; k < 6; ++k) { psi[k] = -stepLength * Pv[k] * S.descent[k]; nrm += psi[k] * psi[k]; }   // :821
+        nrm = sqrt(nrm);
+        const double radius = (double)0.003f;                                     // :25, :835
+        if (nrm > radius) { for (int k = 0; k < 6; ++k) psi[k] = psi[k] / nrm * radius; }
+        else if (nrm < (double)1.0E-7f) return 1;                                 // :840 -> :872
+    } else {
+        const bool accept = (prm.solver == DVO_SOLVER_GN) || !S.have_acc || (energy <= S.accE);
+        if (accept) {
+            for (int k = 0; k < 9; ++k) S.accR[k] = S.cR[k];
+            for (int k = 0; k < 3; ++k) S.accT[k] = S.cT[k];
+            for (int k = 0; k < 36; ++k) S.accH[k] = Hf[k];
+            for (int k = 0; k < 6; ++k) S.accg[k] = tot[k];
+            S.accE = energy;
+            if (prm.solver == DVO_SOLVER_LM && S.have_acc) S.lambda = (S.lambda * 0.1 < 1e-9) ? 1e-9 : S.lambda * 0.1;
+            S.have_acc = 1;
+        } else {
+            S.lambda *= 10.0;
+            if (S.lambda > 1e8) return 1;
+            for (int k = 0; k < 9; ++k) S.cR[k] = S.accR[k];
+            for (int k = 0; k < 3; ++k) S.cT[k] = S.accT[k];
+        }
+        double Am[36], nb[6];
+        for (int k = 0; k < 36; ++k) Am[k] = S.accH[k];
+        const double lam = (prm.solver == DVO_SOLVER_LM) ? S.lambda : 0.0;
+        for (int k = 0; k < 6; ++k) { Am[7 * k] += lam * S.accH[7 * k] + 1e-9; nb[k] = -S.accg[k]; }
+        if (!chol6_dev(Am, nb, psi)) return 1;
+        double n2 = 0; for (int k = 0; k < 6; ++k) n2 += psi[k] * psi[k];
+        if (sqrt(n2) < (double)1.0E-7f) return 1;
+    }
+    double xR[9], xt[3], Rt[3];
+    se3_exp_dev(psi, xR, xt);                                                     // :905-907
+    m3_vec(S.cR, xt, Rt);
+    S.cT[0] += Rt[0]; S.cT[1] += Rt[1]; S.cT[2] += Rt[2];                         // :916
+    m3_mul(S.cR, xR, S.cR);                                                       // :917
+    rotationize_dev(S.cR);                                                        // :919
+    return 0;
+}
+
+template <int ARITH, int JAC, bool NEED_H>
+__global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(SolveArgs a) {
+    constexpr int NACC = AccN<NEED_H>::N;
+    __shared__ double s_red[SOLVE_WARPS][NACC];
+    __shared__ double s_tot[NACC];
+    __shared__ int s_nv[SOLVE_WARPS];
+    __shared__ int s_nvtot, s_stop;
+    __shared__ PoseF s_pose;
+    __shared__ SolverState S;
+    __shared__ dvo_pair_info s_info;
+
+    const int b = a.first + blockIdx.x;
+    const int L = a.geom.L;
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 9; ++k) S.cR[k] = a.pose0[12 * (long long)b + k];
+        for (int k = 0; k < 3; ++k) S.cT[k] = a.pose0[12 * (long long)b + 9 + k];
+        s_info.status = 0; s_info.laplacian_b = 0.f;
+        for (int l = 0; l < DVO_MAX_LEVELS; ++l) {
+            s_info.npts[l] = (l < L) ? a.npts[(long long)b * L + l] : 0; s_info.best_index[l] = -1; s_info.iterations_run[l] = 0;
+            s_info.best_energy[l] = 0.f; s_info.visible_ratio[l] = 0.f;
+        }
+    }
+    __syncthreads();
+
+    for (int l = L - 1; l >= 0; --l) {
+        const int iters = a.prm.iters[l];
+        if (iters <= 0) continue;
+        const int N = a.npts[(long long)b * L + l];
+        const unsigned ne = a.nedge_now[(long long)b * L + l];
+        if (N <= 0 || ne == 0u) { if (threadIdx.x == 0) s_info.status |= 1; continue; }      // reference asserts (:282)
+        const long long base = lvl_at(a.geom, l, b);
+        const float* X = a.X + base; const float* Y = a.Y + base; const float* Z = a.Z + base;
+        const float4* tex = a.texel + base;
+        LevelCam cam;
+        const float scaleFac = (float)ldexp(1.0, -l);                                       // :334
+        cam.M00 = __fmul_rn(scaleFac, a.K.fx); cam.M02 = __fmul_rn(scaleFac, a.K.cx);         // scaleMatrix * K (:344)
+        cam.M11 = __fmul_rn(scaleFac, a.K.fy); cam.M12 = __fmul_rn(scaleFac, a.K.cy);
+        cam.w = a.geom.w[l]; cam.h = a.geom.h[l];
+        if (threadIdx.x == 0) {
+            S.bestE = 1.0E10f; S.bestRatio = 1.0f; S.bestItr = -1; S.bestSumEps = 0.0;        // :642-650
+            for (int k = 0; k < 9; ++k) S.bestR[k] = (k % 4 == 0) ? 1.0 : 0.0;
+            for (int k = 0; k < 3; ++k) S.bestT[k] = 0.0;
+            for (int k = 0; k < 6; ++k) S.descent[k] = 0.0;                                   // :654
+            S.have_acc = 0; S.lambda = a.prm.lm_lambda0; S.accE = 0.f;
+        }
+        for (int itr = 0; itr < iters; ++itr) {
+            if (threadIdx.x == 0) {
+                for (int k = 0; k < 9; ++k) s_pose.R[k] = (float)S.cR[k];                      // :673-674
+                for (int k = 0; k < 3; ++k) s_pose.T[k] = (float)S.cT[k];
+            }
+            __syncthreads();
+            PoseF P = s_pose;
+            double acc[NACC];
+#pragma unroll
+            for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+            int nvis = 0;
+            accumulate_points<ARITH, JAC, NEED_H>(X, Y, Z, N, P, cam, tex, a.prm.weight, a.prm.huber_k, acc, nvis,
+                                                  nullptr, nullptr, nullptr, nullptr, nullptr);
+            block_reduce<NACC>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
+            if (threadIdx.x == 0) {
+                double* tr = nullptr;
+                if (a.trace && itr < a.trace_iters)
+                    tr = a.trace + (((long long)b * L + l) * a.trace_iters + itr) * DVO_TRACE_DOUBLES;
+                s_stop = solver_step(S, s_tot, s_nvtot, N, itr, a.prm, NEED_H, &s_info, l, tr);
+            }
+            __syncthreads();
+            if (s_stop) break;
+        }
+        if (threadIdx.x == 0) {
+            for (int k = 0; k < 9; ++k) S.cR[k] = S.bestR[k];                                  // :997-1001
+            rotationize_dev(S.cR);
+            for (int k = 0; k < 3; ++k) S.cT[k] = S.bestT[k];
+            s_info.best_index[l] = S.bestItr; s_info.best_energy[l] = S.bestE; s_info.visible_ratio[l] = S.bestRatio;
+            s_info.laplacian_b = (float)(S.bestSumEps / (double)N);                            // :1466-1472 at the finest level run
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 9; ++k) a.pose[12 * (long long)b + k] = S.cR[k];
+        for (int k = 0; k < 3; ++k) a.pose[12 * (long long)b + 9 + k] = S.cT[k];
+        a.info[b] = s_info;
+    }
+}
+
+// ------------------------------------------------------------------ single evaluation (parity inspection)
+struct EvalArgs {
+    PyrGeom geom; Intr K;
+    const float *X, *Y, *Z; const int* npts; const float4* texel;
+    const double* pose; int slot, level, weight; float huber_k;
+    double* out;            // g[6], H[36], sumsq, nvis
+    float *eps, *w, *u, *v, *J;
+};
+
+template <int ARITH, int JAC>
+__global__ void __launch_bounds__(SOLVE_THREADS) eval_kernel(EvalArgs a) {
+    constexpr int NACC = AccN<true>::N;
+    __shared__ double s_red[SOLVE_WARPS][NACC];
+    __shared__ double s_tot[NACC];
+    __shared__ int s_nv[SOLVE_WARPS];
+    __shared__ int s_nvtot;
+    const int b = a.slot, l = a.level, L = a.geom.L;
+    const int N = a.npts[(long long)b * L + l];
+    const long long base = lvl_at(a.geom, l, b);
+    PoseF P;
+    for (int k = 0; k < 9; ++k) P.R[k] = (float)a.pose[k];
+    for (int k = 0; k < 3; ++k) P.T[k] = (float)a.pose[9 + k];
+    LevelCam cam;
+    const float scaleFac = (float)ldexp(1.0, -l);
+    cam.M00 = __fmul_rn(scaleFac, a.K.fx); cam.M02 = __fmul_rn(scaleFac, a.K.cx);
+    cam.M11 = __fmul_rn(scaleFac, a.K.fy); cam.M12 = __fmul_rn(scaleFac, a.K.cy);
+    cam.w = a.geom.w[l]; cam.h = a.geom.h[l];
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    int nvis = 0;
+    accumulate_points<ARITH, JAC, true>(a.X + base, a.Y + base, a.Z + base, N, P, cam, a.texel + base, a.weight, a.huber_k,
+                                        acc, nvis, a.eps, a.w, a.u, a.v, a.J);
+    block_reduce<NACC>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 6; ++k) a.out[k] = s_tot[k];
+        int idx = 8;
+        for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { a.out[6 + 6 * r + c] = s_tot[idx]; a.out[6 + 6 * c + r] = s_tot[idx]; ++idx; }
+        a.out[42] = s_tot[6]; a.out[43] = (double)s_nvtot;
+    }
+}
+
+// ------------------------------------------------------------------ GOP composition (src/GOP.cpp:138-196)
+__global__ void gop_kernel(int nseq, int nframes, const int* __restrict__ kind, const double* __restrict__ rel, double* __restrict__ out) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseq) return;
+    double kR[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, kT[3] = {0, 0, 0};
+    for (int f = 0; f < nframes; ++f) {
+        const long long i = (long long)s * nframes + f;
+        const double* r = rel + 12 * i;
+        double gR[9], gT[3], RT[3];
+        m3_vec(kR, r + 9, RT);
+        gT[0] = kT[0] + RT[0]; gT[1] = kT[1] + RT[1]; gT[2] = kT[2] + RT[2];      // :144, :172
+        m3_mul(kR, r, gR);                                                         // :145, :173
+        double* o = out + 19 * i;
+        for (int k = 0; k < 9; ++k) o[k] = gR[k];
+        for (int k = 0; k < 3; ++k) { o[9 + k] = gT[k]; o[12 + k] = gT[k]; }
+        rot_to_quat_dev(gR, o + 15);                                               // :103-114
+        if (kind[i] != 0) { for (int k = 0; k < 9; ++k) kR[k] = gR[k]; for (int k = 0; k < 3; ++k) kT[k] = gT[k]; }   // :184-185, :192-193
+    }
+}
+
+}  // namespace
+
+template <int ARITH, int JAC>
+static void launch_solve_t(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
+    if (need_h) solve_kernel<ARITH, JAC, true><<<count, SOLVE_THREADS, 0, c->stream>>>(a);
+    else solve_kernel<ARITH, JAC, false><<<count, SOLVE_THREADS, 0, c->stream>>>(a);
+}
+
+int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
+    SolveArgs a;
+    a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts;
+    a.nedge_now = c->nedge + (size_t)DVO_FRAME_NOW * c->geom.Bmax * c->geom.L; a.texel = c->texel;
+    a.pose0 = c->pose0; a.pose = c->pose; a.info = c->info; a.trace = c->trace; a.trace_iters = c->cfg.trace_iters;
+    a.prm = *p; a.first = first;
+    // H is needed by GN / LM, and by SUBGRAD_REF only when a trace is kept (parity tests on J^T W J)
+    const bool need_h = (p->solver != DVO_SOLVER_SUBGRAD_REF) || (c->trace != nullptr);
+    if (c->trace) DVO_CUDA(cudaMemsetAsync(c->trace + (size_t)first * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, 0,
+                                           sizeof(double) * (size_t)count * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, c->stream));
+    const int ar = p->arithmetic == DVO_ARITH_FAST ? DVO_ARITH_FAST : DVO_ARITH_EXACT;
+    const int jc = p->jacobian == DVO_JAC_EXACT ? DVO_JAC_EXACT : DVO_JAC_REFERENCE;
+    if (ar == DVO_ARITH_EXACT && jc == DVO_JAC_REFERENCE) launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_REFERENCE>(c, a, count, need_h);
+    else if (ar == DVO_ARITH_EXACT) launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_EXACT>(c, a, count, need_h);
+    else if (jc == DVO_JAC_REFERENCE) launch_solve_t<DVO_ARITH_FAST, DVO_JAC_REFERENCE>(c, a, count, need_h);
+    else launch_solve_t<DVO_ARITH_FAST, DVO_JAC_EXACT>(c, a, count, need_h);
+    c->launches++;
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}
+
+int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k,
+                double* d_out, float* d_eps, float* d_w, float* d_u, float* d_v, float* d_J) {
+    EvalArgs a;
+    a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts; a.texel = c->texel;
+    a.pose = d_pose12; a.slot = slot; a.level = level; a.weight = weight; a.huber_k = huber_k; a.out = d_out;
+    a.eps = d_eps; a.w = d_w; a.u = d_u; a.v = d_v; a.J = d_J;
+    const bool ex = arith != DVO_ARITH_FAST, rj = jac != DVO_JAC_EXACT;
+    if (ex && rj) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_REFERENCE><<<1, SOLVE_THREADS, 0, c->stream>>>(a);
+    else if (ex) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_EXACT><<<1, SOLVE_THREADS, 0, c->stream>>>(a);
+    else if (rj) eval_kernel<DVO_ARITH_FAST, DVO_JAC_REFERENCE><<<1, SOLVE_THREADS, 0, c->stream>>>(a);
+    else eval_kernel<DVO_ARITH_FAST, DVO_JAC_EXACT><<<1, SOLVE_THREADS, 0, c->stream>>>(a);
+    c->launches++;
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}
+
+int launch_gop(dvo_ctx* c, int nseq, int nframes, const int* d_kind, const double* d_rel, double* d_out) {
+    gop_kernel<<<(nseq + 127) / 128, 128, 0, c->stream>>>(nseq, nframes, d_kind, d_rel, d_out);
+    c->launches++;
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}
