@@ -165,7 +165,10 @@ def run_ours(args):
     data = O.synth_batch(rank * B, B, W, H, K, nthreads=nthreads)
     t_synth = time.time() - t0
     al = dvo.BatchAligner(W, H, LEVELS, max_batch=B, device=local, intrinsics=K)
-    stream = torch.cuda.current_stream()
+    # a dedicated non-default stream shared by torch (events, NCCL) and the C-ABI context, so that the CUDA events
+    # below are recorded on the stream the kernels are launched on
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
     al.set_stream(stream.cuda_stream)
     params = dvo.solver_params(solver=code, arithmetic=1 if args.arith == "fast" else 0, iters=iters)
     # inputs resident in HBM (the context's level-0 regions) before any timed region
