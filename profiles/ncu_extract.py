@@ -1,0 +1,33 @@
+"""Summarise an `ncu --page raw --csv` export: one block per kernel launch with the metrics the roofline uses."""
+import csv
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'lts__t_bytes.sum', 'lts__t_sector_hit_rate.pct',
+        'l1tex__t_sector_hit_rate.pct', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'smsp__issue_active.avg.pct', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed.sum', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_tensor.sum', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_warps',
+        'smsp__pcsamp_warps_issue_stalled_long_scoreboard', 'smsp__pcsamp_warps_issue_stalled_barrier',
+        'smsp__pcsamp_warps_issue_stalled_short_scoreboard', 'smsp__pcsamp_warps_issue_stalled_math_pipe_throttle',
+        'smsp__pcsamp_warps_issue_stalled_wait', 'smsp__pcsamp_warps_issue_stalled_not_selected',
+        'smsp__pcsamp_warps_issue_stalled_mio_throttle', 'smsp__pcsamp_warps_issue_stalled_lg_throttle',
+        'smsp__pcsamp_warps_issue_stalled_branch_resolving', 'smsp__pcsamp_warps_issue_stalled_selected',
+        'smsp__pcsamp_warps_issue_stalled_no_instruction', 'smsp__pcsamp_warps_issue_stalled_dispatch_stall']
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    ki = hdr.index('Kernel Name')
+    idx = {w: hdr.index(w) for w in WANT if w in hdr}
+    for r in rows[2:]:
+        print('---', r[ki][:70])
+        for w in WANT:
+            if w in idx:
+                print(f'    {w:70s} {r[idx[w]]:>18s} {units[idx[w]]}')
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
