@@ -100,8 +100,10 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     if (cfg->trace_iters > 0) A(dalloc(&c->trace, B * g.L * cfg->trace_iters * DVO_TRACE_DOUBLES));
     // hysteresis bitmaps that do not fit in shared memory live in a global scratch (one pair of bitmaps per CTA)
     {
-        const size_t words = (size_t)2 * (((g.w[0] + 31) >> 5) + 2) * (g.h[0] + 2);
-        if (words * 4 + 1024 > c->smem_optin) { c->bitmap_scratch_words = words; A(dalloc(&c->bitmap_scratch, words * B)); }
+        const int wd = (g.w[0] + 31) >> 5;
+        size_t wa = (size_t)(wd + 2) * (g.h[0] + 2), wt = (size_t)(wd << 5) * (((g.h[0] + 31) >> 5) | 1);
+        const size_t words = 2 * (wa > wt ? wa : wt);
+        if (words * 4 + 8192 > c->smem_optin) { c->bitmap_scratch_words = words; A(dalloc(&c->bitmap_scratch, words * B)); }
     }
     if (rc != DVO_OK) { dvo_destroy(c); return rc; }
     DVO_CUDA(cudaMemsetAsync(c->npts, 0, sizeof(int) * B * g.L, c->stream));

@@ -49,13 +49,21 @@ int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
 // Canny (cv::Canny(img,150,100,3,true), src/SolveDVO.cpp:1705,1767).
 // One CTA per (slot, frame) image at one level.  Candidate / edge sets live as bitmaps (1 bit per pixel,
 // bit i of word wx <-> x = 32*wx + i) with a one-word / one-row zero border, in shared memory when they fit
-// (640x480: 2 x 42 KB) or in a global scratch otherwise.  Hysteresis is a monotone fixed-point iteration
-// E <- C & dilate3x3(E) from E = strong, whose fixed point is the traversal-order-independent closure the
-// reference computes with a stack -- hence bit-exact.
-// Fused epilogues (the bitmap is already on chip):
-//   now frame: EDT phase 1 -- per-column distance to the nearest edge pixel above/below (u16)
-//   ref frame: selectedPts + enlistRefEdgePts (src/SolveDVO.cpp:1230-1264, 224-264): column-major stable
-//              compaction of edge && depth > 100 pixels, back-projected to 3-D.
+// (640x480: 2 x 42 KB) or in a global scratch otherwise.
+//
+//  phase 1  Sobel + NMS.  Thread <-> image column, rows are swept top to bottom with the 3x3 neighbourhood of
+//           gradient magnitudes kept in registers (separable Sobel: one byte load per pixel); horizontal
+//           neighbours come from warp shuffles, warp-edge lanes exchange through shared memory (one barrier per
+//           row).  `S` row strips run concurrently.  Ballots produce the bitmap words directly.
+//  phase 2  Hysteresis = monotone fixed point E <- C & dilate3x3(E) from E = strong.  Its closure equals the
+//           reference's stack traversal regardless of order, hence bit-exact.  Thread <-> (word column, row
+//           strip): each iteration sweeps the strip down and up so information crosses a whole strip per
+//           iteration; strips whose 3x3 strip neighbourhood did not change are skipped.
+//  phase 3  edge bytes 0/255 (128-bit stores) + edge count.
+//  phase 4  (now) the edge bitmap is transposed (32x32 ballot transposes) so that a column is a bit string, and
+//           every pixel gets its distance to the nearest edge pixel above/below with clz/ffs -- EDT phase 1.
+//           (ref) selected = edge && depth > 100 bitmap, transposed: popcounts + a block scan give the stable
+//           column-major enumeration of selectedPts/enlistRefEdgePts (src/SolveDVO.cpp:1230-1264, 224-264).
 // =====================================================================================================
 struct CannyArgs {
     const uint8_t* gray;   // level region of this frame (slot 0)
@@ -72,6 +80,7 @@ struct CannyArgs {
     long long gscratch_stride;
     int first;
     int low, high;         // squared thresholds (10000, 22500)
+    int bm_words;          // words per bitmap region
 };
 
 __device__ __forceinline__ void sobel3(const uint8_t* __restrict__ g, int w, int h, int y, int x, int& dx, int& dy) {
@@ -89,179 +98,331 @@ __device__ __forceinline__ int mag_at(const uint8_t* __restrict__ g, int w, int 
 
 __device__ __forceinline__ uint32_t expand4(uint32_t nib) { return (((nib & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFFu; }
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) canny_kernel(CannyArgs a) {
+// horizontal Sobel partial sums of one gray row at column x: hs = g(x+1) - g(x-1), hb = g(x-1) + 2 g(x) + g(x+1),
+// BORDER_REPLICATE.  Row index already clamped by the caller.
+__device__ __forceinline__ void row_sums(const uint8_t* __restrict__ grow, int w, int x, int lane, int& hs, int& hb) {
+    const int v = (x < w) ? (int)grow[x] : 0;
+    int l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
+    if (lane == 0) l = (x > 0 && x < w) ? (int)grow[x - 1] : v;
+    if (lane == 31) r = (x + 1 < w) ? (int)grow[x + 1] : v;
+    if (x + 1 >= w) r = v;
+    hs = r - l; hb = l + 2 * v + r;
+}
+
+constexpr int CANNY_MAX_WARPS = 32;
+
+__global__ void __launch_bounds__(1024) canny_kernel(CannyArgs a) {
     extern __shared__ uint32_t smem_u32[];
-    __shared__ int s_scan[THREADS / 32 + 1];
+    __shared__ int s_scan[CANNY_MAX_WARPS + 1];
     __shared__ int s_base;
     __shared__ unsigned s_cnt;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ unsigned char s_chg[2][1024];
+    const int T = blockDim.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = a.first + blockIdx.x;
     const int w = a.w, h = a.h;
-    const int wd = (w + 31) >> 5, pitch = wd + 2, rows = h + 2;
-    const int nwords = pitch * rows;
+    const int wd = (w + 31) >> 5, pitch = wd + 2;
+    const int nwords = a.bm_words;
     uint32_t* C = a.gscratch ? a.gscratch + (long long)blockIdx.x * a.gscratch_stride : smem_u32;
     uint32_t* E = C + nwords;
     const uint8_t* __restrict__ g = a.gray + (long long)b * a.P;
 
-    for (int i = tid; i < 2 * nwords; i += THREADS) C[i] = 0u;
+    for (int i = tid; i < 2 * nwords; i += T) C[i] = 0u;
     if (tid == 0) { s_cnt = 0u; s_base = 0; }
     __syncthreads();
 
-    // ---- phase 1: Sobel + non-maximum suppression, one warp per 32-pixel word ----
-    const int TG22 = 13573;   // (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
-    const int total = h * wd * 32;
-    for (int q = tid; q < total; q += THREADS) {
-        const int y = q / (wd * 32);
-        const int x = q - y * (wd * 32);
-        bool cand = false, strong = false;
-        if (x < w) {
-            int dx, dy; sobel3(g, w, h, y, x, dx, dy);
-            const int m = dx * dx + dy * dy;
-            if (m > a.low) {
-                const int ax = abs(dx), ay = abs(dy) << 15;
-                const int tg22x = ax * TG22;
-                bool keep;
-                if (ay < tg22x) keep = (m > mag_at(g, w, h, y, x - 1)) && (m >= mag_at(g, w, h, y, x + 1));
-                else {
-                    const int tg67x = tg22x + (ax << 16);
-                    if (ay > tg67x) keep = (m > mag_at(g, w, h, y - 1, x)) && (m >= mag_at(g, w, h, y + 1, x));
-                    else { const int s = ((dx ^ dy) < 0) ? -1 : 1; keep = (m > mag_at(g, w, h, y - 1, x - s)) && (m > mag_at(g, w, h, y + 1, x + s)); }
+    // ------------------------------------------------------------------ phase 1: Sobel + NMS
+    // Warp task = (30-column chunk, row strip).  Lane j holds column 30*chunk + j - 1, so lanes 1..30 produce output
+    // and lanes 0 / 31 are halo columns (they load one extra gray value each); warps never synchronise with each
+    // other.  Rows are swept top to bottom: one (prefetched) byte load per pixel, separable Sobel row sums, the 3x3
+    // magnitude neighbourhood in registers, horizontal neighbours by shuffle.  Ballots are merged into the 32-bit
+    // aligned bitmap words with shared-memory atomicOr.
+    {
+        const int TG22 = 13573;   // (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
+        const int nchunk = (w + 29) / 30;
+        const int nwarps = T >> 5;
+        const int S = max(1, nwarps / nchunk);
+        const int R = (h + S - 1) / S;
+        const bool halo = (lane == 0 || lane == 31);
+        for (int task = warp; task < nchunk * S; task += nwarps) {
+            const int k = task % nchunk, st = task / nchunk;
+            const int y0 = st * R, y1 = min(h, y0 + R);
+            if (y0 >= y1) continue;                                   // warp-uniform
+            const int x = 30 * k + lane - 1;
+            const bool incol = (x >= 0 && x < w);
+            const int xc = min(max(x, 0), w - 1);                     // BORDER_REPLICATE
+            const int xe = min(max(lane == 0 ? x - 1 : x + 1, 0), w - 1);
+            auto loadrow = [&](int r, int& v, int& ve) {
+                const uint8_t* __restrict__ p = g + min(max(r, 0), h - 1) * w;
+                v = p[xc]; ve = halo ? (int)p[xe] : 0;
+            };
+            auto sums = [&](int v, int ve, int& hs, int& hb) {
+                int l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
+                if (lane == 0) l = ve;
+                if (lane == 31) r = ve;
+                hs = r - l; hb = l + 2 * v + r;
+            };
+            int hsA, hbA, hsB, hbB, hsC, hbC, v, ve, vn, ven;
+            int mPL, mPC, mPR, mCL, mCC, mCR, dxC, dyC;
+            loadrow(y0 - 2, v, ve); sums(v, ve, hsA, hbA);
+            loadrow(y0 - 1, v, ve); sums(v, ve, hsB, hbB);
+            loadrow(y0, v, ve); sums(v, ve, hsC, hbC);
+            {   // magnitude row y0-1 (zero outside the image)
+                const int dx = hsA + 2 * hsB + hsC, dy = hbC - hbA;
+                mPC = (incol && y0 - 1 >= 0) ? dx * dx + dy * dy : 0;
+                mPL = __shfl_up_sync(0xffffffffu, mPC, 1); mPR = __shfl_down_sync(0xffffffffu, mPC, 1);
+            }
+            hsA = hsB; hbA = hbB; hsB = hsC; hbB = hbC;
+            loadrow(y0 + 1, v, ve); sums(v, ve, hsC, hbC);
+            {   // magnitude row y0
+                dxC = hsA + 2 * hsB + hsC; dyC = hbC - hbA;
+                mCC = incol ? dxC * dxC + dyC * dyC : 0;
+                mCL = __shfl_up_sync(0xffffffffu, mCC, 1); mCR = __shfl_down_sync(0xffffffffu, mCC, 1);
+            }
+            loadrow(y0 + 2, vn, ven);                                 // prefetched one row ahead
+            for (int y = y0; y < y1; ++y) {
+                v = vn; ve = ven;
+                loadrow(y + 3, vn, ven);
+                hsA = hsB; hbA = hbB; hsB = hsC; hbB = hbC;
+                sums(v, ve, hsC, hbC);                                // gray row y+2
+                const int dxN = hsA + 2 * hsB + hsC, dyN = hbC - hbA; // gradient at row y+1
+                const int mNC = (incol && y + 1 < h) ? dxN * dxN + dyN * dyN : 0;
+                const int mNL = __shfl_up_sync(0xffffffffu, mNC, 1), mNR = __shfl_down_sync(0xffffffffu, mNC, 1);
+                bool cand = false, strong = false;
+                const int m = mCC;
+                if (m > a.low && !halo) {                             // m == 0 outside the image
+                    const int ax = abs(dxC), ay = abs(dyC) << 15;
+                    const int tg22x = ax * TG22;
+                    bool keep;
+                    if (ay < tg22x) keep = (m > mCL) && (m >= mCR);
+                    else {
+                        const int tg67x = tg22x + (ax << 16);
+                        if (ay > tg67x) keep = (m > mPC) && (m >= mNC);
+                        else { const bool neg = ((dxC ^ dyC) < 0); keep = (m > (neg ? mPR : mPL)) && (m > (neg ? mNL : mNR)); }
+                    }
+                    cand = keep; strong = keep && (m > a.high);
                 }
-                cand = keep; strong = keep && (m > a.high);
+                const uint32_t cb = __ballot_sync(0xffffffffu, cand), sb = __ballot_sync(0xffffffffu, strong);
+                if (lane < 2) {                                       // lane 0 merges candidates, lane 1 the strong set
+                    const uint32_t bits = ((lane == 0 ? cb : sb) >> 1) & 0x3fffffffu;
+                    if (bits) {
+                        const int c0 = 30 * k, sh = c0 & 31;
+                        uint32_t* Bm = (lane == 0 ? C : E) + (y + 1) * pitch + (c0 >> 5) + 1;
+                        atomicOr(Bm, bits << sh);
+                        if (sh > 2) { const uint32_t hi = bits >> (32 - sh); if (hi) atomicOr(Bm + 1, hi); }
+                    }
+                }
+                mPL = mCL; mPC = mCC; mPR = mCR; mCL = mNL; mCC = mNC; mCR = mNR; dxC = dxN; dyC = dyN;
             }
         }
-        const uint32_t cw = __ballot_sync(0xffffffffu, cand), sw = __ballot_sync(0xffffffffu, strong);
-        if (lane == 0) { const int idx = (y + 1) * pitch + (x >> 5) + 1; C[idx] = cw; E[idx] = sw; }
     }
     __syncthreads();
 
-    // ---- phase 2: hysteresis closure ----
-    const int nw = h * wd;
-    for (;;) {
-        int changed = 0;
-        for (int q = tid; q < nw; q += THREADS) {
-            const int y = q / wd, wx = q - y * wd;
-            const int idx = (y + 1) * pitch + wx + 1;
-            const uint32_t c = C[idx];
-            if (c == 0u) continue;
-            const uint32_t e = E[idx];
-            if (e == c) continue;
-            uint32_t n = 0u;
-#pragma unroll
-            for (int dy = -1; dy <= 1; ++dy) {
-                const int j = idx + dy * pitch;
-                const uint32_t ec = E[j], el = E[j - 1], er = E[j + 1];
-                n |= ec | (ec << 1) | (ec >> 1) | (el >> 31) | (er << 31);
+    // ------------------------------------------------------------------ phase 2: hysteresis closure
+    {
+        const int Hs = max(1, min(h, min(T, 1024) / wd));   // row strips
+        const int Rh = (h + Hs - 1) / Hs;
+        const int items = wd * Hs;
+        const int sh = tid / wd, wx = tid - sh * wd;
+        const bool owner = tid < items;
+        const int ya = sh * Rh, yb = min(h, ya + Rh);
+        for (int i = tid; i < 2 * 1024; i += T) (&s_chg[0][0])[i] = (i < 1024) ? 1 : 0;   // everything active at first
+        __syncthreads();
+        int cur = 0;
+        for (;;) {
+            int changed = 0;
+            bool active = false;
+            if (owner && ya < yb) {
+                for (int dsy = -1; dsy <= 1 && !active; ++dsy)
+                    for (int dwx = -1; dwx <= 1; ++dwx) {
+                        const int s2 = sh + dsy, w2 = wx + dwx;
+                        if (s2 >= 0 && s2 < Hs && w2 >= 0 && w2 < wd && s_chg[cur][s2 * wd + w2]) { active = true; break; }
+                    }
             }
-            uint32_t f = e | (c & n);
-            for (;;) { const uint32_t f2 = f | (c & ((f << 1) | (f >> 1))); if (f2 == f) break; f = f2; }
-            if (f != e) { E[idx] = f; changed = 1; }
+            if (active) {
+                auto visit = [&](int y) {
+                    const int idx = (y + 1) * pitch + wx + 1;
+                    const uint32_t c = C[idx];
+                    if (c == 0u) return;
+                    const uint32_t e = E[idx];
+                    if (e == c) return;
+                    uint32_t n = 0u;
+#pragma unroll
+                    for (int dy = -1; dy <= 1; ++dy) {
+                        const int j = idx + dy * pitch;
+                        const uint32_t ec = E[j], el = E[j - 1], er = E[j + 1];
+                        n |= ec | (ec << 1) | (ec >> 1) | (el >> 31) | (er << 31);
+                    }
+                    uint32_t f = e | (c & n);
+                    for (;;) { const uint32_t f2 = f | (c & ((f << 1) | (f >> 1))); if (f2 == f) break; f = f2; }
+                    if (f != e) { E[idx] = f; changed = 1; }
+                };
+                for (int y = ya; y < yb; ++y) visit(y);
+                for (int y = yb - 2; y >= ya; --y) visit(y);
+            }
+            if (owner) s_chg[cur ^ 1][tid] = (unsigned char)changed;
+            cur ^= 1;
+            if (!__syncthreads_or(changed)) break;
         }
-        if (!__syncthreads_or(changed)) break;
     }
 
-    // ---- phase 3a: edge bytes (0/255) + edge count ----
-    uint8_t* eo = a.edge + (long long)b * a.P;
-    unsigned cnt = 0;
-    const bool vec_ok = (w % 16 == 0) && ((reinterpret_cast<uintptr_t>(eo) & 15) == 0);
-    for (int q = tid; q < nw; q += THREADS) {
-        const int y = q / wd, wx = q - y * wd;
-        const uint32_t e = E[(y + 1) * pitch + wx + 1];
-        cnt += __popc(e);
-        const int x0 = wx << 5;
-        if (vec_ok && x0 + 32 <= w) {
-            uint4 v0, v1;
-            v0.x = expand4(e); v0.y = expand4(e >> 4); v0.z = expand4(e >> 8); v0.w = expand4(e >> 12);
-            v1.x = expand4(e >> 16); v1.y = expand4(e >> 20); v1.z = expand4(e >> 24); v1.w = expand4(e >> 28);
-            uint4* dst = reinterpret_cast<uint4*>(eo + (long long)y * w + x0);
-            dst[0] = v0; dst[1] = v1;
-        } else {
-            for (int i = 0; i < 32 && x0 + i < w; ++i) eo[(long long)y * w + x0 + i] = ((e >> i) & 1u) ? 255 : 0;
+    // ------------------------------------------------------------------ phase 3: edge bytes (0/255) + edge count
+    const int nw = h * wd;
+    {
+        uint8_t* eo = a.edge + (long long)b * a.P;
+        unsigned cnt = 0;
+        const bool vec_ok = (w % 16 == 0) && ((reinterpret_cast<uintptr_t>(eo) & 15) == 0);
+        for (int q = tid; q < nw; q += T) {
+            const int y = q / wd, wx = q - y * wd;
+            const uint32_t e = E[(y + 1) * pitch + wx + 1];
+            cnt += __popc(e);
+            const int x0 = wx << 5;
+            if (vec_ok && x0 + 32 <= w) {
+                uint4 v0, v1;
+                v0.x = expand4(e); v0.y = expand4(e >> 4); v0.z = expand4(e >> 8); v0.w = expand4(e >> 12);
+                v1.x = expand4(e >> 16); v1.y = expand4(e >> 20); v1.z = expand4(e >> 24); v1.w = expand4(e >> 28);
+                uint4* dst = reinterpret_cast<uint4*>(eo + (long long)y * w + x0);
+                dst[0] = v0; dst[1] = v1;
+            } else {
+                for (int i = 0; i < 32 && x0 + i < w; ++i) eo[(long long)y * w + x0 + i] = ((e >> i) & 1u) ? 255 : 0;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
+        if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+    }
+
+    // ------------------------------------------------------------------ phase 4 (ref): selected = edge && depth > 100, in place
+    if (a.do_points) {
+        const uint16_t* __restrict__ dep = a.depth + (long long)b * a.P;
+        for (int q = tid; q < nw; q += T) {
+            const int y = q / wd, wx = q - y * wd;
+            const int idx = (y + 1) * pitch + wx + 1;
+            uint32_t e = E[idx], sel = 0u;
+            while (e) {
+                const int i = __ffs(e) - 1; e &= e - 1;
+                if (dep[(long long)y * w + (wx << 5) + i] > 100) sel |= (1u << i);
+            }
+            E[idx] = sel;
         }
     }
-    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_down_sync(0xffffffffu, cnt, o);
-    if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
     __syncthreads();
     if (tid == 0) a.nedge[(long long)b * a.L] = s_cnt;
 
-    // ---- phase 3b (now): EDT phase 1, per-column distance to the nearest edge pixel ----
+    // ------------------------------------------------------------------ transpose E -> Et (into C's storage): Et[x * hwp + (y >> 5)], bit y & 31
+    const int hw = (h + 31) >> 5, hwp = hw | 1;
+    uint32_t* Et = C;
+    {
+        const int nwarps = T >> 5;
+        for (int blk = warp; blk < hw * wd; blk += nwarps) {
+            const int wy = blk / wd, wx = blk - wy * wd;
+            const int y = (wy << 5) + lane;
+            const uint32_t word = (y < h) ? E[(y + 1) * pitch + wx + 1] : 0u;
+            uint32_t mine = 0u;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { const uint32_t bt = __ballot_sync(0xffffffffu, (word >> j) & 1u); if (lane == j) mine = bt; }
+            Et[((wx << 5) + lane) * hwp + wy] = mine;
+        }
+    }
+    __syncthreads();
+
+    // ------------------------------------------------------------------ phase 4 (now): EDT phase 1 from the column bit strings
+    // thread <-> column; per 32-row word the nearest edge above / below comes from clz / ffs on the masked word, with
+    // carries (last edge row above the word, first edge row below it) tracked incrementally.
     if (a.do_cols) {
         uint16_t* gc = a.gcol + (long long)b * a.P;
-        for (int x = tid; x < w; x += THREADS) {
-            const int wi = (x >> 5) + 1, sh = x & 31;
-            int d = DVO_EDT_INF_1D;
-            for (int y = 0; y < h; ++y) {
-                const uint32_t bit = (E[(y + 1) * pitch + wi] >> sh) & 1u;
-                d = bit ? 0 : min(d + 1, DVO_EDT_INF_1D);
-                gc[(long long)y * w + x] = (uint16_t)d;
-            }
-            d = DVO_EDT_INF_1D;
-            for (int y = h - 1; y >= 0; --y) {
-                const uint32_t bit = (E[(y + 1) * pitch + wi] >> sh) & 1u;
-                d = bit ? 0 : min(d + 1, DVO_EDT_INF_1D);
-                const int prev = gc[(long long)y * w + x];
-                if (d < prev) gc[(long long)y * w + x] = (uint16_t)d;
+        const int BIG = 1 << 20;
+        for (int x = tid; x < w; x += T) {
+            const uint32_t* col = Et + x * hwp;
+            int lastrow = -BIG;                 // last edge row in words < wy
+            int nextrow = -1;                   // first edge row in words > wy (valid while >= 32*(wy+1)), BIG if none
+            for (int wy = 0; wy < hw; ++wy) {
+                const uint32_t Wd = col[wy];
+                const int base = wy << 5;
+                if (nextrow < base + 32) {      // recompute (amortised: each word is scanned once)
+                    nextrow = BIG;
+                    for (int kk = wy + 1; kk < hw; ++kk) { const uint32_t vv = col[kk]; if (vv) { nextrow = (kk << 5) + __ffs(vv) - 1; break; } }
+                }
+                uint16_t* o = gc + (long long)base * w + x;
+#pragma unroll
+                for (int bt = 0; bt < 32; ++bt) {
+                    if (base + bt < h) {
+                        const uint32_t mle = Wd & (0xffffffffu >> (31 - bt));
+                        const uint32_t mge = Wd & (0xffffffffu << bt);
+                        const int dn = mle ? bt - (31 - __clz(mle)) : base + bt - lastrow;
+                        const int up = mge ? (__ffs(mge) - 1) - bt : nextrow - (base + bt);
+                        o[(long long)bt * w] = (uint16_t)min(min(dn, up), DVO_EDT_INF_1D);
+                    }
+                }
+                if (Wd) lastrow = base + 31 - __clz(Wd);
             }
         }
     }
 
-    // ---- phase 3c (ref): column-major stable compaction + back-projection ----
+    // ------------------------------------------------------------------ phase 4 (ref): column-major stable compaction + back-projection
     if (a.do_points) {
         const uint16_t* __restrict__ dep = a.depth + (long long)b * a.P;
         float* X = a.X + (long long)b * a.P; float* Y = a.Y + (long long)b * a.P; float* Z = a.Z + (long long)b * a.P;
-        for (int x0 = 0; x0 < w; x0 += THREADS) {
+        for (int x0 = 0; x0 < w; x0 += T) {
             const int x = x0 + tid;
             int mycnt = 0;
-            int wi = 0, sh = 0;
-            if (x < w) {
-                wi = (x >> 5) + 1; sh = x & 31;
-                for (int y = 0; y < h; ++y)
-                    if ((E[(y + 1) * pitch + wi] >> sh) & 1u) mycnt += (dep[(long long)y * w + x] > 100) ? 1 : 0;
-            }
-            // block exclusive scan of mycnt
+            if (x < w) for (int k = 0; k < hw; ++k) mycnt += __popc(Et[x * hwp + k]);
             int incl = mycnt;
-            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (lane == 31) s_scan[tid >> 5] = incl;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+            if (lane == 31) s_scan[warp] = incl;
             __syncthreads();
             if (tid < 32) {
-                int v = (tid < THREADS / 32) ? s_scan[tid] : 0;
+                const int nwp = T >> 5;
+                const int v = (tid < nwp) ? s_scan[tid] : 0;
                 int iv = v;
-                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
-                if (tid < THREADS / 32) s_scan[tid] = iv - v;       // exclusive warp offsets
-                if (tid == 31) s_scan[THREADS / 32] = iv;            // chunk total
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+                if (tid < nwp) s_scan[tid] = iv - v;               // exclusive warp offsets
+                if (tid == 31) s_scan[CANNY_MAX_WARPS] = iv;       // chunk total
             }
             __syncthreads();
-            int off = s_base + s_scan[tid >> 5] + (incl - mycnt);
+            int off = s_base + s_scan[warp] + (incl - mycnt);
             if (x < w && mycnt) {
-                for (int y = 0; y < h; ++y)
-                    if ((E[(y + 1) * pitch + wi] >> sh) & 1u) {
+                for (int k = 0; k < hw; ++k) {
+                    uint32_t v = Et[x * hwp + k];
+                    while (v) {
+                        const int y = (k << 5) + __ffs(v) - 1; v &= v - 1;
                         const float d = (float)dep[(long long)y * w + x];
-                        if (d > 100.0f) {
-                            const float z = __fdiv_rn(d, 1000.0f);                                      // :248
-                            X[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)x, a.tmpcx)), a.tmpfx);      // :249
-                            Y[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)y, a.tmpcy)), a.tmpfy);      // :250
-                            Z[off] = z;
-                            ++off;
-                        }
+                        const float z = __fdiv_rn(d, 1000.0f);                                          // :248
+                        X[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)x, a.tmpcx)), a.tmpfx);          // :249
+                        Y[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)y, a.tmpcy)), a.tmpfy);          // :250
+                        Z[off] = z;
+                        ++off;
                     }
+                }
             }
             __syncthreads();
-            if (tid == 0) s_base += s_scan[THREADS / 32];
+            if (tid == 0) s_base += s_scan[CANNY_MAX_WARPS];
             __syncthreads();
         }
         if (tid == 0) a.npts[(long long)b * a.L] = s_base;
     }
 }
 
-static size_t canny_smem_bytes(int w, int h) { return (size_t)2 * (((w + 31) >> 5) + 2) * (h + 2) * sizeof(uint32_t); }
+static int canny_bitmap_words(int w, int h) {
+    const int wd = (w + 31) >> 5;
+    const int a = (wd + 2) * (h + 2);
+    const int t = (wd << 5) * (((h + 31) >> 5) | 1);       // transposed layout reuses the candidate bitmap's storage
+    return a > t ? a : t;
+}
 
 int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
     const PyrGeom& g = c->geom;
     for (int l = 0; l < g.L; ++l) {
-        const size_t smem = canny_smem_bytes(g.w[l], g.h[l]);
-        const bool use_global = smem + 1024 > c->smem_optin;
-        if (use_global && !c->bitmap_scratch) { dvo_set_error("canny: bitmap scratch missing for %dx%d", g.w[l], g.h[l]); return DVO_ERR_STATE; }
+        const int words = canny_bitmap_words(g.w[l], g.h[l]);
+        const size_t smem = (size_t)2 * words * sizeof(uint32_t);
+        const bool use_global = smem + 8192 > c->smem_optin;
+        if (use_global && (!c->bitmap_scratch || (size_t)2 * words > c->bitmap_scratch_words)) {
+            dvo_set_error("canny: bitmap scratch missing for %dx%d", g.w[l], g.h[l]); return DVO_ERR_STATE;
+        }
+        // warps = (30-column chunks) x (row strips), 16..32 warps per CTA
+        const int nchunk = (g.w[l] + 29) / 30;
+        int S = 24 / nchunk; if (S < 1) S = 1;
+        int warps = nchunk * S; if (warps > 32) warps = 32; if (warps < 4) warps = 4;
+        const int T = warps * 32;
         for (int f = 0; f < 2; ++f) {
             if (!(frames_mask & (1 << f))) continue;
             CannyArgs a;
@@ -279,17 +440,10 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
             a.tmpcx = scaleFac * c->K.cx; a.tmpcy = scaleFac * c->K.cy;                    // :234-235
             a.gscratch = use_global ? c->bitmap_scratch : nullptr;
             a.gscratch_stride = (long long)c->bitmap_scratch_words;
-            a.first = first; a.low = 10000; a.high = 22500;
+            a.first = first; a.low = 10000; a.high = 22500; a.bm_words = words;
             const size_t dyn = use_global ? 0 : smem;
-            if (g.P[l] >= 64 * 1024) {
-                if (dyn > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(canny_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                canny_kernel<512><<<count, 512, dyn, c->stream>>>(a);
-            } else if (g.P[l] >= 8 * 1024) {
-                if (dyn > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(canny_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                canny_kernel<256><<<count, 256, dyn, c->stream>>>(a);
-            } else {
-                canny_kernel<128><<<count, 128, dyn, c->stream>>>(a);
-            }
+            if (dyn > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(canny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+            canny_kernel<<<count, T, dyn, c->stream>>>(a);
             c->launches++;
         }
     }
@@ -310,6 +464,9 @@ struct EdtArgs {
     int w, h, P, L, first;
 };
 
+// Shared memory per warp: g (u16, column distance), arg (u16, leftmost argmin), dv (i32, result).
+// Every search window is additionally clipped to |x - x'| <= g(x): the candidate x' = x already gives g(x)^2, so
+// no argmin can lie farther away.  With dense edge maps this makes every search a handful of evaluations.
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a) {
     extern __shared__ int smem_i32[];
@@ -318,11 +475,12 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a) {
     const int row = blockIdx.x * WARPS + warp;
     const int b = a.first + blockIdx.y;
     if (row >= a.h) return;                      // whole warp exits together; only __syncwarp below
-    int* g2 = smem_i32 + (size_t)warp * (3 * w);
-    int* dv = g2 + w;
-    int* arg = dv + w;
+    const int wp = (w + 1) & ~1;                 // even number of u16 per array
+    int* dv = smem_i32 + (size_t)warp * (w + wp);
+    unsigned short* gs = reinterpret_cast<unsigned short*>(dv + w);
+    unsigned short* arg = gs + wp;
     const uint16_t* __restrict__ gr = a.gcol + (long long)b * a.P + (long long)row * w;
-    for (int x = lane; x < w; x += 32) { const int gv = gr[x]; g2[x] = gv * gv; }
+    for (int x = lane; x < w; x += 32) gs[x] = gr[x];
     __syncwarp();
     int n = 1; while (n < w + 1) n <<= 1;
     for (int step = n >> 1; step >= 1; step >>= 1) {
@@ -331,15 +489,17 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a) {
         if (cnt >= 32) {
             for (int j = lane; j < cnt; j += 32) {
                 const int p = step * (2 * j + 1);
-                const int lo = (p - step >= 1) ? arg[p - step - 1] : 0;
-                const int hi = (p + step <= w) ? arg[p + step - 1] : w - 1;
                 const int m = p - 1;
+                const int gm = gs[m];
+                int lo = (p - step >= 1) ? (int)arg[p - step - 1] : 0;
+                int hi = (p + step <= w) ? (int)arg[p + step - 1] : w - 1;
+                lo = max(lo, m - gm); hi = min(hi, m + gm);
                 int best = 0x7fffffff, bx = lo;
                 for (int xq = lo; xq <= hi; ++xq) {
-                    const int dxx = m - xq; const int v = g2[xq] + dxx * dxx;
+                    const int dxx = m - xq, gq = gs[xq]; const int v = gq * gq + dxx * dxx;
                     if (v < best) { best = v; bx = xq; }
                 }
-                dv[m] = best; arg[m] = bx;
+                dv[m] = best; arg[m] = (unsigned short)bx;
             }
         } else {
             int c2 = 1; while (c2 < cnt) c2 <<= 1;
@@ -349,12 +509,14 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a) {
             int m = 0;
             if (grp < cnt) {
                 const int p = step * (2 * grp + 1);
-                const int lo = (p - step >= 1) ? arg[p - step - 1] : 0;
-                const int hi = (p + step <= w) ? arg[p + step - 1] : w - 1;
                 m = p - 1;
+                const int gm = gs[m];
+                int lo = (p - step >= 1) ? (int)arg[p - step - 1] : 0;
+                int hi = (p + step <= w) ? (int)arg[p + step - 1] : w - 1;
+                lo = max(lo, m - gm); hi = min(hi, m + gm);
                 int best = 0x7fffffff, bx = lo;
                 for (int xq = lo + sub; xq <= hi; xq += G) {
-                    const int dxx = m - xq; const int v = g2[xq] + dxx * dxx;
+                    const int dxx = m - xq, gq = gs[xq]; const int v = gq * gq + dxx * dxx;
                     if (v < best) { best = v; bx = xq; }
                 }
                 key = ((unsigned long long)(unsigned)best << 32) | (unsigned)bx;
@@ -363,7 +525,7 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a) {
                 const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
                 key = other < key ? other : key;
             }
-            if (grp < cnt && sub == 0) { dv[m] = (int)(key >> 32); arg[m] = (int)(key & 0xffffffffu); }
+            if (grp < cnt && sub == 0) { dv[m] = (int)(key >> 32); arg[m] = (unsigned short)(key & 0xffffu); }
         }
         __syncwarp();
     }
@@ -381,7 +543,8 @@ int launch_edt_rows(dvo_ctx* c, int first, int count) {
     for (int l = 0; l < g.L; ++l) {
         EdtArgs a; a.gcol = c->gcol + g.off[l]; a.d2 = c->d2 + g.off[l]; a.maxd2 = c->maxd2 + l;
         a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L; a.first = first;
-        const size_t smem = (size_t)WARPS * 3 * g.w[l] * sizeof(int);
+        const int wp = (g.w[l] + 1) & ~1;
+        const size_t smem = (size_t)WARPS * (g.w[l] + wp) * sizeof(int);
         if (smem > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(edt_rows_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid((g.h[l] + WARPS - 1) / WARPS, count);
         edt_rows_kernel<WARPS><<<grid, WARPS * 32, smem, c->stream>>>(a);
@@ -399,32 +562,51 @@ int launch_edt_rows(dvo_ctx* c, int first, int count) {
 // =====================================================================================================
 struct NormArgs { const int32_t* d2; float4* texel; const unsigned* maxd2; const unsigned* nedge; int w, h, P, L, first; };
 
+// One CTA = one 32x32 pixel tile: DTn is computed once per pixel (plus a one-pixel halo) into shared memory, the
+// central differences are taken from the tile, and each warp stores 32 consecutive 16-byte texels (512 B) per row.
 __global__ void __launch_bounds__(256) normgrad_kernel(NormArgs a) {
-    const int b = a.first + blockIdx.y;
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= a.P) return;
+    __shared__ float tile[34][35];
+    __shared__ float s_scale;
+    const int b = a.first + blockIdx.z;
     const int w = a.w, h = a.h;
-    const int y = q / w, x = q - y * w;
-    const unsigned mx2 = a.maxd2[(long long)b * a.L];
-    const unsigned ne = a.nedge[(long long)b * a.L];
-    float scale = 0.0f;
-    if (ne > 0u) {
-        const double smax = (double)__fsqrt_rn((float)mx2);          // smin = 0 whenever an edge exists
-        const double sc = 255.0 * ((smax > 2.220446049250313e-16) ? __ddiv_rn(1.0, smax) : 0.0);
-        scale = __double2float_rn(sc);
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    if (threadIdx.x == 0) {
+        const unsigned mx2 = a.maxd2[(long long)b * a.L];
+        const unsigned ne = a.nedge[(long long)b * a.L];
+        float scale = 0.0f;
+        if (ne > 0u) {
+            const double smax = (double)__fsqrt_rn((float)mx2);          // smin = 0 whenever an edge exists
+            const double sc = 255.0 * ((smax > 2.220446049250313e-16) ? __ddiv_rn(1.0, smax) : 0.0);
+            scale = __double2float_rn(sc);
+        }
+        s_scale = scale;
     }
+    __syncthreads();
+    const float scale = s_scale;
     const int32_t* __restrict__ d = a.d2 + (long long)b * a.P;
-    auto dtn = [&](int yy, int xx) -> float { return __fmul_rn(__fsqrt_rn((float)d[yy * w + xx]), scale); };
-    int xl = x - 1 < 0 ? 1 : x - 1, xr = x + 1 >= w ? w - 2 : x + 1;
-    int yu = y - 1 < 0 ? 1 : y - 1, yd = y + 1 >= h ? h - 2 : y + 1;
-    if (w == 1) xl = xr = 0;
-    if (h == 1) yu = yd = 0;
-    float4 t;
-    t.x = dtn(y, x);
-    t.y = __fadd_rn(__fmul_rn(-0.5f, dtn(y, xl)), __fmul_rn(0.5f, dtn(y, xr)));
-    t.z = __fadd_rn(__fmul_rn(-0.5f, dtn(yu, x)), __fmul_rn(0.5f, dtn(yd, x)));
-    t.w = 0.0f;
-    a.texel[(long long)b * a.P + q] = t;
+    for (int i = threadIdx.x; i < 34 * 34; i += 256) {
+        const int ty = i / 34, tx = i - ty * 34;
+        const int y = y0 + ty - 1, x = x0 + tx - 1;
+        float v = 0.0f;
+        if (x >= 0 && x < w && y >= 0 && y < h) v = __fmul_rn(__fsqrt_rn((float)__ldg(d + y * w + x)), scale);
+        tile[ty][tx] = v;
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31;
+    const int x = x0 + tx;
+    if (x >= w) return;
+    float4* __restrict__ out = a.texel + (long long)b * a.P;
+    for (int ty = threadIdx.x >> 5; ty < 32; ty += 8) {
+        const int y = y0 + ty;
+        if (y >= h) break;
+        float4 t;
+        t.x = tile[ty + 1][tx + 1];
+        // REFLECT_101: both taps coincide on the first/last column (row) -> exactly 0
+        t.y = (x == 0 || x == w - 1) ? 0.0f : __fadd_rn(__fmul_rn(-0.5f, tile[ty + 1][tx]), __fmul_rn(0.5f, tile[ty + 1][tx + 2]));
+        t.z = (y == 0 || y == h - 1) ? 0.0f : __fadd_rn(__fmul_rn(-0.5f, tile[ty][tx + 1]), __fmul_rn(0.5f, tile[ty + 2][tx + 1]));
+        t.w = 0.0f;
+        out[(long long)y * w + x] = t;
+    }
 }
 
 int launch_normgrad(dvo_ctx* c, int first, int count) {
@@ -433,9 +615,13 @@ int launch_normgrad(dvo_ctx* c, int first, int count) {
         NormArgs a; a.d2 = c->d2 + g.off[l]; a.texel = c->texel + g.off[l]; a.maxd2 = c->maxd2 + l;
         a.nedge = c->nedge + (size_t)DVO_FRAME_NOW * g.Bmax * g.L + l;
         a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L; a.first = first;
-        dim3 grid((g.P[l] + 255) / 256, count);
-        normgrad_kernel<<<grid, 256, 0, c->stream>>>(a);
-        c->launches++;
+        for (int z0 = 0; z0 < count; z0 += 32768) {          // gridDim.z limit is 65535
+            NormArgs az = a; az.first = first + z0;
+            const int nz = (count - z0 < 32768) ? count - z0 : 32768;
+            dim3 grid((g.w[l] + 31) / 32, (g.h[l] + 31) / 32, nz);
+            normgrad_kernel<<<grid, 256, 0, c->stream>>>(az);
+            c->launches++;
+        }
     }
     DVO_CUDA(cudaGetLastError());
     return DVO_OK;
