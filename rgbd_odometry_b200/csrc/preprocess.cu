@@ -1,5 +1,7 @@
 // preprocess.cu -- pyramid, Canny (+ fused EDT column pass / reference point list), EDT row pass,
 // normalise + gradient.  All integer stages are bit-exact against oracle/dvo_oracle.hpp.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // =====================================================================================================
@@ -459,22 +461,29 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
 // so each level costs O(w) evaluations and the whole row O(w log w), with no sequential stack as in the
 // Meijster/Felzenszwalb scan.  Result is independent of evaluation order (pure min) -> bit-exact.
 // =====================================================================================================
+#define DVO_EDT_SPARSE_DIV 2048     // an image is "sparse" when nedge * DVO_EDT_SPARSE_DIV < P
+
 struct EdtArgs {
     const uint16_t* gcol; int32_t* d2; unsigned* maxd2;   // level regions; maxd2 + level, stride L
     int w, h, P, L, first;
 };
 
-// Shared memory per warp: g (u16, column distance), arg (u16, leftmost argmin), dv (i32, result).
-// Every search window is additionally clipped to |x - x'| <= g(x): the candidate x' = x already gives g(x)^2, so
-// no argmin can lie farther away.  With dense edge maps this makes every search a handful of evaluations.
+// Shared memory per warp: dv (i32, result), g (u16, column distance), arg (u16, leftmost argmin).
+// Every search window is clipped to |x - x'| <= g(x) (the candidate x' = x already gives g(x)^2).  Positions of one
+// bisection level are taken 32 at a time: a lane scans its own window when it is short; long windows (rare, but they
+// would otherwise stall the other 31 lanes) are scanned cooperatively by the whole warp and reduced with REDUX.
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a) {
+__global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a, const unsigned* __restrict__ nedge) {
     extern __shared__ int smem_i32[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int w = a.w;
     const int row = blockIdx.x * WARPS + warp;
     const int b = a.first + blockIdx.y;
     if (row >= a.h) return;                      // whole warp exits together; only __syncwarp below
+    {   // this kernel only takes the images the window kernel skipped (few edge pixels)
+        const unsigned ne = nedge[(long long)b * a.L];
+        if (ne == 0u || (unsigned long long)ne * DVO_EDT_SPARSE_DIV >= (unsigned long long)a.P) return;
+    }
     const int wp = (w + 1) & ~1;                 // even number of u16 per array
     int* dv = smem_i32 + (size_t)warp * (w + wp);
     unsigned short* gs = reinterpret_cast<unsigned short*>(dv + w);
@@ -482,18 +491,24 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a) {
     const uint16_t* __restrict__ gr = a.gcol + (long long)b * a.P + (long long)row * w;
     for (int x = lane; x < w; x += 32) gs[x] = gr[x];
     __syncwarp();
+    constexpr int SOLO_MAX = 6;
     int n = 1; while (n < w + 1) n <<= 1;
     for (int step = n >> 1; step >= 1; step >>= 1) {
         const int cnt = ((w / step) + 1) >> 1;   // positions p = step*(2j+1) <= w, j = 0..cnt-1
-        if (cnt == 0) continue;
-        if (cnt >= 32) {
-            for (int j = lane; j < cnt; j += 32) {
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            const int j = j0 + lane;
+            const bool has = j < cnt;
+            int m = 0, lo = 0, hi = -1;
+            if (has) {
                 const int p = step * (2 * j + 1);
-                const int m = p - 1;
+                m = p - 1;
                 const int gm = gs[m];
-                int lo = (p - step >= 1) ? (int)arg[p - step - 1] : 0;
-                int hi = (p + step <= w) ? (int)arg[p + step - 1] : w - 1;
+                lo = (p - step >= 1) ? (int)arg[p - step - 1] : 0;
+                hi = (p + step <= w) ? (int)arg[p + step - 1] : w - 1;
                 lo = max(lo, m - gm); hi = min(hi, m + gm);
+            }
+            const bool solo = has && (hi - lo < SOLO_MAX);
+            if (solo) {
                 int best = 0x7fffffff, bx = lo;
                 for (int xq = lo; xq <= hi; ++xq) {
                     const int dxx = m - xq, gq = gs[xq]; const int v = gq * gq + dxx * dxx;
@@ -501,38 +516,70 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a) {
                 }
                 dv[m] = best; arg[m] = (unsigned short)bx;
             }
-        } else {
-            int c2 = 1; while (c2 < cnt) c2 <<= 1;
-            const int G = 32 / c2;               // lanes per position
-            const int grp = lane / G, sub = lane - grp * G;
-            unsigned long long key = 0xffffffffffffffffull;
-            int m = 0;
-            if (grp < cnt) {
-                const int p = step * (2 * grp + 1);
-                m = p - 1;
-                const int gm = gs[m];
-                int lo = (p - step >= 1) ? (int)arg[p - step - 1] : 0;
-                int hi = (p + step <= w) ? (int)arg[p + step - 1] : w - 1;
-                lo = max(lo, m - gm); hi = min(hi, m + gm);
-                int best = 0x7fffffff, bx = lo;
-                for (int xq = lo + sub; xq <= hi; xq += G) {
-                    const int dxx = m - xq, gq = gs[xq]; const int v = gq * gq + dxx * dxx;
+            unsigned longmask = __ballot_sync(0xffffffffu, has && !solo);
+            while (longmask) {
+                const int src = __ffs(longmask) - 1; longmask &= longmask - 1;
+                const int Lo = __shfl_sync(0xffffffffu, lo, src), Hi = __shfl_sync(0xffffffffu, hi, src), M = __shfl_sync(0xffffffffu, m, src);
+                int best = 0x7fffffff, bx = 0x7fffffff;
+                for (int xq = Lo + lane; xq <= Hi; xq += 32) {
+                    const int dxx = M - xq, gq = gs[xq]; const int v = gq * gq + dxx * dxx;
                     if (v < best) { best = v; bx = xq; }
                 }
-                key = ((unsigned long long)(unsigned)best << 32) | (unsigned)bx;
+                const int vmin = __reduce_min_sync(0xffffffffu, best);
+                const int xmin = __reduce_min_sync(0xffffffffu, best == vmin ? bx : 0x7fffffff);
+                if (lane == 0) { dv[M] = vmin; arg[M] = (unsigned short)xmin; }
             }
-            for (int o = G >> 1; o > 0; o >>= 1) {
-                const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-                key = other < key ? other : key;
-            }
-            if (grp < cnt && sub == 0) { dv[m] = (int)(key >> 32); arg[m] = (unsigned short)(key & 0xffffu); }
         }
         __syncwarp();
     }
     int32_t* out = a.d2 + (long long)b * a.P + (long long)row * w;
     int mx = 0;
     for (int x = lane; x < w; x += 32) { const int v = dv[x]; out[x] = v; mx = max(mx, v); }
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0) atomicMax(&a.maxd2[(long long)b * a.L], (unsigned)mx);
+}
+
+// ---- EDT rows, primary kernel: expanding window with early exit -------------------------------------------------
+// d2(x) = min_k ( g(x +- k)^2 + k^2 ).  A warp takes 32 consecutive pixels of a row and grows k while k^2 is still
+// smaller than some lane's current best; every later candidate is at least k^2, so stopping is exact.  With contour
+// edge maps the loop length is the largest distance inside the 32-pixel segment (a dozen steps at 640x480), every
+// step is two conflict-free shared-memory loads and two min's for all 32 lanes -- no divergence, no stack.
+// Images with very few edge pixels (loop length ~ image width) are left to the bisection kernel below.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) edt_rows_window_kernel(EdtArgs a, const unsigned* __restrict__ nedge) {
+    extern __shared__ int smem_i32[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = a.w;
+    const int row = blockIdx.x * WARPS + warp;
+    const int b = a.first + blockIdx.y;
+    if (row >= a.h) return;
+    const unsigned ne = nedge[(long long)b * a.L];
+    if (ne != 0u && (unsigned long long)ne * DVO_EDT_SPARSE_DIV < (unsigned long long)a.P) return;   // sparse image: other kernel
+    int32_t* out = a.d2 + (long long)b * a.P + (long long)row * w;
+    if (ne == 0u) {                                  // no edge pixel at all: d2 is the sentinel everywhere
+        for (int x = lane; x < w; x += 32) out[x] = DVO_EDT_INF;
+        if (lane == 0) atomicMax(&a.maxd2[(long long)b * a.L], (unsigned)DVO_EDT_INF);
+        return;
+    }
+    int* g2 = smem_i32 + (size_t)warp * (w + 2) + 1;  // g2[-1] and g2[w] are sentinels
+    const uint16_t* __restrict__ gr = a.gcol + (long long)b * a.P + (long long)row * w;
+    for (int x = lane; x < w; x += 32) { const int gv = gr[x]; g2[x] = gv * gv; }
+    if (lane == 0) { g2[-1] = 0x3fffffff; g2[w] = 0x3fffffff; }
+    __syncwarp();
+    int mx = 0;
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        const int x = x0 + lane;
+        int best = (x < w) ? g2[x] : 0;
+        int kk = 1;
+        for (int k = 1; k < w; ++k) {
+            if (__all_sync(0xffffffffu, kk >= best)) break;
+            const int vl = g2[min(max(x - k, -1), w)], vr = g2[min(x + k, w)];
+            best = min(best, min(vl, vr) + kk);
+            kk += 2 * k + 1;
+        }
+        if (x < w) { out[x] = best; mx = max(mx, best); }
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) atomicMax(&a.maxd2[(long long)b * a.L], (unsigned)mx);
 }
 
@@ -543,12 +590,22 @@ int launch_edt_rows(dvo_ctx* c, int first, int count) {
     for (int l = 0; l < g.L; ++l) {
         EdtArgs a; a.gcol = c->gcol + g.off[l]; a.d2 = c->d2 + g.off[l]; a.maxd2 = c->maxd2 + l;
         a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L; a.first = first;
-        const int wp = (g.w[l] + 1) & ~1;
-        const size_t smem = (size_t)WARPS * (g.w[l] + wp) * sizeof(int);
-        if (smem > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(edt_rows_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned* ne = c->nedge + (size_t)DVO_FRAME_NOW * g.Bmax * g.L + l;
+        const int w = g.w[l];
         dim3 grid((g.h[l] + WARPS - 1) / WARPS, count);
-        edt_rows_kernel<WARPS><<<grid, WARPS * 32, smem, c->stream>>>(a);
-        c->launches++;
+        {   // dense images: expanding-window kernel
+            const size_t smem = (size_t)WARPS * (w + 2) * sizeof(int);
+            if (smem > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(edt_rows_window_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            edt_rows_window_kernel<WARPS><<<grid, WARPS * 32, smem, c->stream>>>(a, ne);
+            c->launches++;
+        }
+        {   // sparse images: bisection kernel (exits immediately for every other image)
+            const int wp = (w + 1) & ~1;
+            const size_t smem = (size_t)WARPS * (w + wp) * sizeof(int);
+            if (smem > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(edt_rows_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            edt_rows_kernel<WARPS><<<grid, WARPS * 32, smem, c->stream>>>(a, ne);
+            c->launches++;
+        }
     }
     DVO_CUDA(cudaGetLastError());
     return DVO_OK;

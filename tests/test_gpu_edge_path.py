@@ -245,10 +245,10 @@ def test_blank_and_degenerate_inputs():
     al.close()
 
 
-@pytest.mark.parametrize("W,H,L", [(100, 75, 3), (82, 61, 2), (1280, 720, 5), (320, 240, 4)])
+@pytest.mark.parametrize("W,H,L", [(100, 75, 3), (82, 61, 2), (1280, 720, 5), (320, 240, 4), (2112, 96, 2)])
 def test_ragged_and_large_sizes(W, H, L):
-    """Odd sizes (cvRound half-to-even level dims, non-multiple-of-32 widths) and 1280x720x5 (BASELINE config 4;
-    hysteresis bitmaps exceed shared memory -> global scratch path)."""
+    """Odd sizes (cvRound half-to-even level dims, non-multiple-of-32 widths), 1280x720x5 (BASELINE config 4;
+    hysteresis bitmaps exceed shared memory -> global scratch path) and a very wide image (EDT bisection fallback)."""
     K = (525.0 * W / 640, 525.0 * W / 640, (W - 1) / 2.0, (H - 1) / 2.0)
     d = O.synth_pair(7, W, H, K)
     al = dvo.BatchAligner(W, H, L, max_batch=1, intrinsics=K)
@@ -305,6 +305,30 @@ def test_edt_adversarial_patterns():
         assert np.array_equal(edge, O.canny(gray[i])), f"image {i}: {mismatch(edge, O.canny(gray[i]))}"
         d2 = al.get_level_buffer(i, 1, 0, "d2")
         assert np.array_equal(d2, O.edt_d2(edge, brute=True)), f"image {i}"
+    al.close()
+
+
+def test_edt_sparse_images_take_the_bisection_kernel():
+    """Images with very few edge pixels (nedge * 2048 < P) are routed to the bisection EDT kernel; a lone blob and a
+    short segment far from everything give distances of hundreds of pixels."""
+    W, H = 320, 240
+    a = np.full((H, W), 30, np.uint8); a[100:103, 200:203] = 255
+    b = np.full((H, W), 30, np.uint8); b[5:8, 5:12] = 230
+    gray = np.stack([a, b])
+    al = dvo.BatchAligner(W, H, 1, max_batch=2, intrinsics=(262.5, 262.5, 159.5, 119.5))
+    al.set_frames(dvo.FRAME_REF, gray, np.full((2, H, W), 1000, np.uint16))
+    al.set_frames(dvo.FRAME_NOW, gray, None)
+    al.build_pyramids(2)
+    al.prepare(2)
+    for i in range(2):
+        edge = al.get_level_buffer(i, 1, 0, "edge")
+        assert np.array_equal(edge, O.canny(gray[i]))
+        n = int((edge > 0).sum())
+        assert 0 < n and n * 2048 < W * H, n
+        d2 = al.get_level_buffer(i, 1, 0, "d2")
+        assert np.array_equal(d2, O.edt_d2(edge)), mismatch(d2, O.edt_d2(edge))
+        dtn, _ = O.dt_normalize(d2)
+        assert bits_equal(al.get_level_buffer(i, 1, 0, "dtn"), dtn)
     al.close()
 
 
