@@ -111,21 +111,23 @@ __device__ __forceinline__ void row_sums(const uint8_t* __restrict__ grow, int w
     hs = r - l; hb = l + 2 * v + r;
 }
 
-constexpr int CANNY_MAX_WARPS = 32;
+constexpr int CANNY_MAX_WARPS = 24;
 
-__global__ void __launch_bounds__(1024) canny_kernel(CannyArgs a) {
+template <bool GLOBAL_BITMAPS>
+__global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     extern __shared__ uint32_t smem_u32[];
     __shared__ int s_scan[CANNY_MAX_WARPS + 1];
     __shared__ int s_base;
     __shared__ unsigned s_cnt;
-    __shared__ unsigned char s_chg[2][1024];
+    __shared__ unsigned char s_chg[2][768];
     const int T = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = a.first + blockIdx.x;
     const int w = a.w, h = a.h;
     const int wd = (w + 31) >> 5, pitch = wd + 2;
     const int nwords = a.bm_words;
-    uint32_t* C = a.gscratch ? a.gscratch + (long long)blockIdx.x * a.gscratch_stride : smem_u32;
+    // bitmaps: shared memory (LDS/STS/ATOMS) or, for images too large for it, a global scratch
+    uint32_t* C = GLOBAL_BITMAPS ? a.gscratch + (long long)blockIdx.x * a.gscratch_stride : smem_u32;
     uint32_t* E = C + nwords;
     const uint8_t* __restrict__ g = a.gray + (long long)b * a.P;
 
@@ -153,10 +155,15 @@ __global__ void __launch_bounds__(1024) canny_kernel(CannyArgs a) {
             const int x = 30 * k + lane - 1;
             const bool incol = (x >= 0 && x < w);
             const int xc = min(max(x, 0), w - 1);                     // BORDER_REPLICATE
-            const int xe = min(max(lane == 0 ? x - 1 : x + 1, 0), w - 1);
-            auto loadrow = [&](int r, int& v, int& ve) {
-                const uint8_t* __restrict__ p = g + min(max(r, 0), h - 1) * w;
-                v = p[xc]; ve = halo ? (int)p[xe] : 0;
+            const int de = min(max(lane == 0 ? x - 1 : x + 1, 0), w - 1) - xc;
+            const int low = a.low, high = a.high;
+            // row pointer that follows r = clamp(row, 0, h-1) incrementally
+            const uint8_t* __restrict__ pr = g + min(max(y0 - 2, 0), h - 1) * w + xc;
+            int rr = y0 - 2;
+            auto loadrow = [&](int& v, int& ve) {                     // loads row rr (clamped), then advances rr
+                v = pr[0]; ve = halo ? (int)pr[de] : 0;
+                if (rr >= 0 && rr < h - 1) pr += w;
+                ++rr;
             };
             auto sums = [&](int v, int ve, int& hs, int& hb) {
                 int l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
@@ -166,25 +173,28 @@ __global__ void __launch_bounds__(1024) canny_kernel(CannyArgs a) {
             };
             int hsA, hbA, hsB, hbB, hsC, hbC, v, ve, vn, ven;
             int mPL, mPC, mPR, mCL, mCC, mCR, dxC, dyC;
-            loadrow(y0 - 2, v, ve); sums(v, ve, hsA, hbA);
-            loadrow(y0 - 1, v, ve); sums(v, ve, hsB, hbB);
-            loadrow(y0, v, ve); sums(v, ve, hsC, hbC);
+            loadrow(v, ve); sums(v, ve, hsA, hbA);                    // gray row y0-2
+            loadrow(v, ve); sums(v, ve, hsB, hbB);                    // y0-1
+            loadrow(v, ve); sums(v, ve, hsC, hbC);                    // y0
             {   // magnitude row y0-1 (zero outside the image)
                 const int dx = hsA + 2 * hsB + hsC, dy = hbC - hbA;
                 mPC = (incol && y0 - 1 >= 0) ? dx * dx + dy * dy : 0;
                 mPL = __shfl_up_sync(0xffffffffu, mPC, 1); mPR = __shfl_down_sync(0xffffffffu, mPC, 1);
             }
             hsA = hsB; hbA = hbB; hsB = hsC; hbB = hbC;
-            loadrow(y0 + 1, v, ve); sums(v, ve, hsC, hbC);
+            loadrow(v, ve); sums(v, ve, hsC, hbC);                    // y0+1
             {   // magnitude row y0
                 dxC = hsA + 2 * hsB + hsC; dyC = hbC - hbA;
                 mCC = incol ? dxC * dxC + dyC * dyC : 0;
                 mCL = __shfl_up_sync(0xffffffffu, mCC, 1); mCR = __shfl_down_sync(0xffffffffu, mCC, 1);
             }
-            loadrow(y0 + 2, vn, ven);                                 // prefetched one row ahead
+            loadrow(vn, ven);                                         // y0+2, prefetched one row ahead
+            const int c0 = 30 * k, sh = c0 & 31;
+            uint32_t* Bm = (lane == 0 ? C : E) + (y0 + 1) * pitch + (c0 >> 5) + 1;   // lane 0 merges candidates, lane 1 the strong set
+            const bool writer = lane < 2;
             for (int y = y0; y < y1; ++y) {
                 v = vn; ve = ven;
-                loadrow(y + 3, vn, ven);
+                loadrow(vn, ven);                                     // gray row y+3
                 hsA = hsB; hbA = hbB; hsB = hsC; hbB = hbC;
                 sums(v, ve, hsC, hbC);                                // gray row y+2
                 const int dxN = hsA + 2 * hsB + hsC, dyN = hbC - hbA; // gradient at row y+1
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(1024) canny_kernel(CannyArgs a) {
                 const int mNL = __shfl_up_sync(0xffffffffu, mNC, 1), mNR = __shfl_down_sync(0xffffffffu, mNC, 1);
                 bool cand = false, strong = false;
                 const int m = mCC;
-                if (m > a.low && !halo) {                             // m == 0 outside the image
+                if (m > low && !halo) {                               // m == 0 outside the image
                     const int ax = abs(dxC), ay = abs(dyC) << 15;
                     const int tg22x = ax * TG22;
                     bool keep;
@@ -202,18 +212,21 @@ __global__ void __launch_bounds__(1024) canny_kernel(CannyArgs a) {
                         if (ay > tg67x) keep = (m > mPC) && (m >= mNC);
                         else { const bool neg = ((dxC ^ dyC) < 0); keep = (m > (neg ? mPR : mPL)) && (m > (neg ? mNL : mNR)); }
                     }
-                    cand = keep; strong = keep && (m > a.high);
+                    cand = keep; strong = keep && (m > high);
                 }
-                const uint32_t cb = __ballot_sync(0xffffffffu, cand), sb = __ballot_sync(0xffffffffu, strong);
-                if (lane < 2) {                                       // lane 0 merges candidates, lane 1 the strong set
-                    const uint32_t bits = ((lane == 0 ? cb : sb) >> 1) & 0x3fffffffu;
-                    if (bits) {
-                        const int c0 = 30 * k, sh = c0 & 31;
-                        uint32_t* Bm = (lane == 0 ? C : E) + (y + 1) * pitch + (c0 >> 5) + 1;
-                        atomicOr(Bm, bits << sh);
-                        if (sh > 2) { const uint32_t hi = bits >> (32 - sh); if (hi) atomicOr(Bm + 1, hi); }
+                const uint32_t cb = __ballot_sync(0xffffffffu, cand);
+                if (cb) {                                             // warp-uniform
+                    const uint32_t sb = __ballot_sync(0xffffffffu, strong);
+                    if (writer) {
+                        const uint32_t bits = ((lane == 0 ? cb : sb) >> 1) & 0x3fffffffu;
+                        if (bits) {
+                            atomicOr(Bm, bits << sh);
+                            const uint32_t hi = (sh > 2) ? bits >> (32 - sh) : 0u;
+                            if (hi) atomicOr(Bm + 1, hi);
+                        }
                     }
                 }
+                Bm += pitch;
                 mPL = mCL; mPC = mCC; mPR = mCR; mCL = mNL; mCC = mNC; mCR = mNR; dxC = dxN; dyC = dyN;
             }
         }
@@ -222,13 +235,13 @@ __global__ void __launch_bounds__(1024) canny_kernel(CannyArgs a) {
 
     // ------------------------------------------------------------------ phase 2: hysteresis closure
     {
-        const int Hs = max(1, min(h, min(T, 1024) / wd));   // row strips
+        const int Hs = max(1, min(h, min(T, 768) / wd));    // row strips
         const int Rh = (h + Hs - 1) / Hs;
         const int items = wd * Hs;
         const int sh = tid / wd, wx = tid - sh * wd;
         const bool owner = tid < items;
         const int ya = sh * Rh, yb = min(h, ya + Rh);
-        for (int i = tid; i < 2 * 1024; i += T) (&s_chg[0][0])[i] = (i < 1024) ? 1 : 0;   // everything active at first
+        for (int i = tid; i < 2 * 768; i += T) (&s_chg[0][0])[i] = (i < 768) ? 1 : 0;     // everything active at first
         __syncthreads();
         int cur = 0;
         for (;;) {
@@ -420,10 +433,10 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
         if (use_global && (!c->bitmap_scratch || (size_t)2 * words > c->bitmap_scratch_words)) {
             dvo_set_error("canny: bitmap scratch missing for %dx%d", g.w[l], g.h[l]); return DVO_ERR_STATE;
         }
-        // warps = (30-column chunks) x (row strips), 16..32 warps per CTA
+        // warps = (30-column chunks) x (row strips), up to 24 warps per CTA (two CTAs per SM)
         const int nchunk = (g.w[l] + 29) / 30;
         int S = 24 / nchunk; if (S < 1) S = 1;
-        int warps = nchunk * S; if (warps > 32) warps = 32; if (warps < 4) warps = 4;
+        int warps = nchunk * S; if (warps > CANNY_MAX_WARPS) warps = CANNY_MAX_WARPS; if (warps < 4) warps = 4;
         const int T = warps * 32;
         for (int f = 0; f < 2; ++f) {
             if (!(frames_mask & (1 << f))) continue;
@@ -444,8 +457,11 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
             a.gscratch_stride = (long long)c->bitmap_scratch_words;
             a.first = first; a.low = 10000; a.high = 22500; a.bm_words = words;
             const size_t dyn = use_global ? 0 : smem;
-            if (dyn > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(canny_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-            canny_kernel<<<count, T, dyn, c->stream>>>(a);
+            if (use_global) canny_kernel<true><<<count, T, 0, c->stream>>>(a);
+            else {
+                if (dyn > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(canny_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+                canny_kernel<false><<<count, T, dyn, c->stream>>>(a);
+            }
             c->launches++;
         }
     }
