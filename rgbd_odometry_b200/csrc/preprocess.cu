@@ -630,8 +630,9 @@ int launch_edt_rows(dvo_ctx* c, int first, int count) {
 // =====================================================================================================
 // normalise + gradient (src/SolveDVO.cpp:1774, 1790, 1063-1098):
 //   DT = sqrtf(d2) (IEEE), DTn = DT * (float)(255 * (1/(max-min))) + 0, gx/gy = 0.5*(next) - 0.5*(prev) with
-//   REFLECT_101 (exactly 0 on the border).  Output packed as one 16-byte texel {DTn, gx, gy, 0} so that the
-//   solver does a single 128-bit gather per reprojected point.
+//   REFLECT_101 (exactly 0 on the border).  Output packed as one 16-byte texel {DTn, gx, gy, w} so that the
+//   solver does a single 128-bit gather per reprojected point; w = getWeightOf(DTn) (src/SolveDVO.cpp:1047-1053)
+//   is a function of the pixel alone, so it is evaluated once here instead of once per point and iteration.
 // =====================================================================================================
 struct NormArgs { const int32_t* d2; float4* texel; const unsigned* maxd2; const unsigned* nedge; int w, h, P, L, first; };
 
@@ -677,7 +678,7 @@ __global__ void __launch_bounds__(256) normgrad_kernel(NormArgs a) {
         // REFLECT_101: both taps coincide on the first/last column (row) -> exactly 0
         t.y = (x == 0 || x == w - 1) ? 0.0f : __fadd_rn(__fmul_rn(-0.5f, tile[ty + 1][tx]), __fmul_rn(0.5f, tile[ty + 1][tx + 2]));
         t.z = (y == 0 || y == h - 1) ? 0.0f : __fadd_rn(__fmul_rn(-0.5f, tile[ty][tx + 1]), __fmul_rn(0.5f, tile[ty + 2][tx + 1]));
-        t.w = 0.0f;
+        t.w = Ar<DVO_ARITH_EXACT>::weight_ref(t.x);      // getWeightOf(DTn) depends on the pixel only: precomputed here
         out[(long long)y * w + x] = t;
     }
 }

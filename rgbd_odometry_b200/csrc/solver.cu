@@ -3,12 +3,13 @@
 // H = J^T W J, the 6-vector step / 6x6 solve, SE(3) update, best-iterate tracking, termination) with no host
 // round trip.  Follows SolveDVO::runIterations (src/SolveDVO.cpp:619-1017), computeJacobianOfNowFrame
 // (:306-414) and getReprojectedEpsilons (:425-462); see SURVEY.md Appendix A for the restated arithmetic.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int SOLVE_THREADS = 256;
-constexpr int SOLVE_WARPS = SOLVE_THREADS / 32;
+constexpr int EVAL_THREADS = 256;     // inspection kernel
 
 // ------------------------------------------------------------------ fp64 3x3 / SE(3) helpers (device)
 __device__ __forceinline__ void m3_mul(const double* A, const double* B, double* C) {
@@ -28,7 +29,7 @@ __device__ __forceinline__ void m3_vec(const double* A, const double* v, double*
 }
 
 // SE(3) exponential, tangent = (upsilon, omega), translation first (Sophus::SE3d::exp, src/SolveDVO.cpp:905).
-__device__ __noinline__ void se3_exp_dev(const double* psi, double* R, double* t) {
+__device__ __forceinline__ void se3_exp_dev(const double* psi, double* R, double* t) {
     const double wx = psi[3], wy = psi[4], wz = psi[5];
     const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
     double A, B, C;
@@ -64,7 +65,7 @@ __device__ __forceinline__ void rot_to_quat_dev(const double* R, double* q) {
 }
 
 // SE(3) logarithm (Sophus::SE3d::log of setRotationMatrix(cR), translation cT; src/SolveDVO.cpp:736-739)
-__device__ __noinline__ void se3_log_dev(const double* R, const double* t, double* psi) {
+__device__ __forceinline__ void se3_log_dev(const double* R, const double* t, double* psi) {
     double q[4]; rot_to_quat_dev(R, q);
     const double qn = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
     double sgn = (q[3] < 0 ? -1.0 : 1.0) / qn;
@@ -86,7 +87,7 @@ __device__ __noinline__ void se3_log_dev(const double* R, const double* t, doubl
 // SolveDVO::rotationize (src/SolveDVO.cpp:1269-1282) returns U V^T of the SVD, i.e. the orthogonal polar factor.
 // Computed here by Newton's iteration X <- (X + X^-T)/2, which converges quadratically; the input is within
 // ~1e-15 of a rotation on every call the solver makes, so one or two steps suffice.
-__device__ __noinline__ void rotationize_dev(double* R) {
+__device__ __forceinline__ void rotationize_dev(double* R) {
     for (int it = 0; it < 40; ++it) {
         const double c00 = R[4] * R[8] - R[5] * R[7], c01 = R[5] * R[6] - R[3] * R[8], c02 = R[3] * R[7] - R[4] * R[6];
         const double c10 = R[2] * R[7] - R[1] * R[8], c11 = R[0] * R[8] - R[2] * R[6], c12 = R[1] * R[6] - R[0] * R[7];
@@ -103,7 +104,7 @@ __device__ __noinline__ void rotationize_dev(double* R) {
 }
 
 // 6x6 SPD solve by Cholesky; reads the upper triangle of H (row-major).  Returns false if not positive definite.
-__device__ __noinline__ bool chol6_dev(const double* H, const double* b, double* x) {
+__device__ __forceinline__ bool chol6_dev(const double* H, const double* b, double* x) {
     double Lm[36];
     for (int i = 0; i < 6; ++i)
         for (int j = 0; j <= i; ++j) {
@@ -122,28 +123,37 @@ __device__ __noinline__ bool chol6_dev(const double* H, const double* b, double*
 struct PoseF { float R[9], T[3]; };
 struct LevelCam { float M00, M02, M11, M12; int w, h; };
 
-// Returns false when the reprojection falls outside the now image (J = eps = w = 0, src/SolveDVO.cpp:371-374).
-template <int ARITH, int JAC>
-__device__ __forceinline__ bool eval_point(float Xp, float Yp, float Zp, const PoseF& P, const LevelCam& cam,
-                                           const float4* __restrict__ tex, int weight_mode, float huber_k, float* Jr,
-                                           float& e, float& wgt, float& u, float& v) {
-    typedef Ar<ARITH> A;
-    typedef Ar<DVO_ARITH_EXACT> E;   // the reprojection is always IEEE-exact so that FAST gathers the same texel
+// Reprojection of one reference edge point (computeJacobianOfNowFrame "Step 2/3", src/SolveDVO.cpp:327-345).
+// idx < 0 when the reprojection falls outside the now image (J = eps = w = 0, :371-374).
+struct Proj { float px, py, pz, inv, X, Y, Z, u, v; int idx; };
+
+__device__ __forceinline__ Proj project_point(float Xp, float Yp, float Zp, const PoseF& P, const LevelCam& cam) {
+    typedef Ar<DVO_ARITH_EXACT> E;   // always IEEE-exact so that FAST arithmetic gathers the same texel
     const float* R = P.R;
+    Proj o;
     // p' = cR^T (P - cT)                                                       (:330)
     const float d0 = E::sub(Xp, P.T[0]), d1 = E::sub(Yp, P.T[1]), d2 = E::sub(Zp, P.T[2]);
-    const float px = E::dot3(R[0], d0, R[3], d1, R[6], d2);
-    const float py = E::dot3(R[1], d0, R[4], d1, R[7], d2);
-    const float pz = E::dot3(R[2], d0, R[5], d1, R[8], d2);
-    const float inv = E::div(1.0f, pz);                                          // :339
-    const float X = E::mul(px, inv), Y = E::mul(py, inv), Z = E::mul(pz, inv);   // :340-341
-    u = E::dot2(cam.M00, X, cam.M02, Z);                                         // :344
-    v = E::dot2(cam.M11, Y, cam.M12, Z);
-    if (!(u >= 0.0f && u < (float)cam.w && v >= 0.0f && v < (float)cam.h)) return false;
-    const int xx = __float2int_rz(u), yy = __float2int_rz(v);                    // :376-377
-    const float4 t = __ldg(tex + yy * cam.w + xx);                               // {DTn, gx, gy, 0}
+    o.px = E::dot3(R[0], d0, R[3], d1, R[6], d2);
+    o.py = E::dot3(R[1], d0, R[4], d1, R[7], d2);
+    o.pz = E::dot3(R[2], d0, R[5], d1, R[8], d2);
+    o.inv = E::div(1.0f, o.pz);                                                  // :339
+    o.X = E::mul(o.px, o.inv); o.Y = E::mul(o.py, o.inv); o.Z = E::mul(o.pz, o.inv);   // :340-341
+    o.u = E::dot2(cam.M00, o.X, cam.M02, o.Z);                                   // :344
+    o.v = E::dot2(cam.M11, o.Y, cam.M12, o.Z);
+    const bool vis = (o.u >= 0.0f && o.u < (float)cam.w && o.v >= 0.0f && o.v < (float)cam.h);
+    o.idx = vis ? __float2int_rz(o.v) * cam.w + __float2int_rz(o.u) : -1;        // :376-377
+    return o;
+}
+
+// Jacobian row, residual and weight from the gathered texel {DTn, gx, gy, getWeightOf(DTn)} (:383-406, :446-450).
+template <int ARITH, int JAC>
+__device__ __forceinline__ void finish_point(const Proj& q, const float4 t, const PoseF& P, const LevelCam& cam,
+                                             int weight_mode, float huber_k, float* Jr, float& e, float& wgt) {
+    typedef Ar<ARITH> A;
+    const float* R = P.R;
     const float G0 = t.y, G1 = t.z;
     if (JAC == DVO_JAC_REFERENCE) {
+        const float X = q.X, Y = q.Y, Z = q.Z;
         const float ZZ = A::mul(Z, Z);
         const float A00 = A::div(cam.M00, Z), A02 = -A::div(A::mul(cam.M00, X), ZZ);     // :388-390
         const float A11 = A::div(cam.M11, Z), A12 = -A::div(A::mul(cam.M11, Y), ZZ);     // :392-393
@@ -158,35 +168,50 @@ __device__ __forceinline__ bool eval_point(float Xp, float Yp, float Zp, const P
         Jr[4] = A::diff2(c, w0, a, w2);
         Jr[5] = A::diff2(a, w1, b, w0);
     } else {
-        const float a = A::mul(A::mul(G0, cam.M00), inv), b = A::mul(A::mul(G1, cam.M11), inv);
-        const float c = -A::mul(A::dot2(a, px, b, py), inv);
+        const float a = A::mul(A::mul(G0, cam.M00), q.inv), b = A::mul(A::mul(G1, cam.M11), q.inv);
+        const float c = -A::mul(A::dot2(a, q.px, b, q.py), q.inv);
         Jr[0] = -a; Jr[1] = -b; Jr[2] = -c;
-        Jr[3] = A::diff2(b, pz, c, py);
-        Jr[4] = A::diff2(c, px, a, pz);
-        Jr[5] = A::diff2(a, py, b, px);
+        Jr[3] = A::diff2(b, q.pz, c, q.py);
+        Jr[4] = A::diff2(c, q.px, a, q.pz);
+        Jr[5] = A::diff2(a, q.py, b, q.px);
     }
     e = t.x;                                                                     // :446
-    if (weight_mode == DVO_WEIGHT_REF_CAUCHY) wgt = A::weight_ref(e);            // :450, :1051
+    if (weight_mode == DVO_WEIGHT_REF_CAUCHY) wgt = (ARITH == DVO_ARITH_EXACT) ? t.w : A::weight_ref(e);   // :450, :1051 (precomputed per texel)
     else if (weight_mode == DVO_WEIGHT_HUBER) { const float ae = fabsf(e); wgt = ae <= huber_k ? 1.0f : A::div(huber_k, ae); }
     else wgt = 1.0f;
-    return true;
 }
 
 // Accumulator layout: [0..5] g, [6] sum eps^2, [7] sum eps, then (NEED_H) 21 upper-triangle entries of H row by row.
 template <bool NEED_H> struct AccN { static constexpr int N = NEED_H ? 29 : 8; };
 
-template <int ARITH, int JAC, bool NEED_H>
+// Software-pipelined sweep over a thread's points: the coordinates are loaded two points ahead and the (random)
+// texel gather of the next point is in flight while the current point's Jacobian / fp64 accumulation executes.
+template <int ARITH, int JAC, bool NEED_H, int THREADS, bool OUT>
 __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, const float* __restrict__ Y,
                                                   const float* __restrict__ Z, int N, const PoseF& P, const LevelCam& cam,
                                                   const float4* __restrict__ tex, int weight_mode, float huber_k,
                                                   double* acc, int& nvis, float* o_eps, float* o_w, float* o_u, float* o_v,
                                                   float* o_J) {
     typedef Ar<ARITH> A;
-    for (int i = threadIdx.x; i < N; i += SOLVE_THREADS) {
-        float Jr[6], e = 0.f, wgt = 0.f, u, v;
-        const bool vis = eval_point<ARITH, JAC>(__ldg(X + i), __ldg(Y + i), __ldg(Z + i), P, cam, tex, weight_mode, huber_k, Jr, e, wgt, u, v);
-        if (o_u) { o_u[i] = u; o_v[i] = v; }
-        if (vis) {
+    int i = threadIdx.x;
+    if (i >= N) return;
+    float cx = __ldg(X + i), cy = __ldg(Y + i), cz = __ldg(Z + i);
+    Proj q = project_point(cx, cy, cz, P, cam);
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q.idx >= 0) t = __ldg(tex + q.idx);
+    int i1 = i + THREADS;
+    if (i1 < N) { cx = __ldg(X + i1); cy = __ldg(Y + i1); cz = __ldg(Z + i1); }
+    for (;;) {
+        const int i2 = i1 + THREADS;
+        float nx = 0.f, ny = 0.f, nz = 1.f;
+        if (i2 < N) { nx = __ldg(X + i2); ny = __ldg(Y + i2); nz = __ldg(Z + i2); }       // coordinates two ahead
+        Proj qn; qn.idx = -1;
+        float4 tn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i1 < N) { qn = project_point(cx, cy, cz, P, cam); if (qn.idx >= 0) tn = __ldg(tex + qn.idx); }   // gather one ahead
+        // ---- consume point i
+        float Jr[6], e = 0.f, wgt = 0.f;
+        if (q.idx >= 0) {
+            finish_point<ARITH, JAC>(q, t, P, cam, weight_mode, huber_k, Jr, e, wgt);
             ++nvis;
             const double de = (double)e;
             acc[6] = fma(de, de, acc[6]);
@@ -201,19 +226,26 @@ __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, c
 #pragma unroll
                     for (int c = r; c < 6; ++c) { acc[idx] = fma(Jw[r], (double)Jr[c], acc[idx]); ++idx; }
             }
-        } else { e = 0.f; wgt = 0.f;
+        } else {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) Jr[k] = 0.f; }
-        if (o_eps) { o_eps[i] = e; o_w[i] = wgt; }
-        if (o_J) {
+            for (int k = 0; k < 6; ++k) Jr[k] = 0.f;
+        }
+        if (OUT) {
+            if (o_u) { o_u[i] = q.u; o_v[i] = q.v; }
+            if (o_eps) { o_eps[i] = e; o_w[i] = wgt; }
+            if (o_J) {
 #pragma unroll
-            for (int k = 0; k < 6; ++k) o_J[6 * i + k] = Jr[k]; }
+                for (int k = 0; k < 6; ++k) o_J[6 * i + k] = Jr[k]; }
+        }
+        if (i1 >= N) break;
+        i = i1; i1 = i2; q = qn; t = tn; cx = nx; cy = ny; cz = nz;
     }
 }
 
 // Deterministic block reduction: fixed shuffle tree inside each warp, then warp partials summed in warp order.
-template <int NACC>
+template <int NACC, int THREADS>
 __device__ __forceinline__ void block_reduce(double* acc, int nvis, double (*s_red)[NACC], int* s_nv, double* s_tot, int* s_nvtot) {
+    constexpr int SOLVE_WARPS = THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < NACC; ++k) {
@@ -252,7 +284,7 @@ struct SolveArgs {
 };
 
 // One iteration's serial tail (thread 0): best tracking, step computation, pose update.  Returns 1 to stop the level.
-__device__ __noinline__ int solver_step(SolverState& S, const double* tot, int nvis, int N, int itr, const dvo_solver_params& prm,
+__device__ __forceinline__ int solver_step(SolverState& S, const double* tot, int nvis, int N, int itr, const dvo_solver_params& prm,
                                         bool need_h, dvo_pair_info* info, int level, double* trace_rec) {
     const float ratio = (float)nvis / (float)N;                                   // :457
     const float energy = (float)sqrt(tot[6]);                                      // :1310-1312
@@ -323,9 +355,10 @@ __device__ __noinline__ int solver_step(SolverState& S, const double* tot, int n
     return 0;
 }
 
-template <int ARITH, int JAC, bool NEED_H>
-__global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(SolveArgs a) {
+template <int ARITH, int JAC, bool NEED_H, int THREADS>
+__global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve_kernel(SolveArgs a) {
     constexpr int NACC = AccN<NEED_H>::N;
+    constexpr int SOLVE_WARPS = THREADS / 32;
     __shared__ double s_red[SOLVE_WARPS][NACC];
     __shared__ double s_tot[NACC];
     __shared__ int s_nv[SOLVE_WARPS];
@@ -379,9 +412,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) solve_kernel(SolveArgs a) {
 #pragma unroll
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
             int nvis = 0;
-            accumulate_points<ARITH, JAC, NEED_H>(X, Y, Z, N, P, cam, tex, a.prm.weight, a.prm.huber_k, acc, nvis,
+            accumulate_points<ARITH, JAC, NEED_H, THREADS, false>(X, Y, Z, N, P, cam, tex, a.prm.weight, a.prm.huber_k, acc, nvis,
                                                   nullptr, nullptr, nullptr, nullptr, nullptr);
-            block_reduce<NACC>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
+            block_reduce<NACC, THREADS>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
             if (threadIdx.x == 0) {
                 double* tr = nullptr;
                 if (a.trace && itr < a.trace_iters)
@@ -417,8 +450,9 @@ struct EvalArgs {
 };
 
 template <int ARITH, int JAC>
-__global__ void __launch_bounds__(SOLVE_THREADS) eval_kernel(EvalArgs a) {
+__global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
     constexpr int NACC = AccN<true>::N;
+    constexpr int SOLVE_WARPS = EVAL_THREADS / 32;
     __shared__ double s_red[SOLVE_WARPS][NACC];
     __shared__ double s_tot[NACC];
     __shared__ int s_nv[SOLVE_WARPS];
@@ -438,9 +472,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS) eval_kernel(EvalArgs a) {
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     int nvis = 0;
-    accumulate_points<ARITH, JAC, true>(a.X + base, a.Y + base, a.Z + base, N, P, cam, a.texel + base, a.weight, a.huber_k,
+    accumulate_points<ARITH, JAC, true, EVAL_THREADS, true>(a.X + base, a.Y + base, a.Z + base, N, P, cam, a.texel + base, a.weight, a.huber_k,
                                         acc, nvis, a.eps, a.w, a.u, a.v, a.J);
-    block_reduce<NACC>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
+    block_reduce<NACC, EVAL_THREADS>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
     if (threadIdx.x == 0) {
         for (int k = 0; k < 6; ++k) a.out[k] = s_tot[k];
         int idx = 8;
@@ -471,13 +505,24 @@ __global__ void gop_kernel(int nseq, int nframes, const int* __restrict__ kind, 
 
 }  // namespace
 
+static int g_solve_threads = 256;
+
 template <int ARITH, int JAC>
 static void launch_solve_t(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
-    if (need_h) solve_kernel<ARITH, JAC, true><<<count, SOLVE_THREADS, 0, c->stream>>>(a);
-    else solve_kernel<ARITH, JAC, false><<<count, SOLVE_THREADS, 0, c->stream>>>(a);
+    if (g_solve_threads == 128) {
+        if (need_h) solve_kernel<ARITH, JAC, true, 128><<<count, 128, 0, c->stream>>>(a);
+        else solve_kernel<ARITH, JAC, false, 128><<<count, 128, 0, c->stream>>>(a);
+    } else if (g_solve_threads == 512) {
+        if (need_h) solve_kernel<ARITH, JAC, true, 512><<<count, 512, 0, c->stream>>>(a);
+        else solve_kernel<ARITH, JAC, false, 512><<<count, 512, 0, c->stream>>>(a);
+    } else {
+        if (need_h) solve_kernel<ARITH, JAC, true, 256><<<count, 256, 0, c->stream>>>(a);
+        else solve_kernel<ARITH, JAC, false, 256><<<count, 256, 0, c->stream>>>(a);
+    }
 }
 
 int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
+    if (const char* e = getenv("DVO_SOLVE_THREADS")) g_solve_threads = atoi(e);
     SolveArgs a;
     a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts;
     a.nedge_now = c->nedge + (size_t)DVO_FRAME_NOW * c->geom.Bmax * c->geom.L; a.texel = c->texel;
@@ -505,10 +550,10 @@ int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac
     a.pose = d_pose12; a.slot = slot; a.level = level; a.weight = weight; a.huber_k = huber_k; a.out = d_out;
     a.eps = d_eps; a.w = d_w; a.u = d_u; a.v = d_v; a.J = d_J;
     const bool ex = arith != DVO_ARITH_FAST, rj = jac != DVO_JAC_EXACT;
-    if (ex && rj) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_REFERENCE><<<1, SOLVE_THREADS, 0, c->stream>>>(a);
-    else if (ex) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_EXACT><<<1, SOLVE_THREADS, 0, c->stream>>>(a);
-    else if (rj) eval_kernel<DVO_ARITH_FAST, DVO_JAC_REFERENCE><<<1, SOLVE_THREADS, 0, c->stream>>>(a);
-    else eval_kernel<DVO_ARITH_FAST, DVO_JAC_EXACT><<<1, SOLVE_THREADS, 0, c->stream>>>(a);
+    if (ex && rj) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_REFERENCE><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+    else if (ex) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_EXACT><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+    else if (rj) eval_kernel<DVO_ARITH_FAST, DVO_JAC_REFERENCE><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+    else eval_kernel<DVO_ARITH_FAST, DVO_JAC_EXACT><<<1, EVAL_THREADS, 0, c->stream>>>(a);
     c->launches++;
     DVO_CUDA(cudaGetLastError());
     return DVO_OK;
