@@ -84,6 +84,11 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     c->smem_optin = prop.sharedMemPerBlockOptin;
     DVO_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
+    DVO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; ++i) DVO_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+    DVO_CUDA(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+    c->e2e_chunk = 256;
+    if (const char* e = getenv("DVO_E2E_CHUNK")) { const int v = atoi(e); if (v > 0) c->e2e_chunk = v; }
     DVO_CUDA(cudaEventCreate(&c->ev_a));
     DVO_CUDA(cudaEventCreate(&c->ev_b));
 
@@ -131,6 +136,9 @@ int dvo_destroy(dvo_ctx* c) {
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    for (int i = 0; i < 16; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+    if (c->ev_entry) cudaEventDestroy(c->ev_entry);
     delete c;
     return DVO_OK;
 }
@@ -226,20 +234,45 @@ int dvo_get_poses(dvo_ctx* c, int first, int count, double* R9T3, dvo_pair_info*
 int dvo_align_batch(dvo_ctx* c, int count, const uint8_t* ref_gray, const uint16_t* ref_depth, const uint8_t* now_gray,
                     const uint16_t* now_depth, const dvo_solver_params* p, double* R9T3, dvo_pair_info* info) {
     if (!c || count < 0 || !ref_gray || !ref_depth || !now_gray || !p) { dvo_set_error("dvo_align_batch: bad argument"); return DVO_ERR_ARG; }
+    if (!c->haveK) { dvo_set_error("dvo_align_batch: intrinsics not set"); return DVO_ERR_STATE; }
     const size_t P0 = c->geom.P[0];
     const int B = c->cfg.max_batch;
-    for (int done = 0; done < count; done += B) {
+    const bool timing = c->timing;
+    c->timing = false;                                   // the per-stage timers synchronise; keep the pipeline asynchronous
+    int rc = DVO_OK;
+    for (int done = 0; done < count && rc == DVO_OK; done += B) {
         const int n = (count - done < B) ? count - done : B;
-        int rc;
-        if ((rc = dvo_set_frames(c, DVO_FRAME_REF, 0, n, ref_gray + P0 * done, ref_depth + P0 * done, DVO_MEM_HOST))) return rc;
-        if ((rc = dvo_set_frames(c, DVO_FRAME_NOW, 0, n, now_gray + P0 * done, now_depth ? now_depth + P0 * done : nullptr, DVO_MEM_HOST))) return rc;
-        if ((rc = dvo_set_initial_pose(c, 0, n, nullptr, DVO_MEM_HOST))) return rc;
-        if ((rc = dvo_build_pyramids(c, 0, n, 3))) return rc;
-        if ((rc = dvo_prepare(c, 0, n, 3))) return rc;
-        if ((rc = dvo_run(c, 0, n, p))) return rc;
-        if ((rc = dvo_get_poses(c, 0, n, R9T3 ? R9T3 + 12 * (size_t)done : nullptr, info ? info + done : nullptr, DVO_MEM_HOST))) return rc;
+        if ((rc = dvo_set_initial_pose(c, 0, n, nullptr, DVO_MEM_HOST))) break;
+        // Uploads run on their own stream, chunk by chunk, so that the copy of chunk k+1 overlaps the kernels of chunk k.
+        // Every chunk owns its slots, so no buffer is reused inside one pass over the context.
+        cudaError_t e = cudaEventRecord(c->ev_entry, c->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0);
+        if (e != cudaSuccess) { dvo_set_error("dvo_align_batch: %s", cudaGetErrorString(e)); rc = DVO_ERR_CUDA; break; }
+        int nchunks = (n + c->e2e_chunk - 1) / c->e2e_chunk;
+        if (nchunks > 16) nchunks = 16;
+        const int chunk = (n + nchunks - 1) / nchunks;
+        int k = 0;
+        for (int c0 = 0; c0 < n && rc == DVO_OK; c0 += chunk, ++k) {
+            const int m = (n - c0 < chunk) ? n - c0 : chunk;
+            const size_t src = P0 * (size_t)(done + c0);
+            const long long dst = lvl_at(c->geom, 0, c0);
+            e = cudaMemcpyAsync(c->gray[0] + dst, ref_gray + src, P0 * m, cudaMemcpyHostToDevice, c->copy_stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(c->depth[0] + dst, ref_depth + src, P0 * m * 2, cudaMemcpyHostToDevice, c->copy_stream);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(c->gray[1] + dst, now_gray + src, P0 * m, cudaMemcpyHostToDevice, c->copy_stream);
+            if (e == cudaSuccess && now_depth && c->depth[1])
+                e = cudaMemcpyAsync(c->depth[1] + dst, now_depth + src, P0 * m * 2, cudaMemcpyHostToDevice, c->copy_stream);
+            if (e == cudaSuccess) e = cudaEventRecord(c->ev_chunk[k], c->copy_stream);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->stream, c->ev_chunk[k], 0);
+            if (e != cudaSuccess) { dvo_set_error("dvo_align_batch: %s", cudaGetErrorString(e)); rc = DVO_ERR_CUDA; break; }
+            if ((rc = dvo_build_pyramids(c, c0, m, 3))) break;
+            if ((rc = dvo_prepare(c, c0, m, 3))) break;
+            if ((rc = dvo_run(c, c0, m, p))) break;
+        }
+        if (rc == DVO_OK)
+            rc = dvo_get_poses(c, 0, n, R9T3 ? R9T3 + 12 * (size_t)done : nullptr, info ? info + done : nullptr, DVO_MEM_HOST);
     }
-    return DVO_OK;
+    c->timing = timing;
+    return rc;
 }
 
 int dvo_level_dims(dvo_ctx* c, int level, int* w, int* h) {

@@ -30,7 +30,9 @@ struct dvo_ctx {
     PyrGeom geom;
     Intr K;
     bool haveK;
-    cudaStream_t own_stream, stream;
+    cudaStream_t own_stream, stream, copy_stream;
+    cudaEvent_t ev_chunk[16], ev_entry;
+    int e2e_chunk;           // frame pairs per upload/compute pipeline stage in dvo_align_batch
     int sm_count;
     size_t smem_optin;
 
@@ -39,7 +41,7 @@ struct dvo_ctx {
     uint8_t* edge[2];        // [frame] Canny edge maps 0/255
     uint16_t* gcol;          // now: EDT phase-1 column distances
     int32_t* d2;             // now: exact squared distance
-    float4* texel;           // now: {DTn, gx, gy, 0}
+    float4* texel;           // now: {DTn, gx, gy, getWeightOf(DTn)}
     float *ptsX, *ptsY, *ptsZ;   // ref: back-projected edge points, capacity P[l] per slot and level
     int* npts;               // [Bmax][L]
     unsigned* nedge;         // [2][Bmax][L]
