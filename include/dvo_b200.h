@@ -168,6 +168,69 @@ long long dvo_launch_count(dvo_ctx* ctx);
  * out[nseq][nframes][19] = R[9], T[3], px py pz qx qy qz qw. */
 int dvo_gop_compose(dvo_ctx* ctx, int nseq, int nframes, const int* kind, const double* rel, double* out, int mem);
 
+/* ================================================================================================================
+ * EPoseEstimator / PyramidalStorageStruct (dense photometric estimator, src/EPoseEstimator.cpp, src/PyramidalStorage.cpp)
+ * A separate context: BGR u8 (HWC) + depth u16 frames, INTER_AREA pyramids of up to 5 levels (the reference always
+ * builds levels 0..4, :88), reference-frame Jacobian.  `compat` = 1 reproduces the reference bug for bug (SURVEY.md
+ * Appendix C quirks: duplicated Jacobian column => singular A, row index paired with cx, unscaled fx, residual flattened
+ * row-major against column-major J rows, holes count as residuals): it yields the reference's A = J^T J and b = J^T eps
+ * entry for entry and takes no step.  `compat` = 0 is the corrected formulation with optional Huber weights
+ * (huber_k > 0, intensity units) and LM damping (lambda0 > 0; 0 = Gauss-Newton).
+ * ================================================================================================================ */
+typedef struct dvo_photo_ctx dvo_photo_ctx;
+
+typedef struct dvo_photo_config {
+    int width, height;   /* level-0 resolution; must be divisible by 2^(levels-1) */
+    int levels;          /* 1..5 */
+    int max_batch;
+    int device;
+} dvo_photo_config;
+
+typedef struct dvo_photo_info {
+    int status;          /* 0 ok; 1 normal equations not positive definite; 2 compat mode (singular A, no step taken) */
+    int iters_run;
+    int nreproj;         /* nReprojected of the last warp (src/EPoseEstimator.cpp:168) */
+    double sumsq_first, sumsq_last;   /* sum eps^2 at the first / last evaluation */
+    double visible;      /* nReprojected / (rows*cols) as a real fraction (the reference's integer division gives 0 or 1) */
+    double A[36];        /* normal matrix of the last accepted linearisation (compat: J^T J of the level) */
+    double b[6];         /* J^T (W) eps of the last accepted linearisation */
+} dvo_photo_info;
+
+/* which = selector for dvo_photo_get_level: the members of PyramidalStorageStruct (include/PyramidalStorage.h:63-77) */
+enum {
+    DVO_PHOTO_BGR = 0,        /* u8  [rows][cols][3]  im_r_color / im_color */
+    DVO_PHOTO_GRAY = 1,       /* u8  [rows][cols]     im_r / im             */
+    DVO_PHOTO_DEPTH = 2,      /* u16 [rows][cols]     dim_r / dim           */
+    DVO_PHOTO_X = 3, DVO_PHOTO_Y = 4, DVO_PHOTO_Z = 5,   /* f64 [rows][cols], metres (evaluate3d :439-477) */
+    DVO_PHOTO_J = 6,          /* f64 [rows*cols][6], row k = column-major pixel k (evaluateJacobian :398-415) */
+    DVO_PHOTO_GRAYVALS = 7, DVO_PHOTO_REDVALS = 8, DVO_PHOTO_GREENVALS = 9, DVO_PHOTO_BLUEVALS = 10   /* f64 [rows][cols] */
+};
+
+int dvo_photo_create(const dvo_photo_config* cfg, dvo_photo_ctx** out);     /* EPoseEstimator::EPoseEstimator */
+int dvo_photo_destroy(dvo_photo_ctx* ctx);
+int dvo_photo_set_stream(dvo_photo_ctx* ctx, void* cuda_stream);
+int dvo_photo_synchronize(dvo_photo_ctx* ctx);
+long long dvo_photo_launch_count(dvo_photo_ctx* ctx);
+/* EPoseEstimator::setCameraMatrix (src/EPoseEstimator.cpp:35-59): double intrinsics of level 0 */
+int dvo_photo_set_intrinsics(dvo_photo_ctx* ctx, double fx, double fy, double cx, double cy);
+/* setRefFrame / setNowFrame (:68-126): copy, BGR2GRAY at full resolution, INTER_AREA pyramids (setRefPyramidalImages :266-290,
+ * setPyramidalImages :216-260).  depth may be NULL for the now frame. */
+int dvo_photo_set_frames(dvo_photo_ctx* ctx, int frame, int first, int count, const uint8_t* bgr, const uint16_t* depth, int mem);
+/* evaluateJacobian + evaluate3d for every level and A = J^T J (:88-102, :229, :320-477) */
+int dvo_photo_prepare_ref(dvo_photo_ctx* ctx, int first, int count, int compat);
+/* initial (R, T) of estimate(); NULL = identity.  12 doubles per slot, host memory. */
+int dvo_photo_set_pose(dvo_photo_ctx* ctx, int first, int count, const double* R9T3);
+/* setPyramidalImages(level) + estimate(R, T) (:135-209): `iters` iterations (the reference hard-codes 3) */
+int dvo_photo_estimate(dvo_photo_ctx* ctx, int first, int count, int level, int iters, int compat, double huber_k, double lambda0);
+int dvo_photo_get_poses(dvo_photo_ctx* ctx, int first, int count, double* R9T3, dvo_photo_info* info);
+/* PyramidalStorageStruct::getLevel (src/PyramidalStorage.cpp:71-102): any stored member of one slot / level, host copy */
+int dvo_photo_get_level(dvo_photo_ctx* ctx, int slot, int frame, int level, int which, void* host_dst, size_t bytes, int compat);
+int dvo_photo_get_A(dvo_photo_ctx* ctx, int slot, int level, double* A36);
+/* one evaluation of estimate()'s loop body at a given pose (inspection): warped canvas (f64 [rows][cols], may be NULL),
+ * b = J^T (W) eps, A, sum eps^2, nReprojected, residual count */
+int dvo_photo_eval(dvo_photo_ctx* ctx, int slot, int level, const double* R9T3, int compat, double huber_k, double* b6, double* A36,
+                   double* sumsq, int* nreproj, int* nused, double* canvas);
+
 #ifdef __cplusplus
 }
 #endif

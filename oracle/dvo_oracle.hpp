@@ -696,4 +696,228 @@ struct Gop {
     }
 };
 
+
+// ======================================================================================================
+// EPoseEstimator (R12-R17): dense photometric estimator with a reference-frame Jacobian cache.
+// `compat` = true restates the reference bug for bug; `compat` = false is the
+// corrected formulation the north_star's "photometric + Huber + LM" configuration runs on.
+// Arrays are row-major [rows][cols]; the reference's column-major flattening (pixel k = c*rows + r,
+// src/EPoseEstimator.cpp:398-410) is applied where it matters (J row order, splat order, quirk 5).
+// ======================================================================================================
+namespace photo {
+
+struct Cam { double fx, fy, cx, cy; };        // double members (include/EPoseEstimator.h:56)
+
+struct RefLevel {
+    int rows = 0, cols = 0, level = 0;
+    std::vector<uint8_t> gray, bgr; std::vector<uint16_t> depth;
+    std::vector<double> X, Y, Z, gx, gy;      // row-major
+    std::vector<double> J;                    // [rows*cols][6], row k = column-major pixel k = c*rows + r
+    double A[36];
+};
+
+// setRefPyramidalImages (src/EPoseEstimator.cpp:266-290): INTER_AREA from full resolution; gray is converted at full
+// resolution first (:71) and then resized.
+inline void build_level_images(const uint8_t* bgr, const uint16_t* depth, int W, int H, int level, std::vector<uint8_t>& gray_l,
+                               std::vector<uint8_t>* bgr_l, std::vector<uint16_t>* depth_l) {
+    const int s = 1 << level, w = W / s, h = H / s;
+    std::vector<uint8_t> gray_full((size_t)W * H);
+    bgr2gray(bgr, (size_t)W * H, gray_full.data());
+    gray_l.resize((size_t)w * h); pyr_area(gray_full.data(), W, H, level, gray_l.data(), 1);
+    if (bgr_l) { bgr_l->resize((size_t)w * h * 3); pyr_area(bgr, W, H, level, bgr_l->data(), 3); }
+    if (depth_l && depth) { depth_l->resize((size_t)w * h); pyr_area(depth, W, H, level, depth_l->data(), 1); }
+}
+
+// filter2D with [0 -1 1] / its transpose, CV_64F, REFLECT_101 (:331-339): forward differences.
+inline void forward_gradients(const uint8_t* g, int rows, int cols, double* gx, double* gy) {
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            const int c1 = (c + 1 < cols) ? c + 1 : cols - 2, r1 = (r + 1 < rows) ? r + 1 : rows - 2;
+            gx[(size_t)r * cols + c] = (double)g[(size_t)r * cols + (cols > 1 ? c1 : c)] - (double)g[(size_t)r * cols + c];
+            gy[(size_t)r * cols + c] = (double)g[(size_t)(rows > 1 ? r1 : r) * cols + c] - (double)g[(size_t)r * cols + c];
+        }
+}
+
+// evaluate3d (:439-477) + evaluateJacobian (:320-430) + A = J^T J (:229) for one level.
+inline void build_ref_level(const uint8_t* bgr, const uint16_t* depth, int W, int H, int level, Cam K, bool compat, RefLevel& L) {
+    build_level_images(bgr, depth, W, H, level, L.gray, &L.bgr, &L.depth);
+    const int s = 1 << level; L.rows = H / s; L.cols = W / s; L.level = level;
+    const int rows = L.rows, cols = L.cols; const size_t N = (size_t)rows * cols;
+    L.gx.resize(N); L.gy.resize(N); L.X.resize(N); L.Y.resize(N); L.Z.resize(N); L.J.assign(N * 6, 0.0);
+    forward_gradients(L.gray.data(), rows, cols, L.gx.data(), L.gy.data());
+    const double sf = std::pow(2.0, -level);
+    const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy;
+    for (int r = 0; r < rows; ++r)
+        for (int c = 0; c < cols; ++c) {
+            const size_t i = (size_t)r * cols + c;
+            const double Zmm = (double)L.depth[i];
+            double X, Y, Z;
+            if (compat) {                                   // :466-472: row index pairs with cx, fx is not scaled
+                X = Zmm / fx * ((double)r - sf * cx); Y = Zmm / fy * ((double)c - sf * cy);
+                X = X / 1000.; Y = Y / 1000.; Z = Zmm / 1000.;
+            } else {
+                Z = Zmm / 1000.;
+                X = Z * ((double)c - sf * cx) / (sf * fx); Y = Z * ((double)r - sf * cy) / (sf * fy);
+            }
+            L.X[i] = X; L.Y[i] = Y; L.Z[i] = Z;
+            const double egx = L.gx[i], egy = L.gy[i];
+            double J1, J2, J3, J4, J5, J6;
+            if (compat) {
+                const double Z_inv = 1.0 / Z, Z2_inv = 1.0 / (Z * Z);                                   // :355-356
+                J1 = fx * egx * Z_inv;                                                                    // :390
+                J2 = fy * egy * Z_inv;
+                J3 = -fy * egy * Y * Z2_inv - fx * egx * X * Z2_inv;
+                J4 = egy * (-fy * Y * Y * Z2_inv - fy) - fx * egx * X * Y * Z2_inv;
+                J5 = egx * (fx * X * X * Z2_inv + fx) + fy * egy * X * Y * Z2_inv;
+                J6 = fy * egy * X * Z_inv - fx * egy * Y * Z_inv;                                         // quirk 2: egy twice
+            } else if (Zmm > 0.0) {
+                const double fxs = sf * fx, fys = sf * fy, Z_inv = 1.0 / Z;
+                J1 = fxs * egx * Z_inv; J2 = fys * egy * Z_inv; J3 = -(J1 * X + J2 * Y) * Z_inv;
+                J4 = J3 * Y - J2 * Z; J5 = J1 * Z - J3 * X; J6 = J2 * X - J1 * Y;
+            } else { J1 = J2 = J3 = J4 = J5 = J6 = 0.0; }
+            double* Jr = &L.J[((size_t)c * rows + r) * 6];                                               // column-major pixel order
+            Jr[0] = J1; Jr[1] = J2; Jr[2] = J3; Jr[3] = J4; Jr[4] = compat ? J4 : J5; Jr[5] = J6;        // quirk 1: col 5 = col 4
+        }
+    for (int k = 0; k < 36; ++k) L.A[k] = 0.0;
+    for (size_t k = 0; k < N; ++k) {                                                                      // A = J^T J (:229)
+        const double* Jr = &L.J[k * 6];
+        for (int a = 0; a < 6; ++a) for (int b2 = 0; b2 < 6; ++b2) L.A[6 * a + b2] += Jr[a] * Jr[b2];
+    }
+}
+
+// 4x4 rigid inverse as a general inverse would give for [R t; 0 1] (Tr.inverse(), :515): R^T, -R^T t.
+inline void rigid_inverse(const double* Tr, double* Ti) {
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Ti[4 * i + j] = Tr[4 * j + i];
+    for (int i = 0; i < 3; ++i) Ti[4 * i + 3] = -((Ti[4 * i] * Tr[3] + Ti[4 * i + 1] * Tr[7]) + Ti[4 * i + 2] * Tr[11]);
+    Ti[12] = Ti[13] = Ti[14] = 0.0; Ti[15] = 1.0;
+}
+
+// warpImage (:490-553): forward splat of the reference gray values, 2x2 block, last writer (largest column-major
+// pixel index) wins, holes stay 0.  `winner` (optional) receives the source pixel index per cell or -1.
+inline int warp_image(const RefLevel& L, Cam K, const double* Tr, bool compat, std::vector<double>& canvas, std::vector<int>* winner) {
+    const int rows = L.rows, cols = L.cols; const size_t N = (size_t)rows * cols;
+    double Ti[16]; rigid_inverse(Tr, Ti);
+    const double sf = std::pow(2.0, -L.level);
+    canvas.assign(N, 0.0); if (winner) winner->assign(N, -1);
+    int n = 0;
+    for (int c = 0; c < cols; ++c)
+        for (int r = 0; r < rows; ++r) {                      // column-major pixel order k = c*rows + r
+            const size_t i = (size_t)r * cols + c;
+            const double X = L.X[i], Y = L.Y[i], Z = L.Z[i];
+            if (!compat && !(L.depth[i] > 0)) continue;
+            const double px = ((Ti[0] * X + Ti[1] * Y) + Ti[2] * Z) + Ti[3] * 1.0;
+            const double py = ((Ti[4] * X + Ti[5] * Y) + Ti[6] * Z) + Ti[7] * 1.0;
+            const double pz = ((Ti[8] * X + Ti[9] * Y) + Ti[10] * Z) + Ti[11] * 1.0;
+            int tR, tC;                                       // destination row / column
+            if (compat) {                                     // :526-527: u is a ROW coordinate, fx unscaled
+                const double u = K.fx * px / pz + sf * K.cx, v = K.fy * py / pz + sf * K.cy;
+                tR = (int)std::floor(u); tC = (int)std::floor(v);
+            } else {
+                if (!(pz > 0.0)) continue;
+                const double uc = (sf * K.fx) * px / pz + sf * K.cx, vr = (sf * K.fy) * py / pz + sf * K.cy;
+                tC = (int)std::floor(uc); tR = (int)std::floor(vr);
+            }
+            if (tR >= 0 && tR < rows - 1 && tC >= 0 && tC < cols - 1) {
+                ++n;
+                const double gv = (double)L.gray[i]; const int k = c * rows + r;
+                for (int dr = 0; dr < 2; ++dr) for (int dc = 0; dc < 2; ++dc) {
+                    canvas[(size_t)(tR + dr) * cols + tC + dc] = gv; if (winner) (*winner)[(size_t)(tR + dr) * cols + tC + dc] = k;
+                }
+            }
+        }
+    return n;
+}
+
+struct IterOut { double b[6]; double A[36]; double sumsq; int nreproj; int nused; };
+
+inline double huber_w(double r, double k) { const double a = std::fabs(r); return a <= k ? 1.0 : k / a; }
+
+// One evaluation of estimate()'s loop body (:163-188): warp, eps = warped - now, b = J^T eps.
+// compat: eps flattened row-major against column-major J rows (quirk 5), holes count (eps = -I_now), unweighted, A = J^T J.
+// fixed : eps paired with its own pixel, holes skipped, optional Huber weights, A = J^T W J recomputed.
+inline void evaluate(const RefLevel& L, const uint8_t* now_gray, Cam K, const double* Tr, bool compat, double huber_k, IterOut& o,
+                     std::vector<double>* canvas_out = nullptr) {
+    const int rows = L.rows, cols = L.cols; const size_t N = (size_t)rows * cols;
+    std::vector<double> canvas; std::vector<int> win;
+    o.nreproj = warp_image(L, K, Tr, compat, canvas, &win);
+    for (int k = 0; k < 6; ++k) o.b[k] = 0.0; for (int k = 0; k < 36; ++k) o.A[k] = 0.0; o.sumsq = 0.0; o.nused = 0;
+    if (compat) {
+        for (size_t k = 0; k < N; ++k) {                      // flattened index k: eps row-major, J column-major
+            const double e = canvas[k] - (double)now_gray[k];
+            const double* Jr = &L.J[k * 6];
+            for (int a = 0; a < 6; ++a) o.b[a] += Jr[a] * e;
+            o.sumsq += e * e; ++o.nused;
+        }
+        std::memcpy(o.A, L.A, sizeof(o.A));
+    } else {
+        for (int c = 0; c < cols; ++c)
+            for (int r = 0; r < rows; ++r) {
+                const size_t i = (size_t)r * cols + c;
+                if (win[i] < 0) continue;
+                const double e = canvas[i] - (double)now_gray[i];
+                const double w = huber_k > 0 ? huber_w(e, huber_k) : 1.0;
+                const double* Jr = &L.J[(size_t)win[i] * 6];      // Jacobian row of the source pixel that owns this cell
+                for (int a = 0; a < 6; ++a) { const double jw = Jr[a] * w; o.b[a] += jw * e; for (int b2 = 0; b2 < 6; ++b2) o.A[6 * a + b2] += jw * Jr[b2]; }
+                o.sumsq += e * e; ++o.nused;
+            }
+    }
+    if (canvas_out) *canvas_out = canvas;
+}
+
+// exponentialMap (:570-597) -- no small-angle guard in the reference (quirk 8); guarded when !compat.
+inline void exp_map(const double* psi, bool compat, double* T4) {
+    const double* t = psi; const double* w = psi + 3;
+    const double th = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+    const double wx[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0}; double wx2[9]; mat3_mul(wx, wx, wx2);
+    double a, b, c;
+    if (!compat && th < 1e-8) { a = 1.0; b = 0.5; c = 1.0 / 6.0; }
+    else { a = std::sin(th) / th; b = (1.0 - std::cos(th)) / (th * th); c = (th - std::sin(th)) / (th * th * th); }
+    double R[9], V[9];
+    for (int i = 0; i < 9; ++i) { const double I = (i % 4 == 0) ? 1.0 : 0.0; R[i] = I + a * wx[i] + b * wx2[i]; V[i] = I + b * wx[i] + c * wx2[i]; }
+    double vt[3]; mat3_vec(V, t, vt);
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) T4[4 * i + j] = R[3 * i + j]; T4[4 * i + 3] = vt[i]; }
+    T4[12] = T4[13] = T4[14] = 0.0; T4[15] = 1.0;
+}
+
+inline void mat4_mul(const double* A, const double* B, double* C) {
+    double r[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r[4 * i + j] = ((A[4 * i] * B[j] + A[4 * i + 1] * B[4 + j]) + A[4 * i + 2] * B[8 + j]) + A[4 * i + 3] * B[12 + j];
+    std::memcpy(C, r, sizeof(r));
+}
+
+// estimate() (:135-209) in the corrected formulation: `iters` iterations of Tr <- Tr * exp(delta), delta = (A + lambda diag A)^-1 b,
+// LM accept/reject on sum eps^2 (lambda0 = 0 -> plain Gauss-Newton as the reference intends).  Returns visible fraction.
+// In compat mode A is singular by construction (quirk 1): the normal equations are produced but no step is taken.
+struct EstimateOut { double R[9], T[3]; double sumsq_first, sumsq_last; int iters_run; int status; double visible; };
+inline void estimate(const RefLevel& L, const uint8_t* now_gray, Cam K, const double* R0, const double* T0, int iters, bool compat,
+                     double huber_k, double lambda0, EstimateOut& out) {
+    double Tr[16] = {0};
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) Tr[4 * i + j] = R0[3 * i + j]; Tr[4 * i + 3] = T0[i]; }
+    Tr[15] = 1.0;
+    out.status = 0; out.iters_run = 0; out.sumsq_first = out.sumsq_last = 0; out.visible = 0;
+    double lambda = lambda0, accTr[16], accA[36], accb[6], accE = 0; bool have = false;
+    for (int itr = 0; itr < iters; ++itr) {
+        IterOut ev; evaluate(L, now_gray, K, Tr, compat, huber_k, ev);
+        out.visible = (double)ev.nreproj / ((double)L.rows * L.cols);
+        if (itr == 0) out.sumsq_first = ev.sumsq;
+        out.sumsq_last = ev.sumsq; out.iters_run = itr + 1;
+        if (compat) { out.status = 2; break; }               // singular normal equations (duplicated Jacobian column)
+        const bool accept = !have || lambda0 <= 0.0 || ev.sumsq <= accE;
+        if (accept) { std::memcpy(accTr, Tr, sizeof(accTr)); std::memcpy(accA, ev.A, sizeof(accA)); std::memcpy(accb, ev.b, sizeof(accb)); accE = ev.sumsq;
+                      if (have && lambda0 > 0.0) lambda = lambda * 0.1 < 1e-9 ? 1e-9 : lambda * 0.1; have = true; }
+        else { lambda *= 10.0; if (lambda > 1e8) break; std::memcpy(Tr, accTr, sizeof(accTr)); }
+        double Am[36], rhs[6], d[6];
+        for (int k = 0; k < 36; ++k) Am[k] = accA[k];
+        for (int k = 0; k < 6; ++k) { Am[7 * k] += (lambda0 > 0.0 ? lambda : 0.0) * accA[7 * k] + 1e-9; rhs[k] = accb[k]; }
+        if (!chol6_solve(Am, rhs, d)) { out.status = 1; break; }
+        // eps = warped - now with J = d(I_ref o warp)/d(psi): the update that decreases ||eps|| is Tr <- Tr * exp(-delta)
+        for (int k = 0; k < 6; ++k) d[k] = -d[k];
+        double E4[16]; exp_map(d, false, E4); mat4_mul(Tr, E4, Tr);
+    }
+    if (have && !compat) std::memcpy(Tr, accTr, sizeof(accTr));
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) out.R[3 * i + j] = Tr[4 * i + j]; out.T[i] = Tr[4 * i + 3]; }
+}
+
+}  // namespace photo
+
 }  // namespace orc

@@ -207,4 +207,49 @@ void orc_gop_replay(int n, const int* kind, const int* reason, const double* rel
     }
 }
 
+
+// ---- EPoseEstimator (photometric) ----
+static photo::RefLevel g_ref_level;   // scratch shared by the calls below (tests are single threaded)
+
+int orc_photo_build_ref_level(const uint8_t* bgr, const uint16_t* depth, int W, int H, int level, const double* K4, int compat,
+                              uint8_t* gray, uint8_t* bgr_l, uint16_t* depth_l, double* X, double* Y, double* Z, double* gx, double* gy,
+                              double* J, double* A36) {
+    photo::RefLevel& L = g_ref_level;
+    photo::build_ref_level(bgr, depth, W, H, level, photo::Cam{K4[0], K4[1], K4[2], K4[3]}, compat != 0, L);
+    const size_t N = (size_t)L.rows * L.cols;
+    if (gray) std::memcpy(gray, L.gray.data(), N);
+    if (bgr_l) std::memcpy(bgr_l, L.bgr.data(), N * 3);
+    if (depth_l) std::memcpy(depth_l, L.depth.data(), N * 2);
+    if (X) std::memcpy(X, L.X.data(), N * 8); if (Y) std::memcpy(Y, L.Y.data(), N * 8); if (Z) std::memcpy(Z, L.Z.data(), N * 8);
+    if (gx) std::memcpy(gx, L.gx.data(), N * 8); if (gy) std::memcpy(gy, L.gy.data(), N * 8);
+    if (J) std::memcpy(J, L.J.data(), N * 48);
+    if (A36) std::memcpy(A36, L.A, 288);
+    return (int)N;
+}
+
+void orc_photo_now_level(const uint8_t* bgr, int W, int H, int level, uint8_t* gray_l) {
+    std::vector<uint8_t> g; photo::build_level_images(bgr, nullptr, W, H, level, g, nullptr, nullptr);
+    std::memcpy(gray_l, g.data(), g.size());
+}
+
+// uses the level built by the last orc_photo_build_ref_level call
+void orc_photo_evaluate(const uint8_t* now_gray_l, const double* K4, const double* Tr16, int compat, double huber_k, double* b6, double* A36,
+                        double* sumsq, int* nreproj, int* nused, double* canvas) {
+    photo::IterOut o; std::vector<double> cv;
+    photo::evaluate(g_ref_level, now_gray_l, photo::Cam{K4[0], K4[1], K4[2], K4[3]}, Tr16, compat != 0, huber_k, o, canvas ? &cv : nullptr);
+    std::memcpy(b6, o.b, 48); std::memcpy(A36, o.A, 288); *sumsq = o.sumsq; *nreproj = o.nreproj; *nused = o.nused;
+    if (canvas) std::memcpy(canvas, cv.data(), cv.size() * 8);
+}
+
+void orc_photo_estimate(const uint8_t* now_gray_l, const double* K4, const double* R9, const double* T3, int iters, int compat, double huber_k,
+                        double lambda0, double* Rout, double* Tout, double* sumsq_first, double* sumsq_last, int* iters_run, int* status,
+                        double* visible) {
+    photo::EstimateOut o;
+    photo::estimate(g_ref_level, now_gray_l, photo::Cam{K4[0], K4[1], K4[2], K4[3]}, R9, T3, iters, compat != 0, huber_k, lambda0, o);
+    std::memcpy(Rout, o.R, 72); std::memcpy(Tout, o.T, 24); *sumsq_first = o.sumsq_first; *sumsq_last = o.sumsq_last; *iters_run = o.iters_run;
+    *status = o.status; *visible = o.visible;
+}
+
+void orc_photo_exp_map(const double* psi, int compat, double* T16) { photo::exp_map(psi, compat != 0, T16); }
+
 }  // extern "C"

@@ -24,6 +24,15 @@ class PairInfo(C.Structure):
                 ("visible_ratio", C.c_float * MAX_LEVELS), ("laplacian_b", C.c_float)]
 
 
+class PhotoConfig(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("levels", C.c_int), ("max_batch", C.c_int), ("device", C.c_int)]
+
+
+class PhotoInfo(C.Structure):
+    _fields_ = [("status", C.c_int), ("iters_run", C.c_int), ("nreproj", C.c_int), ("sumsq_first", C.c_double),
+                ("sumsq_last", C.c_double), ("visible", C.c_double), ("A", C.c_double * 36), ("b", C.c_double * 6)]
+
+
 # every symbol include/dvo_b200.h declares
 SYMBOLS = [
     "dvo_last_error", "dvo_device_count", "dvo_create", "dvo_destroy", "dvo_set_stream", "dvo_synchronize",
@@ -31,6 +40,9 @@ SYMBOLS = [
     "dvo_set_initial_pose", "dvo_run", "dvo_get_poses", "dvo_align_batch", "dvo_level_dims", "dvo_get_level_buffer",
     "dvo_get_points", "dvo_eval_normal_equations", "dvo_get_trace", "dvo_enable_timing", "dvo_get_stage_ms",
     "dvo_launch_count", "dvo_gop_compose",
+    "dvo_photo_create", "dvo_photo_destroy", "dvo_photo_set_stream", "dvo_photo_synchronize", "dvo_photo_launch_count",
+    "dvo_photo_set_intrinsics", "dvo_photo_set_frames", "dvo_photo_prepare_ref", "dvo_photo_set_pose", "dvo_photo_estimate",
+    "dvo_photo_get_poses", "dvo_photo_get_level", "dvo_photo_get_A", "dvo_photo_eval",
 ]
 
 _lib = None
@@ -74,6 +86,22 @@ def load(build_if_missing=True):
     lib.dvo_enable_timing.argtypes = [C.c_void_p, C.c_int]
     lib.dvo_get_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
     lib.dvo_gop_compose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.dvo_photo_create.argtypes = [C.POINTER(PhotoConfig), C.POINTER(C.c_void_p)]
+    lib.dvo_photo_destroy.argtypes = [C.c_void_p]
+    lib.dvo_photo_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dvo_photo_synchronize.argtypes = [C.c_void_p]
+    lib.dvo_photo_launch_count.restype = C.c_longlong
+    lib.dvo_photo_launch_count.argtypes = [C.c_void_p]
+    lib.dvo_photo_set_intrinsics.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.dvo_photo_set_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.dvo_photo_prepare_ref.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.dvo_photo_set_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dvo_photo_estimate.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+    lib.dvo_photo_get_poses.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.dvo_photo_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+    lib.dvo_photo_get_A.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dvo_photo_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
+                                   C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
     _lib = lib
     return lib
 

@@ -16,11 +16,6 @@ SYNTH_LIB = os.path.join(PKG, "synth", "libdvo_synth.so")
 HOST_DIR = os.path.join(PKG, "host")
 HOST_LIB = os.path.join(PKG, "libdvo_host.so")
 
-NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC,-ffp-contract=off", "-shared", "-cudart", "static",
-]
-
 
 def _nvcc():
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
@@ -43,11 +38,26 @@ def cuda_sources():
     return srcs, deps
 
 
+# per-file extra flags: the photometric path mirrors the oracle's fp64 operation order, so no FMA contraction there
+PER_FILE_FLAGS = {"photometric.cu": ["-fmad=false"]}
+COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off"]
+OBJ_DIR = os.path.join(PKG, "build")
+
+
 def build_cuda(force=False, verbose=False):
     srcs, deps = cuda_sources()
-    if force or _stale(LIB, srcs + deps):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + srcs
-        subprocess.check_call(cmd, cwd=CSRC)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs, relink = [], force or not os.path.exists(LIB)
+    for src in srcs:
+        name = os.path.basename(src)
+        obj = os.path.join(OBJ_DIR, name[:-3] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + deps):
+            cmd = [_nvcc()] + COMPILE_FLAGS + PER_FILE_FLAGS.get(name, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+            subprocess.check_call(cmd, cwd=CSRC)
+            relink = True
+    if relink or _stale(LIB, objs):
+        subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", LIB] + objs)
     return LIB
 
 

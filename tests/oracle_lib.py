@@ -369,3 +369,65 @@ def gop_replay(kind, reason, rel):
     lib().orc_gop_replay(n, _p(kind, C.c_int32), _p(reason, C.c_int32), _p(rel, C.c_double), _p(out, C.c_double),
                          _p(is_key, C.c_int32), _p(r_out, C.c_int32))
     return out, is_key, r_out
+
+
+# ---------------------------------------------------------------- EPoseEstimator (photometric) oracle
+def photo_build_ref_level(bgr, depth, level, K=K640, compat=True):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    depth = np.ascontiguousarray(depth, np.uint16)
+    H, W = depth.shape
+    s = 1 << level
+    h, w = H // s, W // s
+    K4 = np.array(K, np.float64)
+    o = {"gray": np.empty((h, w), np.uint8), "bgr": np.empty((h, w, 3), np.uint8), "depth": np.empty((h, w), np.uint16),
+         "X": np.empty((h, w)), "Y": np.empty((h, w)), "Z": np.empty((h, w)), "gx": np.empty((h, w)), "gy": np.empty((h, w)),
+         "J": np.empty((h * w, 6)), "A": np.empty((6, 6))}
+    lib().orc_photo_build_ref_level(_p(bgr, C.c_uint8), _p(depth, C.c_uint16), W, H, level, _p(K4, C.c_double), int(compat),
+                                    _p(o["gray"], C.c_uint8), _p(o["bgr"], C.c_uint8), _p(o["depth"], C.c_uint16), _p(o["X"], C.c_double),
+                                    _p(o["Y"], C.c_double), _p(o["Z"], C.c_double), _p(o["gx"], C.c_double), _p(o["gy"], C.c_double),
+                                    _p(o["J"], C.c_double), _p(o["A"], C.c_double))
+    return o
+
+
+def photo_now_level(bgr, level):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    H, W = bgr.shape[:2]
+    s = 1 << level
+    out = np.empty((H // s, W // s), np.uint8)
+    lib().orc_photo_now_level(_p(bgr, C.c_uint8), W, H, level, _p(out, C.c_uint8))
+    return out
+
+
+def _tr16(R, T):
+    Tr = np.eye(4)
+    Tr[:3, :3] = np.asarray(R, np.float64).reshape(3, 3)
+    Tr[:3, 3] = np.asarray(T, np.float64).reshape(3)
+    return np.ascontiguousarray(Tr)
+
+
+def photo_evaluate(now_gray_l, R, T, K=K640, compat=True, huber_k=0.0, want_canvas=False):
+    """Uses the level built by the last photo_build_ref_level call."""
+    now_gray_l = np.ascontiguousarray(now_gray_l, np.uint8)
+    K4 = np.array(K, np.float64)
+    Tr = _tr16(R, T)
+    b, A = np.empty(6), np.empty((6, 6))
+    sumsq, nre, nus = C.c_double(), C.c_int(), C.c_int()
+    cv = np.empty(now_gray_l.shape, np.float64) if want_canvas else None
+    lib().orc_photo_evaluate(_p(now_gray_l, C.c_uint8), _p(K4, C.c_double), _p(Tr, C.c_double), int(compat), C.c_double(huber_k),
+                             _p(b, C.c_double), _p(A, C.c_double), C.byref(sumsq), C.byref(nre), C.byref(nus), _p(cv, C.c_double))
+    return {"b": b, "A": A, "sumsq": sumsq.value, "nreproj": nre.value, "nused": nus.value, "canvas": cv}
+
+
+def photo_estimate(now_gray_l, R0, T0, iters, K=K640, compat=False, huber_k=0.0, lambda0=0.0):
+    now_gray_l = np.ascontiguousarray(now_gray_l, np.uint8)
+    K4 = np.array(K, np.float64)
+    R0 = np.ascontiguousarray(R0, np.float64).reshape(9)
+    T0 = np.ascontiguousarray(T0, np.float64).reshape(3)
+    R, T = np.empty(9), np.empty(3)
+    s0, s1, vis = C.c_double(), C.c_double(), C.c_double()
+    ir, st = C.c_int(), C.c_int()
+    lib().orc_photo_estimate(_p(now_gray_l, C.c_uint8), _p(K4, C.c_double), _p(R0, C.c_double), _p(T0, C.c_double), iters, int(compat),
+                             C.c_double(huber_k), C.c_double(lambda0), _p(R, C.c_double), _p(T, C.c_double), C.byref(s0), C.byref(s1),
+                             C.byref(ir), C.byref(st), C.byref(vis))
+    return {"R": R.reshape(3, 3), "T": T, "sumsq_first": s0.value, "sumsq_last": s1.value, "iters_run": ir.value, "status": st.value,
+            "visible": vis.value}
