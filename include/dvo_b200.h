@@ -112,8 +112,9 @@ int dvo_set_intrinsics(dvo_ctx* ctx, float fx, float fy, float cx, float cy);
  * (src/SolveDVO.cpp:490-614).  Full-resolution images; the pyramid is built by dvo_build_pyramids.
  * depth may be NULL for the now frame (the edge solver never reads it). */
 int dvo_set_frames(dvo_ctx* ctx, int frame, int first, int count, const uint8_t* gray, const uint16_t* depth, int mem);
-/* SolveDVO::setPrevFrameAsRefFrame (src/SolveDVO.cpp:561-584): the now frame of every slot becomes its
- * reference frame (pyramid, edges and depth are moved on the device; needs keep_now_depth). */
+/* SolveDVO::setPrevFrameAsRefFrame (src/SolveDVO.cpp:561-584): the PREVIOUS now frame of every slot (p_now_*, kept on the
+ * device by dvo_set_frames(NOW) when keep_now_depth = 1) becomes its reference frame's level 0; follow with
+ * dvo_build_pyramids(.., 1) and dvo_prepare(.., 1) as the reference does. */
 int dvo_promote_now_to_ref(dvo_ctx* ctx, int first, int count);
 
 /* pyramid construction (src/camTopic2PublisherPyD.cpp:338-348): levels 1.. from level 0, both frames */
@@ -139,6 +140,13 @@ int dvo_get_poses(dvo_ctx* ctx, int first, int count, double* R9T3, dvo_pair_inf
 int dvo_align_batch(dvo_ctx* ctx, int count, const uint8_t* ref_gray, const uint16_t* ref_depth,
                     const uint8_t* now_gray, const uint16_t* now_depth, const dvo_solver_params* params,
                     double* R9T3, dvo_pair_info* info);
+
+/* SolveDVO::loop (src/SolveDVO.cpp:1896-2373) for nseq independent sequences in lock step (slot = sequence).
+ * gray / depth: [nseq][nframes][H][W] host buffers.  rel_poses [nseq][nframes][12] (relative to the current key frame),
+ * kind [nseq][nframes] (1 key frame, 0 ordinary, 2 ordinary promoted by updateMostRecentToKeyFrame), global_poses
+ * [nseq][nframes][19] (may be NULL) as dvo_gop_compose writes them.  Needs keep_now_depth = 1. */
+int dvo_run_sequences(dvo_ctx* ctx, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* params,
+                      int keyframe_every, double* rel_poses, int* kind, double* global_poses);
 
 /* ---- inspection (parity tests; not on the hot path) ---- */
 int dvo_level_dims(dvo_ctx* ctx, int level, int* w, int* h);

@@ -114,6 +114,18 @@ class BatchAligner:
                                        _ptr(poses), C.cast(info, C.c_void_p) if want_info else None), "dvo_align_batch")
         return poses, info
 
+    def run_sequences(self, gray, depth, params, keyframe_every=5):
+        """SolveDVO::loop over nseq sequences in lock step.  gray/depth: (nseq, nframes, H, W)."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        nseq, nframes = gray.shape[:2]
+        rel = np.empty((nseq, nframes, 12), np.float64)
+        kind = np.empty((nseq, nframes), np.int32)
+        glob = np.empty((nseq, nframes, 19), np.float64)
+        check(self.lib.dvo_run_sequences(self.h, nseq, nframes, _ptr(gray), _ptr(depth), C.byref(params), keyframe_every, _ptr(rel),
+                                         _ptr(kind), _ptr(glob)), "dvo_run_sequences")
+        return rel, kind, glob
+
     def level_dims(self, level):
         w, h = C.c_int(), C.c_int()
         check(self.lib.dvo_level_dims(self.h, level, C.byref(w), C.byref(h)), "dvo_level_dims")

@@ -97,7 +97,8 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     auto A = [&](int r) { if (rc == DVO_OK) rc = r; };
     for (int f = 0; f < 2; ++f) { A(dalloc(&c->gray[f], T)); A(dalloc(&c->edge[f], T)); }
     A(dalloc(&c->depth[0], T));
-    if (cfg->keep_now_depth) A(dalloc(&c->depth[1], T));
+    if (cfg->keep_now_depth) { A(dalloc(&c->depth[1], T)); A(dalloc(&c->prev_gray, B * (size_t)g.P[0])); A(dalloc(&c->prev_depth, B * (size_t)g.P[0])); }
+    c->now_valid = (unsigned char*)calloc(B, 1); c->prev_valid = (unsigned char*)calloc(B, 1);
     A(dalloc(&c->gcol, T)); A(dalloc(&c->d2, T)); A(dalloc(&c->texel, T));
     A(dalloc(&c->ptsX, T)); A(dalloc(&c->ptsY, T)); A(dalloc(&c->ptsZ, T));
     A(dalloc(&c->npts, B * g.L)); A(dalloc(&c->nedge, 2 * B * g.L)); A(dalloc(&c->maxd2, B * g.L));
@@ -130,7 +131,8 @@ int dvo_destroy(dvo_ctx* c) {
     for (int f = 0; f < 2; ++f) { cudaFree(c->gray[f]); cudaFree(c->depth[f]); cudaFree(c->edge[f]); }
     cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ);
     cudaFree(c->npts); cudaFree(c->nedge); cudaFree(c->maxd2); cudaFree(c->pose0); cudaFree(c->pose); cudaFree(c->info);
-    cudaFree(c->trace); cudaFree(c->bitmap_scratch);
+    cudaFree(c->trace); cudaFree(c->bitmap_scratch); cudaFree(c->prev_gray); cudaFree(c->prev_depth);
+    free(c->now_valid); free(c->prev_valid);
     if (c->h_pose) cudaFreeHost(c->h_pose);
     if (c->h_info) cudaFreeHost(c->h_info);
     if (c->ev_a) cudaEventDestroy(c->ev_a);
@@ -167,6 +169,19 @@ int dvo_set_frames(dvo_ctx* c, int frame, int first, int count, const uint8_t* g
     StageTimer t(c, DVO_STAGE_H2D);
     const size_t P0 = c->geom.P[0];
     const cudaMemcpyKind k = mem == DVO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (frame == DVO_FRAME_NOW && c->prev_gray) {
+        // setRcvdFrameAsNowFrame keeps the outgoing now frame as p_now_* (src/SolveDVO.cpp:594-600)
+        bool any = false, all = true;
+        for (int i = first; i < first + count; ++i) { any |= c->now_valid[i] != 0; all &= c->now_valid[i] != 0; }
+        if (any && !all) { dvo_set_error("dvo_set_frames: slots [%d,%d) mix first and subsequent now frames", first, first + count); return DVO_ERR_STATE; }
+        if (all && count > 0) {
+            DVO_CUDA(cudaMemcpyAsync(c->prev_gray + P0 * first, c->gray[1] + lvl_at(c->geom, 0, first), P0 * count, cudaMemcpyDeviceToDevice, c->stream));
+            DVO_CUDA(cudaMemcpyAsync(c->prev_depth + P0 * first, c->depth[1] + lvl_at(c->geom, 0, first), P0 * count * 2, cudaMemcpyDeviceToDevice, c->stream));
+            for (int i = first; i < first + count; ++i) c->prev_valid[i] = 1;
+        }
+        if (!depth) { dvo_set_error("dvo_set_frames: a context with keep_now_depth needs the now frame's depth"); return DVO_ERR_ARG; }
+    }
+    if (frame == DVO_FRAME_NOW) for (int i = first; i < first + count; ++i) c->now_valid[i] = 1;
     DVO_CUDA(cudaMemcpyAsync(c->gray[frame] + lvl_at(c->geom, 0, first), gray, P0 * count, k, c->stream));
     if (depth && c->depth[frame])
         DVO_CUDA(cudaMemcpyAsync(c->depth[frame] + lvl_at(c->geom, 0, first), depth, P0 * count * sizeof(uint16_t), k, c->stream));
@@ -273,6 +288,57 @@ int dvo_align_batch(dvo_ctx* c, int count, const uint8_t* ref_gray, const uint16
     }
     c->timing = timing;
     return rc;
+}
+
+// SolveDVO::loop (src/SolveDVO.cpp:1896-2373) for `nseq` independent sequences processed in lock step (slot = sequence):
+// frame 0 is the first reference / key frame (:2013-2017); every later frame is aligned against the current reference with
+// the previous frame's pose as the initial guess (:1931-1932, :2097-2104); when (n - lastRefFrame) == keyframe_every the
+// previous frame becomes the reference, the pose is reset and the frame is solved again (:2155-2233).  The solve the
+// reference performs against the outgoing key frame right before a switch is discarded there (:2210-2227) and is skipped.
+int dvo_run_sequences(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* p,
+                      int keyframe_every, double* rel_poses, int* kind, double* global_poses) {
+    if (!c || nseq < 1 || nseq > c->cfg.max_batch || nframes < 1 || !gray || !depth || !p || !rel_poses || !kind) { dvo_set_error("dvo_run_sequences: bad argument"); return DVO_ERR_ARG; }
+    if (!c->prev_gray) { dvo_set_error("dvo_run_sequences: create the context with keep_now_depth = 1"); return DVO_ERR_STATE; }
+    if (!c->haveK) { dvo_set_error("dvo_run_sequences: intrinsics not set"); return DVO_ERR_STATE; }
+    const size_t P0 = c->geom.P[0];
+    int rc;
+    auto upload = [&](int frame, int t) -> int {          // frame t of every sequence -> slots [0, nseq)
+        for (int s = 0; s < nseq; ++s) {
+            const size_t src = ((size_t)s * nframes + t) * P0;
+            int r = dvo_set_frames(c, frame, s, 1, gray + src, depth + src, DVO_MEM_HOST);
+            if (r) return r;
+        }
+        return DVO_OK;
+    };
+    for (int s = 0; s < nseq; ++s) { c->now_valid[s] = 0; c->prev_valid[s] = 0; }
+    if ((rc = upload(DVO_FRAME_REF, 0))) return rc;
+    if ((rc = dvo_build_pyramids(c, 0, nseq, 1))) return rc;
+    if ((rc = dvo_prepare(c, 0, nseq, 1))) return rc;
+    std::vector<double> ident((size_t)12 * nseq, 0.0);
+    for (int s = 0; s < nseq; ++s) { ident[12 * (size_t)s] = ident[12 * (size_t)s + 4] = ident[12 * (size_t)s + 8] = 1.0; }
+    std::vector<double> cur(ident);
+    for (int s = 0; s < nseq; ++s) { memcpy(rel_poses + ((size_t)s * nframes) * 12, ident.data(), 96); kind[(size_t)s * nframes] = 1; }   // pushAsKeyFrame(0, 1, I, 0)
+    int lastRef = 0;
+    for (int t = 1; t < nframes; ++t) {
+        if ((rc = upload(DVO_FRAME_NOW, t))) return rc;                                   // setRcvdFrameAsNowFrame
+        if ((rc = dvo_build_pyramids(c, 0, nseq, 2))) return rc;
+        if ((rc = dvo_prepare(c, 0, nseq, 2))) return rc;
+        const bool switch_ref = (t - lastRef) == keyframe_every && lastRef != t - 1;
+        if (switch_ref) {
+            lastRef = t - 1;
+            if ((rc = dvo_promote_now_to_ref(c, 0, nseq))) return rc;                     // setPrevFrameAsRefFrame
+            if ((rc = dvo_build_pyramids(c, 0, nseq, 1))) return rc;
+            if ((rc = dvo_prepare(c, 0, nseq, 1))) return rc;                             // computeDistTransfrmOfRef + preProcessRefFrame
+            for (int s = 0; s < nseq; ++s) kind[(size_t)s * nframes + t - 1] = 2;         // gop.updateMostRecentToKeyFrame
+            cur = ident;                                                                  // cR_64 = I, cT_64 = 0
+        }
+        if ((rc = dvo_set_initial_pose(c, 0, nseq, cur.data(), DVO_MEM_HOST))) return rc;
+        if ((rc = dvo_run(c, 0, nseq, p))) return rc;
+        if ((rc = dvo_get_poses(c, 0, nseq, cur.data(), nullptr, DVO_MEM_HOST))) return rc;
+        for (int s = 0; s < nseq; ++s) { memcpy(rel_poses + ((size_t)s * nframes + t) * 12, cur.data() + 12 * (size_t)s, 96); kind[(size_t)s * nframes + t] = 0; }   // pushAsOrdinaryFrame
+    }
+    if (global_poses) return dvo_gop_compose(c, nseq, nframes, kind, rel_poses, global_poses, DVO_MEM_HOST);
+    return DVO_OK;
 }
 
 int dvo_level_dims(dvo_ctx* c, int level, int* w, int* h) {

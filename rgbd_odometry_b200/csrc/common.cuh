@@ -38,6 +38,10 @@ struct dvo_ctx {
 
     uint8_t* gray[2];        // [frame] gray pyramid
     uint16_t* depth[2];      // [frame] depth pyramid (now: only if keep_now_depth)
+    uint8_t* prev_gray;      // level-0 copy of the previous now frame (p_now_framemono, src/SolveDVO.cpp:594-600); keep_now_depth only
+    uint16_t* prev_depth;    // p_now_depth
+    unsigned char* now_valid;   // host: slot has received a now frame
+    unsigned char* prev_valid;  // host: slot has a previous now frame
     uint8_t* edge[2];        // [frame] Canny edge maps 0/255
     uint16_t* gcol;          // now: EDT phase-1 column distances
     int32_t* d2;             // now: exact squared distance

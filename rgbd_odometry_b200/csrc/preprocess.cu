@@ -702,15 +702,17 @@ int launch_normgrad(dvo_ctx* c, int first, int count) {
 }
 
 // =====================================================================================================
-// setPrevFrameAsRefFrame (src/SolveDVO.cpp:561-584): move the now frame's pyramid into the reference slot.
+// setPrevFrameAsRefFrame (src/SolveDVO.cpp:561-584): im_r = p_now_framemono, dim_r = p_now_depth.  The previous now
+// frame's level-0 images (saved by dvo_set_frames) become the reference frame's level 0; the caller rebuilds the
+// reference pyramid, edges and point list exactly as the reference does (computeDistTransfrmOfRef, preProcessRefFrame).
 // =====================================================================================================
 int launch_promote(dvo_ctx* c, int first, int count) {
     const PyrGeom& g = c->geom;
-    if (!c->depth[DVO_FRAME_NOW]) { dvo_set_error("promote: context was created without keep_now_depth"); return DVO_ERR_STATE; }
-    for (int l = 0; l < g.L; ++l) {
-        const long long o = lvl_at(g, l, first); const size_t n = (size_t)count * g.P[l];
-        DVO_CUDA(cudaMemcpyAsync(c->gray[0] + o, c->gray[1] + o, n, cudaMemcpyDeviceToDevice, c->stream));
-        DVO_CUDA(cudaMemcpyAsync(c->depth[0] + o, c->depth[1] + o, n * 2, cudaMemcpyDeviceToDevice, c->stream));
-    }
+    if (!c->prev_gray) { dvo_set_error("promote: context was created without keep_now_depth"); return DVO_ERR_STATE; }
+    for (int i = first; i < first + count; ++i)
+        if (!c->prev_valid[i]) { dvo_set_error("promote: slot %d has no previous now frame (isPrevFrameAvailable)", i); return DVO_ERR_STATE; }
+    const size_t P0 = g.P[0];
+    DVO_CUDA(cudaMemcpyAsync(c->gray[0] + lvl_at(g, 0, first), c->prev_gray + P0 * first, P0 * count, cudaMemcpyDeviceToDevice, c->stream));
+    DVO_CUDA(cudaMemcpyAsync(c->depth[0] + lvl_at(g, 0, first), c->prev_depth + P0 * first, P0 * count * 2, cudaMemcpyDeviceToDevice, c->stream));
     return DVO_OK;
 }

@@ -1,0 +1,65 @@
+"""Consecutive-pair odometry (SolveDVO::loop, src/SolveDVO.cpp:1896-2373): warm start, key frame every 5 frames = the
+previous frame, pose reset + re-solve, GOP composition -- GPU (dvo_run_sequences) against the same schedule driven
+through the CPU oracle."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import rgbd_odometry_b200 as dvo
+
+pytestmark = pytest.mark.gpu
+
+
+def rot_angle(Ra, Rb):
+    return float(np.arccos(np.clip((np.trace(Ra.T @ Rb) - 1) / 2, -1, 1)))
+
+
+def oracle_sequence(gray, depth, levels, iters, K, keyframe_every=5):
+    n = gray.shape[0]
+    rel = np.zeros((n, 12)); kind = np.zeros(n, np.int32)
+    rel[0, [0, 4, 8]] = 1.0; kind[0] = 1
+    ref = 0; last_ref = 0
+    R, T = np.eye(3), np.zeros(3)
+    for t in range(1, n):
+        if (t - last_ref) == keyframe_every and last_ref != t - 1:
+            last_ref = t - 1; ref = t - 1; kind[t - 1] = 2
+            R, T = np.eye(3), np.zeros(3)
+        o = O.align_pair(gray[ref], depth[ref], gray[t], levels, iters, K, R0=R, T0=T)
+        R, T = o["R"], o["T"]
+        rel[t, :9] = R.reshape(9); rel[t, 9:] = T
+    glob, is_key, _ = O.gop_replay(kind, np.full(n, 5, np.int32), rel)
+    return rel, kind, glob
+
+
+@pytest.mark.parametrize("W,H,L,K", [(320, 240, 4, (262.5, 262.5, 159.5, 119.5))])
+def test_sequences_match_oracle_schedule(W, H, L, K):
+    nseq, nframes = 3, 12
+    seqs = [O.synth_sequence(70 + s, nframes, W, H, K, max_angle_deg=0.4, max_trans_m=0.008) for s in range(nseq)]
+    gray = np.stack([s[0] for s in seqs]); depth = np.stack([s[1] for s in seqs])
+    iters = (8, 8, 8, 8)
+    al = dvo.BatchAligner(W, H, L, max_batch=nseq, keep_now_depth=True, intrinsics=K)
+    rel, kind, glob = al.run_sequences(gray, depth, dvo.solver_params(iters=iters))
+    for s in range(nseq):
+        orel, okind, oglob = oracle_sequence(gray[s], depth[s], L, iters, K)
+        assert np.array_equal(kind[s], okind), (kind[s], okind)
+        assert list(np.nonzero(okind == 2)[0]) == [4, 8]
+        for t in range(nframes):
+            assert rot_angle(rel[s, t, :9].reshape(3, 3), orel[t, :9].reshape(3, 3)) < 1e-5
+            assert np.linalg.norm(rel[s, t, 9:] - orel[t, 9:]) < 1e-5
+            assert rot_angle(glob[s, t, :9].reshape(3, 3), oglob[t, :9].reshape(3, 3)) < 1e-5
+            assert np.linalg.norm(glob[s, t, 9:12] - oglob[t, 9:12]) < 1e-5
+    # global poses follow the true trajectory (loose: the estimator's own accuracy, not a parity bound)
+    Rw, Tw = seqs[0][2], seqs[0][3]
+    err = np.linalg.norm(glob[0, -1, 9:12] - Tw[-1])
+    assert err < np.linalg.norm(Tw[-1]) + 0.05
+    al.close()
+
+
+def test_promote_requires_a_previous_now_frame():
+    al = dvo.BatchAligner(160, 120, 2, max_batch=1, keep_now_depth=True, intrinsics=(131.25, 131.25, 79.5, 59.5))
+    with pytest.raises(dvo.DvoError, match="previous now frame"):
+        al.promote_now_to_ref(1)
+    al2 = dvo.BatchAligner(160, 120, 2, max_batch=1, keep_now_depth=False)
+    with pytest.raises(dvo.DvoError, match="keep_now_depth"):
+        al2.promote_now_to_ref(1)
+    al.close(); al2.close()
