@@ -1,0 +1,163 @@
+#include "SolveDVO.h"
+
+#include <cassert>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <sstream>
+#include <string>
+
+SolveDVO::SolveDVO(int width, int height, int levels)
+    : fx(0), fy(0), cx(0), cy(0), isCameraIntrinsicsAvailable(false), isFrameAvailable(false), isRefFrameAvailable(false),
+      isNowFrameAvailable(false), isPrevFrameAvailable(false), nFrame(0), lastRefFrame(0), ctx_(nullptr), width_(width), height_(height),
+      levels_(levels) {
+    ratio_of_visible_pts_thresh = 0.8f; laplacianThreshExitCond = 3.0f;                 // src/SolveDVO.cpp:22-23
+    psiNormTerminationThreshold = 1.0E-7f; trustRegionHyperSphereRadius = 0.003f;       // :24-25
+    for (int i = 0; i < levels; ++i) iterationsConfig.push_back(50);                    // :30-33
+    std::memset(&solver, 0, sizeof(solver));
+    solver.solver = DVO_SOLVER_SUBGRAD_REF; solver.jacobian = DVO_JAC_REFERENCE; solver.weight = DVO_WEIGHT_REF_CAUCHY;
+    solver.arithmetic = DVO_ARITH_EXACT; solver.huber_k = 1.345f; solver.lm_lambda0 = 1e-3;
+    std::memset(&lastInfo, 0, sizeof(lastInfo));
+    dvo_config cfg = {width, height, levels, 1, 0, /*keep_now_depth*/ 1, /*trace_iters*/ 128};
+    const int rc = dvo_create(&cfg, &ctx_);
+    if (rc != DVO_OK) { std::fprintf(stderr, "SolveDVO: %s\n", dvo_last_error()); std::abort(); }   // no CPU fallback
+}
+SolveDVO::~SolveDVO() { if (ctx_) dvo_destroy(ctx_); }
+
+void SolveDVO::check(int rc, const char* what) {
+    if (rc != DVO_OK) { std::fprintf(stderr, "SolveDVO::%s: %s\n", what, dvo_last_error()); assert(rc == DVO_OK); std::abort(); }
+}
+
+void SolveDVO::setCameraMatrix(const char* calibFile) {
+    std::ifstream f(calibFile);
+    if (!f.is_open()) { std::fprintf(stderr, "[SolveDVO::setCameraMatrix] Error opening camera params file : %s\n", calibFile); return; }   // :94-99
+    std::stringstream ss; ss << f.rdbuf(); const std::string s = ss.str();
+    size_t p = s.find("<cameraMatrix"); if (p == std::string::npos) return;
+    p = s.find("<data>", p); if (p == std::string::npos) return;
+    std::stringstream d(s.substr(p + 6));
+    double v[9]; for (int i = 0; i < 9; ++i) if (!(d >> v[i])) return;
+    setIntrinsics((float)v[0], (float)v[4], (float)v[2], (float)v[5]);                  // :103-106
+}
+void SolveDVO::setIntrinsics(float fx_, float fy_, float cx_, float cy_) {
+    fx = fx_; fy = fy_; cx = cx_; cy = cy_;
+    check(dvo_set_intrinsics(ctx_, fx, fy, cx, cy), "setIntrinsics");
+    isCameraIntrinsicsAvailable = true;
+}
+
+void SolveDVO::setRcvdFrame(const dvo::ImageView& framemono, const dvo::ImageView& dframe) {
+    assert(framemono.rows == height_ && framemono.cols == width_ && framemono.type == dvo::U8C1);
+    assert(dframe.rows == height_ && dframe.cols == width_ && dframe.type == dvo::U16C1);
+    isFrameAvailable = false;
+    rcvd_gray_.assign((const uint8_t*)framemono.data, (const uint8_t*)framemono.data + framemono.bytes());
+    rcvd_depth_.assign((const uint16_t*)dframe.data, (const uint16_t*)dframe.data + (size_t)dframe.rows * dframe.cols);
+    isFrameAvailable = true;
+}
+
+void SolveDVO::setRcvdFrameAsRefFrame() {
+    assert(isFrameAvailable);
+    isRefFrameAvailable = false;
+    check(dvo_set_frames(ctx_, DVO_FRAME_REF, 0, 1, rcvd_gray_.data(), rcvd_depth_.data(), DVO_MEM_HOST), "setRcvdFrameAsRefFrame");
+    check(dvo_build_pyramids(ctx_, 0, 1, 1), "setRcvdFrameAsRefFrame");
+    isRefFrameAvailable = true;
+    computeDistTransfrmOfRef();
+}
+void SolveDVO::setPrevFrameAsRefFrame() {
+    assert(isPrevFrameAvailable);
+    isRefFrameAvailable = false;
+    check(dvo_promote_now_to_ref(ctx_, 0, 1), "setPrevFrameAsRefFrame");
+    check(dvo_build_pyramids(ctx_, 0, 1, 1), "setPrevFrameAsRefFrame");
+    isRefFrameAvailable = true;
+    computeDistTransfrmOfRef();
+}
+void SolveDVO::setRcvdFrameAsNowFrame() {
+    assert(isFrameAvailable && "FRAME NOT AVAILABLE");
+    if (isNowFrameAvailable) isPrevFrameAvailable = true;       // p_now_* are kept on the device by dvo_set_frames (:594-600)
+    isNowFrameAvailable = false;
+    check(dvo_set_frames(ctx_, DVO_FRAME_NOW, 0, 1, rcvd_gray_.data(), rcvd_depth_.data(), DVO_MEM_HOST), "setRcvdFrameAsNowFrame");
+    check(dvo_build_pyramids(ctx_, 0, 1, 2), "setRcvdFrameAsNowFrame");
+    isNowFrameAvailable = true;
+    computeDistTransfrmOfNow();
+}
+// Canny + (ref) edge-point list; the reference's ref DT / gradients are computed and never read and are skipped
+void SolveDVO::computeDistTransfrmOfRef() { assert(isRefFrameAvailable); check(dvo_prepare(ctx_, 0, 1, 1), "computeDistTransfrmOfRef"); }
+void SolveDVO::computeDistTransfrmOfNow() { assert(isNowFrameAvailable); check(dvo_prepare(ctx_, 0, 1, 2), "computeDistTransfrmOfNow"); }
+
+void SolveDVO::preProcessRefFrame() {
+    assert(isRefFrameAvailable);
+    // selectedPts + enlistRefEdgePts ran on the device inside dvo_prepare; keep the reference's invariant (:282)
+    for (int l = 0; l < levels_; ++l) { int n = 0; check(dvo_get_points(ctx_, 0, l, nullptr, nullptr, nullptr, 0, &n), "preProcessRefFrame"); assert(n > 0 && "nSelectedPts > 0"); }
+}
+
+void SolveDVO::runIterations(int level, int maxIterations, dvo::Matrix3d& cR, dvo::Vector3d& cT, dvo::VectorXf& energyAtEachIteration,
+                             dvo::VectorXf& finalEpsilons, dvo::MatrixXf& finalReprojections, int& bestEnergyIndex, float& finalVisibleRatio) {
+    assert(level >= 0 && level < levels_);                      // :625 (the reference asserts level <= 3)
+    assert(maxIterations > 0 && maxIterations <= 128);
+    assert(isRefFrameAvailable && isNowFrameAvailable && isCameraIntrinsicsAvailable);
+    dvo_solver_params p = solver;
+    for (int l = 0; l < DVO_MAX_LEVELS; ++l) p.iters[l] = 0;
+    p.iters[level] = maxIterations;
+    double pose[12];
+    for (int i = 0; i < 9; ++i) pose[i] = cR.m[i];
+    for (int i = 0; i < 3; ++i) pose[9 + i] = cT.v[i];
+    check(dvo_set_initial_pose(ctx_, 0, 1, pose, DVO_MEM_HOST), "runIterations");
+    check(dvo_run(ctx_, 0, 1, &p), "runIterations");
+    check(dvo_get_poses(ctx_, 0, 1, pose, &lastInfo, DVO_MEM_HOST), "runIterations");
+    for (int i = 0; i < 9; ++i) cR.m[i] = pose[i];
+    for (int i = 0; i < 3; ++i) cT.v[i] = pose[9 + i];
+    std::vector<double> tr((size_t)128 * 56);
+    check(dvo_get_trace(ctx_, 0, level, tr.data()), "runIterations");
+    energyAtEachIteration.assign(maxIterations, 0.f);           // :634
+    for (int k = 0; k < maxIterations && k < lastInfo.iterations_run[level]; ++k) energyAtEachIteration[k] = (float)tr[(size_t)k * 56 + 42];
+    const int n = lastInfo.npts[level];
+    finalEpsilons.assign(n, 0.f); finalReprojections.rows = 3; finalReprojections.cols = n; finalReprojections.data.assign((size_t)3 * n, 1.f);
+    if (n > 0) {
+        double H[36], g[6], ss; int nvis;
+        check(dvo_eval_normal_equations(ctx_, 0, level, pose, p.jacobian, p.weight, p.arithmetic, p.huber_k, H, g, &ss, &nvis, finalEpsilons.data(),
+                                        nullptr, finalReprojections.data.data(), finalReprojections.data.data() + n, nullptr), "runIterations");
+    }
+    bestEnergyIndex = lastInfo.best_index[level]; finalVisibleRatio = lastInfo.visible_ratio[level];
+}
+
+float SolveDVO::processResidueHistogram(dvo::VectorXf& residi, bool /*quite*/) {
+    float b_cap = 0; for (size_t i = 0; i < residi.size(); ++i) b_cap += residi[i];     // :1466-1472
+    return residi.empty() ? 0.f : b_cap / (float)residi.size();
+}
+
+int SolveDVO::processFrame() {
+    assert(isFrameAvailable && isCameraIntrinsicsAvailable);
+    dvo::VectorXf energy, eps; dvo::MatrixXf reproj; int bestIdx = -1; float vis = 0.f;
+    if (!isRefFrameAvailable) {                                 // phase A (:2009-2030): first frame is the reference / key frame
+        setRcvdFrameAsRefFrame(); preProcessRefFrame(); lastRefFrame = 0;
+        gop.pushAsKeyFrame((int)nFrame, 1, cR_64, cT_64);
+        isFrameAvailable = false; nFrame++;
+        return gop.size() - 1;
+    }
+    setRcvdFrameAsNowFrame();                                   // phase B (:2060-2240)
+    bool signalGetNewRefImage = (nFrame - lastRefFrame) == 5;   // :2155-2160
+    const bool switch_ref = signalGetNewRefImage && lastRefFrame != (nFrame - 1);
+    if (!switch_ref) {
+        for (int f = (int)iterationsConfig.size() - 1; f >= 0; --f)                    // :2097-2104
+            if (iterationsConfig[f] > 0) runIterations(f, iterationsConfig[f], cR_64, cT_64, energy, eps, reproj, bestIdx, vis);
+        gop.pushAsOrdinaryFrame((int)nFrame, cR_64, cT_64);                              // :2239
+    } else {
+        // the reference first solves against the outgoing key frame and discards the result (:2097-2104, :2210-2211)
+        lastRefFrame = nFrame - 1;                                                       // :2201
+        setPrevFrameAsRefFrame(); preProcessRefFrame();
+        gop.updateMostRecentToKeyFrame(5);                                               // :2207
+        cR_64 = dvo::Matrix3d::Identity(); cT_64 = dvo::Vector3d::Zero();                // :2210-2211
+        for (int f = (int)iterationsConfig.size() - 1; f >= 0; --f)                    // :2220-2227
+            if (iterationsConfig[f] > 0) runIterations(f, iterationsConfig[f], cR_64, cT_64, energy, eps, reproj, bestIdx, vis);
+        gop.pushAsOrdinaryFrame((int)nFrame, cR_64, cT_64);                              // :2232
+    }
+    isFrameAvailable = false; nFrame++;
+    return gop.size() - 1;
+}
+
+void SolveDVO::loopFromFrames(const uint8_t* gray, const uint16_t* depth, int nframes) {
+    const size_t P = (size_t)width_ * height_;
+    for (int t = 0; t < nframes; ++t) {
+        dvo::ImageView g(gray + P * t, height_, width_, dvo::U8C1), d(depth + P * t, height_, width_, dvo::U16C1);
+        setRcvdFrame(g, d);
+        processFrame();
+    }
+}

@@ -1,0 +1,54 @@
+// SolveDVO.h -- edge distance-transform direct odometry (reference include/SolveDVO.h:148-360, src/SolveDVO.cpp).
+// Same class and member names for the hot path; the members the reference keeps private (:199-315) are public here so the
+// class can be driven without ROS.  Ingest replaces the ROS callback (imageArrivedCallBack, :490-534): setRcvdFrame takes
+// the full-resolution mono8 / depth16 frame and the NEAREST pyramid the publisher node would have sent
+// (src/camTopic2PublisherPyD.cpp:338-348) is built on the device.  All compute runs in libdvo_b200.so; no host fallback.
+#pragma once
+#include <vector>
+
+#include "GOP.h"
+#include "dvo_b200.h"
+#include "dvo_types.h"
+
+class SolveDVO {
+public:
+    SolveDVO(int width = 640, int height = 480, int levels = 4);
+    ~SolveDVO();
+
+    void setCameraMatrix(const char* calibFile);                       // :88-126 (OpenCV-XML cameraMatrix)
+    void setIntrinsics(float fx, float fy, float cx, float cy);
+
+    // ---- ingest (replaces imageArrivedCallBack :490-534): level-0 mono8 + depth16 (mm); zeros become 1 (:512)
+    void setRcvdFrame(const dvo::ImageView& framemono, const dvo::ImageView& dframe);
+    void setRcvdFrameAsRefFrame();                                     // :537-557  (+ computeDistTransfrmOfRef)
+    void setRcvdFrameAsNowFrame();                                     // :588-614  (+ computeDistTransfrmOfNow, keeps p_now_*)
+    void setPrevFrameAsRefFrame();                                     // :561-584
+    void preProcessRefFrame();                                         // :269-303  (asserts nSelectedPts > 0 per level)
+    void computeDistTransfrmOfRef();                                   // :1679-1738
+    void computeDistTransfrmOfNow();                                   // :1740-1799
+
+    // :619-1017 -- in/out pose, per-iteration energies, residuals / reprojections of the best iterate, its index, visible ratio
+    void runIterations(int level, int maxIterations, dvo::Matrix3d& cR, dvo::Vector3d& cT, dvo::VectorXf& energyAtEachIteration,
+                       dvo::VectorXf& finalEpsilons, dvo::MatrixXf& finalReprojections, int& bestEnergyIndex, float& finalVisibleRatio);
+    float processResidueHistogram(dvo::VectorXf& residi, bool quite = true);   // :1398-1483 (quiet path: mean residual)
+
+    // one body of loop() (:2017, :2083-2240) for the frame last given to setRcvdFrame; returns the GOP index it pushed
+    int processFrame();
+    void loopFromFrames(const uint8_t* gray, const uint16_t* depth, int nframes);   // loop() over an in-memory sequence
+
+    // constants / state with the reference's names (:21-33, :171-197)
+    float fx, fy, cx, cy;
+    bool isCameraIntrinsicsAvailable, isFrameAvailable, isRefFrameAvailable, isNowFrameAvailable, isPrevFrameAvailable;
+    float trustRegionHyperSphereRadius, psiNormTerminationThreshold, laplacianThreshExitCond, ratio_of_visible_pts_thresh;
+    std::vector<int> iterationsConfig;
+    GOP<double> gop;
+    dvo::Matrix3d cR_64; dvo::Vector3d cT_64;
+    long nFrame, lastRefFrame;
+    dvo_solver_params solver;                                          // SUBGRAD_REF / REFERENCE Jacobian / REF_CAUCHY by default
+    dvo_pair_info lastInfo;
+    dvo_ctx* context() { return ctx_; }
+private:
+    dvo_ctx* ctx_; int width_, height_, levels_;
+    std::vector<uint8_t> rcvd_gray_; std::vector<uint16_t> rcvd_depth_;
+    void check(int rc, const char* what);
+};

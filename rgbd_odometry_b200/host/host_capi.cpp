@@ -1,0 +1,114 @@
+// host_capi.cpp -- C shim so the pytest suite can drive the C++ classes (SolveDVO, EPoseEstimator, PyramidalStorageStruct,
+// GOP) through ctypes exactly as a C++ caller of the reference would.
+#include <cstring>
+
+#include "EPoseEstimator.h"
+#include "GOP.h"
+#include "SolveDVO.h"
+
+extern "C" {
+
+// SolveDVO::loop over one in-memory sequence; out: nframes * 19 doubles (R, T, pose), is_key, reason
+int hostapi_solvedvo_sequence(const uint8_t* gray, const uint16_t* depth, int nframes, int W, int H, int levels, float fx, float fy, float cx,
+                              float cy, const int* iters, double* out19, int* is_key, int* reason) {
+    SolveDVO s(W, H, levels);
+    s.setIntrinsics(fx, fy, cx, cy);
+    for (int l = 0; l < levels; ++l) s.iterationsConfig[l] = iters[l];
+    s.loopFromFrames(gray, depth, nframes);
+    if (s.gop.size() != nframes) return -1;
+    for (int i = 0; i < nframes; ++i) {
+        const dvo::Matrix3d& R = s.gop.getGlobalRAt(i); const dvo::Vector3d& T = s.gop.getGlobalTAt(i); const dvo::Pose& p = s.gop.getGlobalPoseAt(i);
+        double* o = out19 + 19 * (size_t)i;
+        for (int k = 0; k < 9; ++k) o[k] = R.m[k];
+        for (int k = 0; k < 3; ++k) o[9 + k] = T.v[k];
+        o[12] = p.position.x; o[13] = p.position.y; o[14] = p.position.z;
+        o[15] = p.orientation.x; o[16] = p.orientation.y; o[17] = p.orientation.z; o[18] = p.orientation.w;
+        is_key[i] = s.gop.isKeyFrameAt(i); reason[i] = s.gop.getReasonAt(i);
+    }
+    return 0;
+}
+
+// SolveDVO::runIterations at one level of one pair; outputs as the reference's out-parameters
+int hostapi_solvedvo_run_iterations(const uint8_t* ref_gray, const uint16_t* ref_depth, const uint8_t* now_gray, const uint16_t* now_depth, int W,
+                                    int H, int levels, float fx, float fy, float cx, float cy, int level, int maxIter, double* R9, double* T3,
+                                    float* energies, float* eps, float* reproj_u, float* reproj_v, int* best_index, float* visible_ratio,
+                                    int* npts, float* b_cap) {
+    SolveDVO s(W, H, levels);
+    s.setIntrinsics(fx, fy, cx, cy);
+    dvo::ImageView g(ref_gray, H, W, dvo::U8C1), d(ref_depth, H, W, dvo::U16C1), g2(now_gray, H, W, dvo::U8C1), d2(now_depth, H, W, dvo::U16C1);
+    s.setRcvdFrame(g, d); s.setRcvdFrameAsRefFrame(); s.preProcessRefFrame();
+    s.setRcvdFrame(g2, d2); s.setRcvdFrameAsNowFrame();
+    dvo::Matrix3d cR; dvo::Vector3d cT;
+    std::memcpy(cR.m, R9, 72); std::memcpy(cT.v, T3, 24);
+    dvo::VectorXf en, ep; dvo::MatrixXf rp; int bi; float vr;
+    s.runIterations(level, maxIter, cR, cT, en, ep, rp, bi, vr);
+    std::memcpy(R9, cR.m, 72); std::memcpy(T3, cT.v, 24);
+    for (int k = 0; k < maxIter; ++k) energies[k] = en[k];
+    *npts = (int)ep.size();
+    for (size_t i = 0; i < ep.size(); ++i) { eps[i] = ep[i]; reproj_u[i] = rp(0, (int)i); reproj_v[i] = rp(1, (int)i); }
+    *best_index = bi; *visible_ratio = vr; *b_cap = s.processResidueHistogram(ep, true);
+    return 0;
+}
+
+// EPoseEstimator: setRefFrame / setNowFrame / setPyramidalImages(level) / estimate, plus one PyramidalStorage::getLevel
+int hostapi_eposeestimator(const uint8_t* ref_bgr, const uint16_t* ref_depth, const uint8_t* now_bgr, const uint16_t* now_depth, int W, int H,
+                           double fx, double fy, double cx, double cy, int compat, int level, int iters, double huber_k, double lambda0, double* R9,
+                           double* T3, double* A36, float* visible, int* status, double* J_level, double* X_level, uint8_t* gray_level) {
+    EPoseEstimator e(compat != 0);
+    e.setCameraMatrix(fx, fy, cx, cy);
+    e.iterations = iters; e.huber_k = huber_k; e.lm_lambda0 = lambda0;
+    dvo::ImageView rb(ref_bgr, H, W, dvo::U8C3), rd(ref_depth, H, W, dvo::U16C1), nb(now_bgr, H, W, dvo::U8C3), nd(now_depth, H, W, dvo::U16C1);
+    e.setRefFrame(rb, rd); e.setNowFrame(nb, nd);
+    e.setPyramidalImages(level);
+    std::memcpy(A36, e.A, 288);
+    dvo::Matrix3d R; dvo::Vector3d T; std::memcpy(R.m, R9, 72); std::memcpy(T.v, T3, 24);
+    *visible = e.estimate(R, T);
+    std::memcpy(R9, R.m, 72); std::memcpy(T3, T.v, 24);
+    *status = e.lastInfo.status;
+    if (J_level || X_level || gray_level) {
+        std::vector<uint8_t> c, g; std::vector<uint16_t> d; dvo::ArrayXXd X, Y, Z, gv, rv, gr, bv; dvo::MatrixXd J;
+        e.pydStore.getLevel(level, c, g, d, X, Y, Z, J, gv, rv, gr, bv);
+        if (J_level) std::memcpy(J_level, J.data.data(), J.data.size() * 8);
+        if (X_level) std::memcpy(X_level, X.data.data(), X.data.size() * 8);
+        if (gray_level) std::memcpy(gray_level, g.data(), g.size());
+    }
+    return e.pydStore.size();
+}
+
+// GOP<float> and GOP<double> replay (explicit instantiations, src/GOP.cpp:244-245)
+int hostapi_gop_replay(int n, const int* kind, const int* reason, const double* rel, double* out19, int* is_key, int* reason_out, int use_float) {
+    if (use_float) {
+        GOP<float> g;
+        for (int i = 0; i < n; ++i) {
+            dvo::Matrix3f R; dvo::Vector3f T;
+            for (int k = 0; k < 9; ++k) R.m[k] = (float)rel[12 * (size_t)i + k];
+            for (int k = 0; k < 3; ++k) T.v[k] = (float)rel[12 * (size_t)i + 9 + k];
+            if (kind[i] == 1) g.pushAsKeyFrame(i, reason[i], R, T); else g.pushAsOrdinaryFrame(i, R, T);
+            if (kind[i] == 2) g.updateMostRecentToKeyFrame(reason[i]);
+        }
+        for (int i = 0; i < n; ++i) {
+            double* o = out19 + 19 * (size_t)i; const dvo::Pose& p = g.getGlobalPoseAt(i);
+            for (int k = 0; k < 9; ++k) o[k] = g.getGlobalRAt(i).m[k];
+            for (int k = 0; k < 3; ++k) o[9 + k] = g.getGlobalTAt(i).v[k];
+            o[12] = p.position.x; o[13] = p.position.y; o[14] = p.position.z; o[15] = p.orientation.x; o[16] = p.orientation.y; o[17] = p.orientation.z; o[18] = p.orientation.w;
+            is_key[i] = g.isKeyFrameAt(i); reason_out[i] = g.getReasonAt(i);
+        }
+        return g.size();
+    }
+    GOP<double> g;
+    for (int i = 0; i < n; ++i) {
+        dvo::Matrix3d R; dvo::Vector3d T;
+        std::memcpy(R.m, rel + 12 * (size_t)i, 72); std::memcpy(T.v, rel + 12 * (size_t)i + 9, 24);
+        if (kind[i] == 1) g.pushAsKeyFrame(i, reason[i], R, T); else g.pushAsOrdinaryFrame(i, R, T);
+        if (kind[i] == 2) g.updateMostRecentToKeyFrame(reason[i]);
+    }
+    for (int i = 0; i < n; ++i) {
+        double* o = out19 + 19 * (size_t)i; const dvo::Pose& p = g.getGlobalPoseAt(i);
+        std::memcpy(o, g.getGlobalRAt(i).m, 72); std::memcpy(o + 9, g.getGlobalTAt(i).v, 24);
+        o[12] = p.position.x; o[13] = p.position.y; o[14] = p.position.z; o[15] = p.orientation.x; o[16] = p.orientation.y; o[17] = p.orientation.z; o[18] = p.orientation.w;
+        is_key[i] = g.isKeyFrameAt(i); reason_out[i] = g.getReasonAt(i);
+    }
+    return g.size();
+}
+
+}  // extern "C"

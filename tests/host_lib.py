@@ -1,0 +1,73 @@
+"""ctypes access to the C shim of the C++ host classes (rgbd_odometry_b200/libdvo_host.so)."""
+import ctypes as C
+
+import numpy as np
+
+from rgbd_odometry_b200 import build as _build
+
+_h = None
+
+
+def lib():
+    global _h
+    if _h is None:
+        _h = C.CDLL(_build.build_host())
+    return _h
+
+
+def _p(a, t=None):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def gop_replay(kind, reason, rel, use_float=False):
+    n = len(kind)
+    kind = np.ascontiguousarray(kind, np.int32); reason = np.ascontiguousarray(reason, np.int32)
+    rel = np.ascontiguousarray(rel, np.float64).reshape(n, 12)
+    out = np.empty((n, 19)); is_key = np.empty(n, np.int32); r_out = np.empty(n, np.int32)
+    m = lib().hostapi_gop_replay(n, _p(kind), _p(reason), _p(rel), _p(out), _p(is_key), _p(r_out), int(use_float))
+    assert m == n
+    return out, is_key, r_out
+
+
+def solvedvo_sequence(gray, depth, levels, iters, K):
+    n, H, W = gray.shape
+    gray = np.ascontiguousarray(gray, np.uint8); depth = np.ascontiguousarray(depth, np.uint16)
+    it = np.array(iters, np.int32)
+    out = np.empty((n, 19)); is_key = np.empty(n, np.int32); reason = np.empty(n, np.int32)
+    rc = lib().hostapi_solvedvo_sequence(_p(gray), _p(depth), n, W, H, levels, C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]),
+                                         C.c_float(K[3]), _p(it), _p(out), _p(is_key), _p(reason))
+    assert rc == 0
+    return out, is_key, reason
+
+
+def solvedvo_run_iterations(ref_gray, ref_depth, now_gray, now_depth, levels, level, max_iter, K, R0=None, T0=None):
+    H, W = ref_gray.shape
+    R = np.eye(3).reshape(9).copy() if R0 is None else np.array(R0, np.float64).reshape(9).copy()
+    T = np.zeros(3) if T0 is None else np.array(T0, np.float64).copy()
+    en = np.zeros(max_iter, np.float32)
+    cap = W * H
+    eps, ru, rv = (np.zeros(cap, np.float32) for _ in range(3))
+    bi, npts = C.c_int(), C.c_int()
+    vr, bcap = C.c_float(), C.c_float()
+    rc = lib().hostapi_solvedvo_run_iterations(_p(np.ascontiguousarray(ref_gray)), _p(np.ascontiguousarray(ref_depth)),
+                                               _p(np.ascontiguousarray(now_gray)), _p(np.ascontiguousarray(now_depth)), W, H, levels,
+                                               C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3]), level, max_iter, _p(R), _p(T),
+                                               _p(en), _p(eps), _p(ru), _p(rv), C.byref(bi), C.byref(vr), C.byref(npts), C.byref(bcap))
+    assert rc == 0
+    n = npts.value
+    return {"R": R.reshape(3, 3), "T": T, "energies": en, "eps": eps[:n], "u": ru[:n], "v": rv[:n], "best_index": bi.value,
+            "visible_ratio": vr.value, "b_cap": bcap.value}
+
+
+def eposeestimator(ref_bgr, ref_depth, now_bgr, now_depth, K, compat, level, iters=3, huber_k=0.0, lambda0=0.0, R0=None, T0=None):
+    H, W = ref_depth.shape
+    R = np.eye(3).reshape(9).copy() if R0 is None else np.array(R0, np.float64).reshape(9).copy()
+    T = np.zeros(3) if T0 is None else np.array(T0, np.float64).copy()
+    A = np.empty((6, 6)); vis = C.c_float(); st = C.c_int()
+    h, w = H >> level, W >> level
+    J = np.empty((h * w, 6)); X = np.empty((h, w)); g = np.empty((h, w), np.uint8)
+    nlev = lib().hostapi_eposeestimator(_p(np.ascontiguousarray(ref_bgr)), _p(np.ascontiguousarray(ref_depth)), _p(np.ascontiguousarray(now_bgr)),
+                                        _p(np.ascontiguousarray(now_depth)), W, H, C.c_double(K[0]), C.c_double(K[1]), C.c_double(K[2]),
+                                        C.c_double(K[3]), int(compat), level, iters, C.c_double(huber_k), C.c_double(lambda0), _p(R), _p(T), _p(A),
+                                        C.byref(vis), C.byref(st), _p(J), _p(X), _p(g))
+    return {"R": R.reshape(3, 3), "T": T, "A": A, "visible": vis.value, "status": st.value, "J": J, "X": X, "gray": g, "levels": nlev}
