@@ -586,12 +586,22 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_window_kernel(EdtArgs a, 
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
         int best = (x < w) ? g2[x] : 0;
-        int kk = 1;
-        for (int k = 1; k < w; ++k) {
+        // while the whole 32-pixel segment +- k stays inside the row no index clamping is needed: 4 steps per exit test
+        const int kint = min(x0, w - 32 - x0);
+        const int* gc = g2 + min(x, w - 1);
+        int k = 1, kk = 1;
+        while (k < w) {
             if (__all_sync(0xffffffffu, kk >= best)) break;
-            const int vl = g2[min(max(x - k, -1), w)], vr = g2[min(x + k, w)];
-            best = min(best, min(vl, vr) + kk);
-            kk += 2 * k + 1;
+            if (k + 3 <= kint) {
+                const int a0 = min(gc[-k], gc[k]), a1 = min(gc[-k - 1], gc[k + 1]), a2 = min(gc[-k - 2], gc[k + 2]), a3 = min(gc[-k - 3], gc[k + 3]);
+                const int k1 = kk + 2 * k + 1, k2 = kk + 4 * k + 4, k3 = kk + 6 * k + 9;
+                best = min(min(best, a0 + kk), min(a1 + k1, min(a2 + k2, a3 + k3)));
+                kk += 8 * k + 16; k += 4;
+            } else {
+                const int vl = g2[min(max(x - k, -1), w)], vr = g2[min(x + k, w)];
+                best = min(best, min(vl, vr) + kk);
+                kk += 2 * k + 1; ++k;
+            }
         }
         if (x < w) { out[x] = best; mx = max(mx, best); }
     }
