@@ -64,6 +64,7 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     }
     if (cfg->device < 0 || cfg->device >= ndev) { dvo_set_error("dvo_create: device %d out of range (%d devices)", cfg->device, ndev); return DVO_ERR_ARG; }
     DVO_CUDA(cudaSetDevice(cfg->device));
+    if (const char* e = getenv("DVO_L2_FETCH")) { cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e)); cudaGetLastError(); }   // experiment knob
     dvo_ctx* c = new (std::nothrow) dvo_ctx();
     if (!c) return DVO_ERR_NOMEM;
     memset(c, 0, sizeof(*c));
