@@ -5,6 +5,7 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -101,7 +102,7 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     if (cfg->keep_now_depth) { A(dalloc(&c->depth[1], T)); A(dalloc(&c->prev_gray, B * (size_t)g.P[0])); A(dalloc(&c->prev_depth, B * (size_t)g.P[0])); }
     c->now_valid = (unsigned char*)calloc(B, 1); c->prev_valid = (unsigned char*)calloc(B, 1);
     A(dalloc(&c->gcol, T)); A(dalloc(&c->d2, T)); A(dalloc(&c->texel, T));
-    A(dalloc(&c->ptsX, T)); A(dalloc(&c->ptsY, T)); A(dalloc(&c->ptsZ, T));
+    A(dalloc(&c->ptsX, T)); A(dalloc(&c->ptsY, T)); A(dalloc(&c->ptsZ, T)); A(dalloc(&c->ptsPix, T));
     A(dalloc(&c->npts, B * g.L)); A(dalloc(&c->nedge, 2 * B * g.L)); A(dalloc(&c->maxd2, B * g.L));
     A(dalloc(&c->pose0, B * 12)); A(dalloc(&c->pose, B * 12)); A(dalloc(&c->info, B));
     if (cfg->trace_iters > 0) A(dalloc(&c->trace, B * g.L * cfg->trace_iters * DVO_TRACE_DOUBLES));
@@ -130,7 +131,7 @@ int dvo_destroy(dvo_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int f = 0; f < 2; ++f) { cudaFree(c->gray[f]); cudaFree(c->depth[f]); cudaFree(c->edge[f]); }
-    cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ);
+    cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ); cudaFree(c->ptsPix);
     cudaFree(c->npts); cudaFree(c->nedge); cudaFree(c->maxd2); cudaFree(c->pose0); cudaFree(c->pose); cudaFree(c->info);
     cudaFree(c->trace); cudaFree(c->bitmap_scratch); cudaFree(c->prev_gray); cudaFree(c->prev_depth);
     free(c->now_valid); free(c->prev_valid);
@@ -383,6 +384,22 @@ int dvo_get_level_buffer(dvo_ctx* c, int slot, int frame, int level, int which, 
     return DVO_OK;
 }
 
+// The device keeps the point list in row-major pixel order; the reference enumerates column-major (xx outer, yy inner,
+// src/SolveDVO.cpp:1237-1241).  perm[k] = device index of the k-th point in the reference's order.
+static int reference_order(dvo_ctx* c, int slot, int level, int n, std::vector<int>& perm) {
+    perm.resize(n);
+    if (n == 0) return DVO_OK;
+    std::vector<int> pix(n);
+    DVO_CUDA(cudaMemcpyAsync(pix.data(), c->ptsPix + lvl_at(c->geom, level, slot), sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    const int w = c->geom.w[level], h = c->geom.h[level];
+    std::vector<long long> key(n);
+    for (int i = 0; i < n; ++i) { const int y = pix[i] / w, x = pix[i] - y * w; key[i] = ((long long)x * h + y) * (long long)n + i; }
+    std::sort(key.begin(), key.end());
+    for (int k = 0; k < n; ++k) perm[k] = (int)(key[k] % n);
+    return DVO_OK;
+}
+
 int dvo_get_points(dvo_ctx* c, int slot, int level, float* X, float* Y, float* Z, int capacity, int* n) {
     if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !n) return DVO_ERR_ARG;
     int cnt = 0;
@@ -390,12 +407,18 @@ int dvo_get_points(dvo_ctx* c, int slot, int level, float* X, float* Y, float* Z
     DVO_CUDA(cudaStreamSynchronize(c->stream));
     *n = cnt;
     const int m = cnt < capacity ? cnt : capacity;
+    if (m <= 0 || !(X || Y || Z)) return DVO_OK;
+    std::vector<int> perm;
+    int rc = reference_order(c, slot, level, cnt, perm);
+    if (rc) return rc;
     const long long o = lvl_at(c->geom, level, slot);
-    if (m > 0) {
-        if (X) DVO_CUDA(cudaMemcpyAsync(X, c->ptsX + o, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
-        if (Y) DVO_CUDA(cudaMemcpyAsync(Y, c->ptsY + o, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
-        if (Z) DVO_CUDA(cudaMemcpyAsync(Z, c->ptsZ + o, sizeof(float) * m, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<float> tmp(cnt);
+    float* dst[3] = {X, Y, Z}; const float* src[3] = {c->ptsX + o, c->ptsY + o, c->ptsZ + o};
+    for (int a = 0; a < 3; ++a) {
+        if (!dst[a]) continue;
+        DVO_CUDA(cudaMemcpyAsync(tmp.data(), src[a], sizeof(float) * cnt, cudaMemcpyDeviceToHost, c->stream));
         DVO_CUDA(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < m; ++k) dst[a][k] = tmp[perm[k]];
     }
     return DVO_OK;
 }
@@ -420,21 +443,29 @@ int dvo_eval_normal_equations(dvo_ctx* c, int slot, int level, const double* R9T
     int rc = launch_eval(c, slot, level, d_pose, jacobian, weight, arithmetic, huber_k, d_out, de, dw, du, dv, dJ);
     if (rc == DVO_OK) {
         double out[44];
+        std::vector<float> host(pp ? n1 * 10 : 0);
         cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(out), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess && pp && N > 0) {
-            if (eps) cudaMemcpyAsync(eps, de, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
-            if (w) cudaMemcpyAsync(w, dw, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
-            if (u) cudaMemcpyAsync(u, du, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
-            if (v) cudaMemcpyAsync(v, dv, sizeof(float) * N, cudaMemcpyDeviceToHost, c->stream);
-            if (J) cudaMemcpyAsync(J, dJ, sizeof(float) * 6 * N, cudaMemcpyDeviceToHost, c->stream);
-        }
-        e = cudaStreamSynchronize(c->stream);
+        if (e == cudaSuccess && pp && N > 0) e = cudaMemcpyAsync(host.data(), d_pp, sizeof(float) * n1 * 10, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { dvo_set_error("dvo_eval_normal_equations: %s", cudaGetErrorString(e)); rc = DVO_ERR_CUDA; }
         else {
             if (g6) memcpy(g6, out, sizeof(double) * 6);
             if (H36) memcpy(H36, out + 6, sizeof(double) * 36);
             if (sumsq) *sumsq = out[42];
             if (nvis) *nvis = (int)out[43];
+            if (pp && N > 0) {                       // per-point arrays are returned in the reference's (column-major) order
+                std::vector<int> perm;
+                rc = reference_order(c, slot, level, N, perm);
+                if (rc == DVO_OK)
+                    for (int k = 0; k < N; ++k) {
+                        const size_t i = (size_t)perm[k];
+                        if (eps) eps[k] = host[i];
+                        if (w) w[k] = host[n1 + i];
+                        if (u) u[k] = host[2 * n1 + i];
+                        if (v) v[k] = host[3 * n1 + i];
+                        if (J) for (int q = 0; q < 6; ++q) J[6 * (size_t)k + q] = host[4 * n1 + 6 * i + q];
+                    }
+            }
         }
     }
     cudaFree(d_pose); cudaFree(d_out); cudaFree(d_pp);

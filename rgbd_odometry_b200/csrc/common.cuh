@@ -46,7 +46,8 @@ struct dvo_ctx {
     uint16_t* gcol;          // now: EDT phase-1 column distances
     int32_t* d2;             // now: exact squared distance
     float4* texel;           // now: {DTn, gx, gy, getWeightOf(DTn)}
-    float *ptsX, *ptsY, *ptsZ;   // ref: back-projected edge points, capacity P[l] per slot and level
+    float *ptsX, *ptsY, *ptsZ;   // ref: back-projected edge points (row-major pixel order), capacity P[l] per slot and level
+    int* ptsPix;                 // ref: pixel index y*w+x of every point (restores the reference's column-major order)
     int* npts;               // [Bmax][L]
     unsigned* nedge;         // [2][Bmax][L]
     unsigned* maxd2;         // [Bmax][L]

@@ -64,8 +64,8 @@ int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
 //  phase 3  edge bytes 0/255 (128-bit stores) + edge count.
 //  phase 4  (now) the edge bitmap is transposed (32x32 ballot transposes) so that a column is a bit string, and
 //           every pixel gets its distance to the nearest edge pixel above/below with clz/ffs -- EDT phase 1.
-//           (ref) selected = edge && depth > 100 bitmap, transposed: popcounts + a block scan give the stable
-//           column-major enumeration of selectedPts/enlistRefEdgePts (src/SolveDVO.cpp:1230-1264, 224-264).
+//           (ref) selected = edge && depth > 100 bitmap: popcounts + a block scan give a stable enumeration of
+//           selectedPts/enlistRefEdgePts (src/SolveDVO.cpp:1230-1264, 224-264), emitted row-major (see phase 4).
 // =====================================================================================================
 struct CannyArgs {
     const uint8_t* gray;   // level region of this frame (slot 0)
@@ -73,6 +73,7 @@ struct CannyArgs {
     const uint16_t* depth; // ref
     uint16_t* gcol;        // now
     float *X, *Y, *Z;      // ref, level region
+    int* pix;              // ref, level region: pixel index y*w+x of every emitted point
     int* npts;             // + level, stride L
     unsigned* nedge;       // + level, stride L (this frame)
     int w, h, P, L;
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     // ------------------------------------------------------------------ transpose E -> Et (into C's storage): Et[x * hwp + (y >> 5)], bit y & 31
     const int hw = (h + 31) >> 5, hwp = hw | 1;
     uint32_t* Et = C;
-    {
+    if (a.do_cols) {
         const int nwarps = T >> 5;
         for (int blk = warp; blk < hw * wd; blk += nwarps) {
             const int wy = blk / wd, wx = blk - wy * wd;
@@ -373,47 +374,49 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
         }
     }
 
-    // ------------------------------------------------------------------ phase 4 (ref): column-major stable compaction + back-projection
+    // ------------------------------------------------------------------ phase 4 (ref): stable compaction + back-projection
+    // selectedPts / enlistRefEdgePts (src/SolveDVO.cpp:1230-1264, 224-264).  The reference enumerates column-major; the
+    // list is emitted ROW-major here because the solver gathers from row-major texels: 32 consecutive points of a
+    // horizontal contour then share 8 DRAM atoms inside one warp instruction.  Every sum over points is order
+    // independent up to fp64 rounding; the pixel index of each point is kept so that the reference's order can be
+    // restored wherever a per-point list is exposed (dvo_get_points, dvo_eval_normal_equations).
     if (a.do_points) {
         const uint16_t* __restrict__ dep = a.depth + (long long)b * a.P;
         float* X = a.X + (long long)b * a.P; float* Y = a.Y + (long long)b * a.P; float* Z = a.Z + (long long)b * a.P;
-        for (int x0 = 0; x0 < w; x0 += T) {
-            const int x = x0 + tid;
-            int mycnt = 0;
-            if (x < w) for (int k = 0; k < hw; ++k) mycnt += __popc(Et[x * hwp + k]);
-            int incl = mycnt;
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-            if (lane == 31) s_scan[warp] = incl;
-            __syncthreads();
-            if (tid < 32) {
-                const int nwp = T >> 5;
-                const int v = (tid < nwp) ? s_scan[tid] : 0;
-                int iv = v;
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
-                if (tid < nwp) s_scan[tid] = iv - v;               // exclusive warp offsets
-                if (tid == 31) s_scan[CANNY_MAX_WARPS] = iv;       // chunk total
-            }
-            __syncthreads();
-            int off = s_base + s_scan[warp] + (incl - mycnt);
-            if (x < w && mycnt) {
-                for (int k = 0; k < hw; ++k) {
-                    uint32_t v = Et[x * hwp + k];
-                    while (v) {
-                        const int y = (k << 5) + __ffs(v) - 1; v &= v - 1;
-                        const float d = (float)dep[(long long)y * w + x];
-                        const float z = __fdiv_rn(d, 1000.0f);                                          // :248
-                        X[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)x, a.tmpcx)), a.tmpfx);          // :249
-                        Y[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)y, a.tmpcy)), a.tmpfy);          // :250
-                        Z[off] = z;
-                        ++off;
-                    }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) s_base += s_scan[CANNY_MAX_WARPS];
-            __syncthreads();
+        int* pix = a.pix + (long long)b * a.P;
+        const int per = (nw + T - 1) / T;
+        const int q0 = min(nw, tid * per), q1 = min(nw, q0 + per);
+        int mycnt = 0;
+        for (int q = q0; q < q1; ++q) { const int y = q / wd, wx = q - y * wd; mycnt += __popc(E[(y + 1) * pitch + wx + 1]); }
+        int incl = mycnt;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        if (tid < 32) {
+            const int nwp = T >> 5;
+            const int v = (tid < nwp) ? s_scan[tid] : 0;
+            int iv = v;
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, iv, o); if (lane >= o) iv += t; }
+            if (tid < nwp) s_scan[tid] = iv - v;               // exclusive warp offsets
+            if (tid == 31) s_scan[CANNY_MAX_WARPS] = iv;       // total
         }
-        if (tid == 0) a.npts[(long long)b * a.L] = s_base;
+        __syncthreads();
+        int off = s_scan[warp] + (incl - mycnt);
+        for (int q = q0; q < q1; ++q) {
+            const int y = q / wd, wx = q - y * wd;
+            uint32_t v = E[(y + 1) * pitch + wx + 1];
+            while (v) {
+                const int x = (wx << 5) + __ffs(v) - 1; v &= v - 1;
+                const float d = (float)dep[(long long)y * w + x];
+                const float z = __fdiv_rn(d, 1000.0f);                                          // :248
+                X[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)x, a.tmpcx)), a.tmpfx);          // :249
+                Y[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)y, a.tmpcy)), a.tmpfy);          // :250
+                Z[off] = z;
+                pix[off] = y * w + x;
+                ++off;
+            }
+        }
+        if (tid == 0) a.npts[(long long)b * a.L] = s_scan[CANNY_MAX_WARPS];
     }
 }
 
@@ -444,7 +447,7 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
             a.gray = c->gray[f] + g.off[l]; a.edge = c->edge[f] + g.off[l];
             a.depth = c->depth[f] ? c->depth[f] + g.off[l] : nullptr;
             a.gcol = c->gcol + g.off[l];
-            a.X = c->ptsX + g.off[l]; a.Y = c->ptsY + g.off[l]; a.Z = c->ptsZ + g.off[l];
+            a.X = c->ptsX + g.off[l]; a.Y = c->ptsY + g.off[l]; a.Z = c->ptsZ + g.off[l]; a.pix = c->ptsPix + g.off[l];
             a.npts = c->npts + l; a.nedge = c->nedge + (size_t)f * g.Bmax * g.L + l;
             a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L;
             a.do_points = (f == DVO_FRAME_REF); a.do_cols = (f == DVO_FRAME_NOW);
