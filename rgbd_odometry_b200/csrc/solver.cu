@@ -3,9 +3,12 @@
 // H = J^T W J, the 6-vector step / 6x6 solve, SE(3) update, best-iterate tracking, termination) with no host
 // round trip.  Follows SolveDVO::runIterations (src/SolveDVO.cpp:619-1017), computeJacobianOfNowFrame
 // (:306-414) and getReprojectedEpsilons (:425-462); see SURVEY.md Appendix A for the restated arithmetic.
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -191,18 +194,18 @@ __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, c
                                                   const float* __restrict__ Z, int N, const PoseF& P, const LevelCam& cam,
                                                   const float4* __restrict__ tex, int weight_mode, float huber_k,
                                                   double* acc, int& nvis, float* o_eps, float* o_w, float* o_u, float* o_v,
-                                                  float* o_J) {
+                                                  float* o_J, int start = threadIdx.x, int stride = THREADS) {
     typedef Ar<ARITH> A;
-    int i = threadIdx.x;
+    int i = start;
     if (i >= N) return;
     float cx = __ldg(X + i), cy = __ldg(Y + i), cz = __ldg(Z + i);
     Proj q = project_point(cx, cy, cz, P, cam);
     float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
     if (q.idx >= 0) t = __ldg(tex + q.idx);
-    int i1 = i + THREADS;
+    int i1 = i + stride;
     if (i1 < N) { cx = __ldg(X + i1); cy = __ldg(Y + i1); cz = __ldg(Z + i1); }
     for (;;) {
-        const int i2 = i1 + THREADS;
+        const int i2 = i1 + stride;
         float nx = 0.f, ny = 0.f, nz = 1.f;
         if (i2 < N) { nx = __ldg(X + i2); ny = __ldg(Y + i2); nz = __ldg(Z + i2); }       // coordinates two ahead
         Proj qn; qn.idx = -1;
@@ -281,6 +284,7 @@ struct SolveArgs {
     const float *X, *Y, *Z; const int* npts; const unsigned* nedge_now; const float4* texel;
     const double* pose0; double* pose; dvo_pair_info* info; double* trace; int trace_iters;
     dvo_solver_params prm; int first;
+    int resume;             // 1: continue from the pose / info already in the output buffers (second launch of a level split)
 };
 
 // One iteration's serial tail (thread 0): best tracking, step computation, pose update.  Returns 1 to stop the level.
@@ -355,7 +359,14 @@ __device__ __forceinline__ int solver_step(SolverState& S, const double* tot, in
     return 0;
 }
 
-template <int ARITH, int JAC, bool NEED_H, int THREADS>
+// CL = CTAs per frame pair.  CL == 1: one CTA owns a pair.  CL > 1: a thread-block cluster owns a pair -- the point list
+// is striped over the cluster's CTAs, partial sums are combined by rank 0 through distributed shared memory in rank
+// order (deterministic), rank 0 runs the serial step and pushes the next pose / stop flag into every rank's shared
+// memory.  Spreading one pair over several SMs keeps fewer pairs in flight, so a level's texels stay L2-resident across
+// iterations instead of being re-fetched from HBM every iteration.  MEASURED (1024 pairs, GN 10 it/level): CL = 1: 4.29 ms,
+// CL = 2: 4.58 ms, CL = 4: 5.53 ms, CL = 8: 8.62 ms -- the two cluster barriers and the serial step per iteration cost more
+// than the L2 residency returns, so CL = 1 is the default (DVO_SOLVE_CLUSTER selects the others).
+template <int ARITH, int JAC, bool NEED_H, int THREADS, int CL>
 __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve_kernel(SolveArgs a) {
     constexpr int NACC = AccN<NEED_H>::N;
     constexpr int SOLVE_WARPS = THREADS / 32;
@@ -367,25 +378,45 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
     __shared__ SolverState S;
     __shared__ dvo_pair_info s_info;
 
-    const int b = a.first + blockIdx.x;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (CL > 1) ? (int)cluster.block_rank() : 0;
+    const int b = a.first + blockIdx.x / CL;
     const int L = a.geom.L;
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < 9; ++k) S.cR[k] = a.pose0[12 * (long long)b + k];
-        for (int k = 0; k < 3; ++k) S.cT[k] = a.pose0[12 * (long long)b + 9 + k];
-        s_info.status = 0; s_info.laplacian_b = 0.f;
-        for (int l = 0; l < DVO_MAX_LEVELS; ++l) {
-            s_info.npts[l] = (l < L) ? a.npts[(long long)b * L + l] : 0; s_info.best_index[l] = -1; s_info.iterations_run[l] = 0;
-            s_info.best_energy[l] = 0.f; s_info.visible_ratio[l] = 0.f;
+    const bool lead = (rank == 0 && threadIdx.x == 0);
+    if (lead) {
+        const double* src = a.resume ? a.pose : a.pose0;
+        for (int k = 0; k < 9; ++k) S.cR[k] = src[12 * (long long)b + k];
+        for (int k = 0; k < 3; ++k) S.cT[k] = src[12 * (long long)b + 9 + k];
+        if (a.resume) s_info = a.info[b];
+        else {
+            s_info.status = 0; s_info.laplacian_b = 0.f;
+            for (int l = 0; l < DVO_MAX_LEVELS; ++l) {
+                s_info.npts[l] = (l < L) ? a.npts[(long long)b * L + l] : 0; s_info.best_index[l] = -1; s_info.iterations_run[l] = 0;
+                s_info.best_energy[l] = 0.f; s_info.visible_ratio[l] = 0.f;
+            }
         }
     }
     __syncthreads();
+
+    // rank 0: publish s_pose / s_stop to every rank of the cluster, then cluster barrier
+    auto publish = [&]() {
+        if (CL > 1) {
+            __syncthreads();
+            if (rank == 0 && threadIdx.x < 13 * (CL - 1)) {
+                const int r = 1 + threadIdx.x / 13, k = threadIdx.x % 13;
+                if (k < 12) { float* dst = cluster.map_shared_rank(reinterpret_cast<float*>(&s_pose), r); dst[k] = reinterpret_cast<float*>(&s_pose)[k]; }
+                else { int* dst = cluster.map_shared_rank(&s_stop, r); *dst = s_stop; }
+            }
+            cluster.sync();
+        } else __syncthreads();
+    };
 
     for (int l = L - 1; l >= 0; --l) {
         const int iters = a.prm.iters[l];
         if (iters <= 0) continue;
         const int N = a.npts[(long long)b * L + l];
         const unsigned ne = a.nedge_now[(long long)b * L + l];
-        if (N <= 0 || ne == 0u) { if (threadIdx.x == 0) s_info.status |= 1; continue; }      // reference asserts (:282)
+        if (N <= 0 || ne == 0u) { if (lead) s_info.status |= 1; continue; }                  // reference asserts (:282)
         const long long base = lvl_at(a.geom, l, b);
         const float* X = a.X + base; const float* Y = a.Y + base; const float* Z = a.Z + base;
         const float4* tex = a.texel + base;
@@ -394,37 +425,50 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
         cam.M00 = __fmul_rn(scaleFac, a.K.fx); cam.M02 = __fmul_rn(scaleFac, a.K.cx);         // scaleMatrix * K (:344)
         cam.M11 = __fmul_rn(scaleFac, a.K.fy); cam.M12 = __fmul_rn(scaleFac, a.K.cy);
         cam.w = a.geom.w[l]; cam.h = a.geom.h[l];
-        if (threadIdx.x == 0) {
+        if (lead) {
             S.bestE = 1.0E10f; S.bestRatio = 1.0f; S.bestItr = -1; S.bestSumEps = 0.0;        // :642-650
             for (int k = 0; k < 9; ++k) S.bestR[k] = (k % 4 == 0) ? 1.0 : 0.0;
             for (int k = 0; k < 3; ++k) S.bestT[k] = 0.0;
             for (int k = 0; k < 6; ++k) S.descent[k] = 0.0;                                   // :654
             S.have_acc = 0; S.lambda = a.prm.lm_lambda0; S.accE = 0.f;
+            for (int k = 0; k < 9; ++k) s_pose.R[k] = (float)S.cR[k];                          // :673-674
+            for (int k = 0; k < 3; ++k) s_pose.T[k] = (float)S.cT[k];
+            s_stop = 0;
         }
+        publish();
         for (int itr = 0; itr < iters; ++itr) {
-            if (threadIdx.x == 0) {
-                for (int k = 0; k < 9; ++k) s_pose.R[k] = (float)S.cR[k];                      // :673-674
-                for (int k = 0; k < 3; ++k) s_pose.T[k] = (float)S.cT[k];
-            }
-            __syncthreads();
             PoseF P = s_pose;
             double acc[NACC];
 #pragma unroll
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
             int nvis = 0;
             accumulate_points<ARITH, JAC, NEED_H, THREADS, false>(X, Y, Z, N, P, cam, tex, a.prm.weight, a.prm.huber_k, acc, nvis,
-                                                  nullptr, nullptr, nullptr, nullptr, nullptr);
+                                                  nullptr, nullptr, nullptr, nullptr, nullptr, rank * THREADS + (int)threadIdx.x, THREADS * CL);
             block_reduce<NACC, THREADS>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
-            if (threadIdx.x == 0) {
+            if (CL > 1) {
+                cluster.sync();                                                               // every rank's partial sums are in place
+                if (rank == 0) {
+                    if (threadIdx.x < NACC) {
+                        double v = s_tot[threadIdx.x];
+                        for (int r = 1; r < CL; ++r) v += cluster.map_shared_rank(s_tot, r)[threadIdx.x];
+                        s_tot[threadIdx.x] = v;
+                    }
+                    if (threadIdx.x == 32) { int n = s_nvtot; for (int r = 1; r < CL; ++r) n += *cluster.map_shared_rank(&s_nvtot, r); s_nvtot = n; }
+                    __syncthreads();
+                }
+            }
+            if (lead) {
                 double* tr = nullptr;
                 if (a.trace && itr < a.trace_iters)
                     tr = a.trace + (((long long)b * L + l) * a.trace_iters + itr) * DVO_TRACE_DOUBLES;
                 s_stop = solver_step(S, s_tot, s_nvtot, N, itr, a.prm, NEED_H, &s_info, l, tr);
+                for (int k = 0; k < 9; ++k) s_pose.R[k] = (float)S.cR[k];                      // pose of the next iteration (:673-674)
+                for (int k = 0; k < 3; ++k) s_pose.T[k] = (float)S.cT[k];
             }
-            __syncthreads();
+            publish();
             if (s_stop) break;
         }
-        if (threadIdx.x == 0) {
+        if (lead) {
             for (int k = 0; k < 9; ++k) S.cR[k] = S.bestR[k];                                  // :997-1001
             rotationize_dev(S.cR);
             for (int k = 0; k < 3; ++k) S.cT[k] = S.bestT[k];
@@ -433,11 +477,12 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0) {
+    if (lead) {
         for (int k = 0; k < 9; ++k) a.pose[12 * (long long)b + k] = S.cR[k];
         for (int k = 0; k < 3; ++k) a.pose[12 * (long long)b + 9 + k] = S.cT[k];
         a.info[b] = s_info;
     }
+    if (CL > 1) cluster.sync();            // no CTA may exit while a peer can still touch its shared memory
 }
 
 // ------------------------------------------------------------------ single evaluation (parity inspection)
@@ -505,41 +550,80 @@ __global__ void gop_kernel(int nseq, int nframes, const int* __restrict__ kind, 
 
 }  // namespace
 
-static int g_solve_threads = 256;
+static int g_solve_cluster = 1;          // CTAs per pair on the fine (large) levels; 1 disables the split
+static int g_solve_cluster_minpix = 65536;
+
+template <int ARITH, int JAC, bool NEED_H, int CL>
+static cudaError_t launch_solve_k(dvo_ctx* c, const SolveArgs& a, int count) {
+    constexpr int THREADS = 256;
+    if (CL == 1) { solve_kernel<ARITH, JAC, NEED_H, THREADS, 1><<<count, THREADS, 0, c->stream>>>(a); return cudaGetLastError(); }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)count * CL); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, solve_kernel<ARITH, JAC, NEED_H, THREADS, CL>, a);
+}
 
 template <int ARITH, int JAC>
-static void launch_solve_t(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
-    if (g_solve_threads == 128) {
-        if (need_h) solve_kernel<ARITH, JAC, true, 128><<<count, 128, 0, c->stream>>>(a);
-        else solve_kernel<ARITH, JAC, false, 128><<<count, 128, 0, c->stream>>>(a);
-    } else if (g_solve_threads == 512) {
-        if (need_h) solve_kernel<ARITH, JAC, true, 512><<<count, 512, 0, c->stream>>>(a);
-        else solve_kernel<ARITH, JAC, false, 512><<<count, 512, 0, c->stream>>>(a);
-    } else {
-        if (need_h) solve_kernel<ARITH, JAC, true, 256><<<count, 256, 0, c->stream>>>(a);
-        else solve_kernel<ARITH, JAC, false, 256><<<count, 256, 0, c->stream>>>(a);
+static cudaError_t launch_solve_t(dvo_ctx* c, const SolveArgs& a, int count, bool need_h, int cl) {
+    if (need_h) {
+        if (cl == 2) return launch_solve_k<ARITH, JAC, true, 2>(c, a, count);
+        if (cl == 4) return launch_solve_k<ARITH, JAC, true, 4>(c, a, count);
+        if (cl == 8) return launch_solve_k<ARITH, JAC, true, 8>(c, a, count);
+        return launch_solve_k<ARITH, JAC, true, 1>(c, a, count);
     }
+    if (cl == 2) return launch_solve_k<ARITH, JAC, false, 2>(c, a, count);
+    if (cl == 4) return launch_solve_k<ARITH, JAC, false, 4>(c, a, count);
+    if (cl == 8) return launch_solve_k<ARITH, JAC, false, 8>(c, a, count);
+    return launch_solve_k<ARITH, JAC, false, 1>(c, a, count);
+}
+
+static cudaError_t launch_solve_any(dvo_ctx* c, const SolveArgs& a, int count, bool need_h, int cl) {
+    const int ar = a.prm.arithmetic == DVO_ARITH_FAST ? DVO_ARITH_FAST : DVO_ARITH_EXACT;
+    const int jc = a.prm.jacobian == DVO_JAC_EXACT ? DVO_JAC_EXACT : DVO_JAC_REFERENCE;
+    if (ar == DVO_ARITH_EXACT && jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_REFERENCE>(c, a, count, need_h, cl);
+    if (ar == DVO_ARITH_EXACT) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_EXACT>(c, a, count, need_h, cl);
+    if (jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_REFERENCE>(c, a, count, need_h, cl);
+    return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_EXACT>(c, a, count, need_h, cl);
 }
 
 int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
-    if (const char* e = getenv("DVO_SOLVE_THREADS")) g_solve_threads = atoi(e);
+    if (const char* e = getenv("DVO_SOLVE_CLUSTER")) g_solve_cluster = atoi(e);
+    if (const char* e = getenv("DVO_SOLVE_CLUSTER_MINPIX")) g_solve_cluster_minpix = atoi(e);
     SolveArgs a;
     a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts;
     a.nedge_now = c->nedge + (size_t)DVO_FRAME_NOW * c->geom.Bmax * c->geom.L; a.texel = c->texel;
     a.pose0 = c->pose0; a.pose = c->pose; a.info = c->info; a.trace = c->trace; a.trace_iters = c->cfg.trace_iters;
-    a.prm = *p; a.first = first;
+    a.prm = *p; a.first = first; a.resume = 0;
     // H is needed by GN / LM, and by SUBGRAD_REF only when a trace is kept (parity tests on J^T W J)
     const bool need_h = (p->solver != DVO_SOLVER_SUBGRAD_REF) || (c->trace != nullptr);
     if (c->trace) DVO_CUDA(cudaMemsetAsync(c->trace + (size_t)first * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, 0,
                                            sizeof(double) * (size_t)count * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, c->stream));
-    const int ar = p->arithmetic == DVO_ARITH_FAST ? DVO_ARITH_FAST : DVO_ARITH_EXACT;
-    const int jc = p->jacobian == DVO_JAC_EXACT ? DVO_JAC_EXACT : DVO_JAC_REFERENCE;
-    if (ar == DVO_ARITH_EXACT && jc == DVO_JAC_REFERENCE) launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_REFERENCE>(c, a, count, need_h);
-    else if (ar == DVO_ARITH_EXACT) launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_EXACT>(c, a, count, need_h);
-    else if (jc == DVO_JAC_REFERENCE) launch_solve_t<DVO_ARITH_FAST, DVO_JAC_REFERENCE>(c, a, count, need_h);
-    else launch_solve_t<DVO_ARITH_FAST, DVO_JAC_EXACT>(c, a, count, need_h);
+    // Level split: coarse levels (few points, dominated by the serial step) run with one CTA per pair; the large
+    // levels run with a cluster per pair so that fewer pairs are in flight and their texels stay in L2.
+    const int cl = (g_solve_cluster == 2 || g_solve_cluster == 4 || g_solve_cluster == 8) ? g_solve_cluster : 1;
+    bool any_fine = false, any_coarse = false;
+    for (int l = 0; l < c->geom.L; ++l) {
+        if (p->iters[l] <= 0) continue;
+        if (cl > 1 && c->geom.P[l] >= g_solve_cluster_minpix) any_fine = true; else any_coarse = true;
+    }
+    if (!any_fine) {
+        DVO_CUDA(launch_solve_any(c, a, count, need_h, 1));
+        c->launches++;
+        return DVO_OK;
+    }
+    if (any_coarse) {
+        SolveArgs ac = a;
+        for (int l = 0; l < c->geom.L; ++l) if (c->geom.P[l] >= g_solve_cluster_minpix) ac.prm.iters[l] = 0;
+        DVO_CUDA(launch_solve_any(c, ac, count, need_h, 1));
+        c->launches++;
+    }
+    SolveArgs af = a;
+    for (int l = 0; l < c->geom.L; ++l) if (c->geom.P[l] < g_solve_cluster_minpix) af.prm.iters[l] = 0;
+    af.resume = any_coarse ? 1 : 0;
+    DVO_CUDA(launch_solve_any(c, af, count, need_h, cl));
     c->launches++;
-    DVO_CUDA(cudaGetLastError());
     return DVO_OK;
 }
 
