@@ -49,6 +49,7 @@ struct dvo_ctx {
     float *ptsX, *ptsY, *ptsZ;   // ref: back-projected edge points (row-major pixel order), capacity P[l] per slot and level
     int* ptsPix;                 // ref: pixel index y*w+x of every point (restores the reference's column-major order)
     int* npts;               // [Bmax][L]
+    int* solve_order;        // [Bmax] pair slots of the current solve launch, heaviest first
     unsigned* nedge;         // [2][Bmax][L]
     unsigned* maxd2;         // [Bmax][L]
     double* pose0;           // [Bmax][12]

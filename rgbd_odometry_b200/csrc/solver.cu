@@ -3,12 +3,9 @@
 // H = J^T W J, the 6-vector step / 6x6 solve, SE(3) update, best-iterate tracking, termination) with no host
 // round trip.  Follows SolveDVO::runIterations (src/SolveDVO.cpp:619-1017), computeJacobianOfNowFrame
 // (:306-414) and getReprojectedEpsilons (:425-462); see SURVEY.md Appendix A for the restated arithmetic.
-#include <cooperative_groups.h>
 #include <stdlib.h>
 
 #include "common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -37,7 +34,7 @@ __device__ __forceinline__ void se3_exp_dev(const double* psi, double* R, double
     const double th2 = wx * wx + wy * wy + wz * wz, th = sqrt(th2);
     double A, B, C;
     if (th < 1e-5) { A = 1.0 - th2 / 6.0; B = 0.5 - th2 / 24.0; C = 1.0 / 6.0 - th2 / 120.0; }
-    else { const double s = sin(th), c = cos(th); A = s / th; B = (1.0 - c) / th2; C = (th - s) / (th2 * th); }
+    else { double s, c; sincos(th, &s, &c); const double ith = 1.0 / th, ith2 = ith * ith; A = s * ith; B = (1.0 - c) * ith2; C = (th - s) * (ith2 * ith); }
     const double O[9] = {0, -wz, wy, wz, 0, -wx, -wy, wx, 0};
     double O2[9]; m3_mul(O, O, O2);
     double V[9];
@@ -107,24 +104,65 @@ __device__ __forceinline__ void rotationize_dev(double* R) {
 }
 
 // 6x6 SPD solve by Cholesky; reads the upper triangle of H (row-major).  Returns false if not positive definite.
+// The solver's serial step runs on one thread per pair while the CTA waits, so its dependent fp64 chain is what
+// counts: the factor is kept as L with the reciprocal diagonal (one rsqrt per column, no division or square root
+// anywhere else) and everything stays in registers.  Agrees with the oracle's sqrt/divide form to a few ulps.
 __device__ __forceinline__ bool chol6_dev(const double* H, const double* b, double* x) {
-    double Lm[36];
-    for (int i = 0; i < 6; ++i)
-        for (int j = 0; j <= i; ++j) {
-            double s = H[6 * j + i];
-            for (int k = 0; k < j; ++k) s -= Lm[6 * i + k] * Lm[6 * j + k];
-            if (i == j) { if (!(s > 0)) return false; Lm[6 * i + i] = sqrt(s); }
-            else Lm[6 * i + j] = s / Lm[6 * j + j];
+    double Lm[6][6], inv[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+        double d = H[6 * j + j];
+#pragma unroll
+        for (int k = 0; k < j; ++k) d = fma(-Lm[j][k], Lm[j][k], d);
+        if (!(d > 0)) return false;
+        const double r = rsqrt(d);
+        inv[j] = r;
+#pragma unroll
+        for (int i = j + 1; i < 6; ++i) {
+            double v = H[6 * j + i];
+#pragma unroll
+            for (int k = 0; k < j; ++k) v = fma(-Lm[i][k], Lm[j][k], v);
+            Lm[i][j] = v * r;
         }
+    }
     double y[6];
-    for (int i = 0; i < 6; ++i) { double s = b[i]; for (int k = 0; k < i; ++k) s -= Lm[6 * i + k] * y[k]; y[i] = s / Lm[6 * i + i]; }
-    for (int i = 5; i >= 0; --i) { double s = y[i]; for (int k = i + 1; k < 6; ++k) s -= Lm[6 * k + i] * x[k]; x[i] = s / Lm[6 * i + i]; }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        double v = b[i];
+#pragma unroll
+        for (int k = 0; k < i; ++k) v = fma(-Lm[i][k], y[k], v);
+        y[i] = v * inv[i];
+    }
+#pragma unroll
+    for (int i = 5; i >= 0; --i) {
+        double v = y[i];
+#pragma unroll
+        for (int k = i + 1; k < 6; ++k) v = fma(-Lm[k][i], x[k], v);
+        x[i] = v * inv[i];
+    }
     return true;
 }
 
 // ------------------------------------------------------------------ per-point evaluation
 struct PoseF { float R[9], T[3]; };
-struct LevelCam { float M00, M02, M11, M12; int w, h; };
+struct LevelCam { float M00, M02, M11, M12; int w, h; float wf, hf, M00_lo, M11_lo; };
+
+// Z = p'_z * RN(1/p'_z) (:339-341) can only round to 1 or to the float just below 1 (the reciprocal is correctly
+// rounded, so the product lies within 2^-24 of 1).  The four IEEE divisions of the reference's A1 matrix (:388-393)
+// therefore have closed forms: c/Z is a per-level constant, and a/(Z*Z) = a/(1-2^-23) is the float rounding of
+// double(a) * RN64(1/(1-2^-23)) -- checked against a/Z for all 2^32 float inputs.  Any other Z takes
+// the generic IEEE division.
+#define DVO_Z_BELOW_ONE 0x3F7FFFFF
+__device__ __forceinline__ LevelCam make_level_cam(const Intr& K, const PyrGeom& geom, int l) {
+    LevelCam cam;
+    const float scaleFac = (float)ldexp(1.0, -l);                                       // :334
+    cam.M00 = __fmul_rn(scaleFac, K.fx); cam.M02 = __fmul_rn(scaleFac, K.cx);            // scaleMatrix * K (:344)
+    cam.M11 = __fmul_rn(scaleFac, K.fy); cam.M12 = __fmul_rn(scaleFac, K.cy);
+    cam.w = geom.w[l]; cam.h = geom.h[l]; cam.wf = (float)cam.w; cam.hf = (float)cam.h;
+    cam.M00_lo = __fdiv_rn(cam.M00, __int_as_float(DVO_Z_BELOW_ONE));
+    cam.M11_lo = __fdiv_rn(cam.M11, __int_as_float(DVO_Z_BELOW_ONE));
+    return cam;
+}
 
 // Reprojection of one reference edge point (computeJacobianOfNowFrame "Step 2/3", src/SolveDVO.cpp:327-345).
 // idx < 0 when the reprojection falls outside the now image (J = eps = w = 0, :371-374).
@@ -143,7 +181,7 @@ __device__ __forceinline__ Proj project_point(float Xp, float Yp, float Zp, cons
     o.X = E::mul(o.px, o.inv); o.Y = E::mul(o.py, o.inv); o.Z = E::mul(o.pz, o.inv);   // :340-341
     o.u = E::dot2(cam.M00, o.X, cam.M02, o.Z);                                   // :344
     o.v = E::dot2(cam.M11, o.Y, cam.M12, o.Z);
-    const bool vis = (o.u >= 0.0f && o.u < (float)cam.w && o.v >= 0.0f && o.v < (float)cam.h);
+    const bool vis = (o.u >= 0.0f && o.u < cam.wf && o.v >= 0.0f && o.v < cam.hf);
     o.idx = vis ? __float2int_rz(o.v) * cam.w + __float2int_rz(o.u) : -1;        // :376-377
     return o;
 }
@@ -157,9 +195,18 @@ __device__ __forceinline__ void finish_point(const Proj& q, const float4 t, cons
     const float G0 = t.y, G1 = t.z;
     if (JAC == DVO_JAC_REFERENCE) {
         const float X = q.X, Y = q.Y, Z = q.Z;
-        const float ZZ = A::mul(Z, Z);
-        const float A00 = A::div(cam.M00, Z), A02 = -A::div(A::mul(cam.M00, X), ZZ);     // :388-390
-        const float A11 = A::div(cam.M11, Z), A12 = -A::div(A::mul(cam.M11, Y), ZZ);     // :392-393
+        float A00, A02, A11, A12;
+        const bool one = (Z == 1.0f), lo = (__float_as_int(Z) == DVO_Z_BELOW_ONE);
+        if (ARITH == DVO_ARITH_EXACT && (one || lo)) {
+            const double rzz = one ? 1.0 : 0x1.000002000004p+0;                          // RN64(1 / (1 - 2^-23))
+            A00 = one ? cam.M00 : cam.M00_lo; A11 = one ? cam.M11 : cam.M11_lo;          // :388, :392
+            A02 = -(float)((double)A::mul(cam.M00, X) * rzz);                            // :390
+            A12 = -(float)((double)A::mul(cam.M11, Y) * rzz);                            // :393
+        } else {
+            const float ZZ = A::mul(Z, Z);
+            A00 = A::div(cam.M00, Z); A02 = -A::div(A::mul(cam.M00, X), ZZ);
+            A11 = A::div(cam.M11, Z); A12 = -A::div(A::mul(cam.M11, Y), ZZ);
+        }
         const float w0 = A::dot3(R[0], X, R[3], Y, R[6], Z);                             // :399
         const float w1 = A::dot3(R[1], X, R[4], Y, R[7], Z);
         const float w2 = A::dot3(R[2], X, R[5], Y, R[8], Z);
@@ -194,7 +241,9 @@ __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, c
                                                   const float* __restrict__ Z, int N, const PoseF& P, const LevelCam& cam,
                                                   const float4* __restrict__ tex, int weight_mode, float huber_k,
                                                   double* acc, int& nvis, float* o_eps, float* o_w, float* o_u, float* o_v,
-                                                  float* o_J, int start = threadIdx.x, int stride = THREADS) {
+                                                  float* o_J) {
+    constexpr int stride = THREADS;
+    const int start = threadIdx.x;
     typedef Ar<ARITH> A;
     int i = start;
     if (i >= N) return;
@@ -245,17 +294,49 @@ __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, c
     }
 }
 
-// Deterministic block reduction: fixed shuffle tree inside each warp, then warp partials summed in warp order.
+// Deterministic block reduction of NACC fp64 accumulators per thread.
+// Stage 1 (per warp).  TRANSPOSED (the 29-accumulator Gauss-Newton case): eight accumulators at a time are parked
+// in a [8][36] shared tile (row = accumulator, column = lane); lane (r, q) = (lane / 4, lane % 4) sums columns
+// q, q+4, .. of row r and two xor-shuffles combine the four quarters -- 1 store + 1 load per value instead of the
+// 5-level shuffle tree (15 instructions per value), which was a third of the fixed per-iteration cost.  The row
+// stride of 36 doubles makes both the stores and the strided loads bank-conflict free.  The small tile (2.3 KB per
+// warp) is deliberate: a full [29][33] tile cost 61 KB per CTA of L1 capacity and slowed the gather-bound sweep.
+// The 8-accumulator sub-gradient case keeps the shuffle tree (its tile pass would not be shorter).
+// Stage 2: thread k sums the warp partials in warp order.
+template <int NACC> struct ReduceScratch {
+    static constexpr bool TRANSPOSED = (NACC > 8);
+    static constexpr int ROW = 36, PER_WARP = TRANSPOSED ? 8 * ROW : 1;
+};
+
 template <int NACC, int THREADS>
-__device__ __forceinline__ void block_reduce(double* acc, int nvis, double (*s_red)[NACC], int* s_nv, double* s_tot, int* s_nvtot) {
+__device__ __forceinline__ void block_reduce(double* acc, int nvis, double* s_scr, double (*s_red)[NACC], int* s_nv, double* s_tot, int* s_nvtot) {
     constexpr int SOLVE_WARPS = THREADS / 32;
+    typedef ReduceScratch<NACC> RS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (RS::TRANSPOSED) {
+        double* ws = s_scr + warp * RS::PER_WARP;
+        const int r = lane >> 2, q = lane & 3;
 #pragma unroll
-    for (int k = 0; k < NACC; ++k) {
-        double v = acc[k];
+        for (int p0 = 0; p0 < NACC; p0 += 8) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][k] = v;
+            for (int k = 0; k < 8; ++k) if (p0 + k < NACC) ws[k * RS::ROW + lane] = acc[p0 + k];
+            __syncwarp();
+            double v = 0.0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v += ws[r * RS::ROW + 4 * j + q];
+            v += __shfl_xor_sync(0xffffffffu, v, 1);
+            v += __shfl_xor_sync(0xffffffffu, v, 2);
+            if (q == 0 && p0 + r < NACC) s_red[warp][p0 + r] = v;
+            __syncwarp();
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if (lane == 0) s_red[warp][k] = v;
+        }
     }
     for (int o = 16; o > 0; o >>= 1) nvis += __shfl_down_sync(0xffffffffu, nvis, o);
     if (lane == 0) s_nv[warp] = nvis;
@@ -282,9 +363,8 @@ struct SolverState {
 struct SolveArgs {
     PyrGeom geom; Intr K;
     const float *X, *Y, *Z; const int* npts; const unsigned* nedge_now; const float4* texel;
-    const double* pose0; double* pose; dvo_pair_info* info; double* trace; int trace_iters;
+    const double* pose0; double* pose; dvo_pair_info* info; double* trace; int trace_iters; const int* order;
     dvo_solver_params prm; int first;
-    int resume;             // 1: continue from the pose / info already in the output buffers (second launch of a level split)
 };
 
 // One iteration's serial tail (thread 0): best tracking, step computation, pose update.  Returns 1 to stop the level.
@@ -315,7 +395,7 @@ __device__ __forceinline__ int solver_step(SolverState& S, const double* tot, in
         double g[6]; for (int k = 0; k < 6; ++k) g[k] = tot[k];
         double cPsi[6]; se3_log_dev(S.cR, S.cT, cPsi);                            // :736-739
         double cn = 0; for (int k = 0; k < 6; ++k) cn += cPsi[k] * cPsi[k]; cn = sqrt(cn);
-        if (cn > 0) for (int k = 0; k < 6; ++k) cPsi[k] = cPsi[k] / cn;           // :740-741
+        if (cn > 0) { const double icn = 1.0 / cn; for (int k = 0; k < 6; ++k) cPsi[k] *= icn; }   // :740-741 (one reciprocal instead of six divisions)
         const double stepLength = 9.0 * 1.0E-2 / ((itr > 5) ? (double)(itr - 4) : 1.0);   // :773
         for (int k = 0; k < 6; ++k) g[k] += 0.05 * cPsi[k];                       // :796
         for (int k = 0; k < 6; ++k) S.descent[k] = 0.5 * g[k] + 0.5 * S.descent[k];      // :799
@@ -324,7 +404,7 @@ __device__ __forceinline__ int solver_step(SolverState& S, const double* tot, in
         for (int k = 0; k < 6; ++k) { psi[k] = -stepLength * Pv[k] * S.descent[k]; nrm += psi[k] * psi[k]; }   // :821
         nrm = sqrt(nrm);
         const double radius = (double)0.003f;                                     // :25, :835
-        if (nrm > radius) { for (int k = 0; k < 6; ++k) psi[k] = psi[k] / nrm * radius; }
+        if (nrm > radius) { const double sc = radius / nrm; for (int k = 0; k < 6; ++k) psi[k] *= sc; }
         else if (nrm < (double)1.0E-7f) return 1;                                 // :840 -> :872
     } else {
         const bool accept = (prm.solver == DVO_SOLVER_GN) || !S.have_acc || (energy <= S.accE);
@@ -359,17 +439,46 @@ __device__ __forceinline__ int solver_step(SolverState& S, const double* tot, in
     return 0;
 }
 
-// CL = CTAs per frame pair.  CL == 1: one CTA owns a pair.  CL > 1: a thread-block cluster owns a pair -- the point list
-// is striped over the cluster's CTAs, partial sums are combined by rank 0 through distributed shared memory in rank
-// order (deterministic), rank 0 runs the serial step and pushes the next pose / stop flag into every rank's shared
-// memory.  Spreading one pair over several SMs keeps fewer pairs in flight, so a level's texels stay L2-resident across
-// iterations instead of being re-fetched from HBM every iteration.  MEASURED (1024 pairs, GN 10 it/level): CL = 1: 4.29 ms,
-// CL = 2: 4.58 ms, CL = 4: 5.53 ms, CL = 8: 8.62 ms -- the two cluster barriers and the serial step per iteration cost more
-// than the L2 residency returns, so CL = 1 is the default (DVO_SOLVE_CLUSTER selects the others).
-template <int ARITH, int JAC, bool NEED_H, int THREADS, int CL>
+// Launch order: heaviest pairs first (longest-processing-time-first).  A pair occupies its CTA for the whole schedule
+// (~1 ms), so with B / (CTAs resident) only a few "waves" the makespan is set by what the last-started CTAs still
+// have to do; starting the big pairs first leaves the short ones for the tail.  Work = sum_l iters[l] * npts[l],
+// bucketed into 256 classes by a single CTA (counting sort; the order inside a class is irrelevant to the results).
+__global__ void __launch_bounds__(1024) solve_order_kernel(const int* __restrict__ npts, int L, dvo_solver_params prm, int first, int count,
+                                                           int* __restrict__ order) {
+    __shared__ unsigned s_max, s_cnt[256], s_base[256];
+    const int tid = threadIdx.x;
+    if (tid == 0) s_max = 1u;
+    if (tid < 256) s_cnt[tid] = 0u;
+    __syncthreads();
+    auto work = [&](int i) {
+        unsigned wk = 0;
+        for (int l = 0; l < L; ++l) wk += (unsigned)max(prm.iters[l], 0) * (unsigned)npts[(long long)(first + i) * L + l];
+        return wk;
+    };
+    unsigned m = 0;
+    for (int i = tid; i < count; i += blockDim.x) m = max(m, work(i));
+    atomicMax(&s_max, m);
+    __syncthreads();
+    const float scale = 255.0f / (float)s_max;
+    for (int i = tid; i < count; i += blockDim.x) atomicAdd(&s_cnt[255 - min(255, (int)((float)work(i) * scale))], 1u);
+    __syncthreads();
+    if (tid == 0) { unsigned run = 0; for (int k = 0; k < 256; ++k) { s_base[k] = run; run += s_cnt[k]; } }
+    __syncthreads();
+    for (int i = tid; i < count; i += blockDim.x) {
+        const int cls = 255 - min(255, (int)((float)work(i) * scale));
+        order[atomicAdd(&s_base[cls], 1u)] = first + i;
+    }
+}
+
+// One CTA owns a frame pair for the whole coarse-to-fine schedule.  (A thread-block-cluster variant that striped a
+// pair's points over 2/4/8 CTAs and combined partial sums through distributed shared memory was measured slower --
+// 4.29 ms -> 4.58 / 5.53 / 8.62 ms per 1024 pairs -- and removed; so was a cp.async shared-memory ring that kept 2..8
+// texel gathers in flight per thread: 4.56 .. 4.72 ms.  See DESIGN.md "measured and rejected".)
+template <int ARITH, int JAC, bool NEED_H, int THREADS>
 __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve_kernel(SolveArgs a) {
     constexpr int NACC = AccN<NEED_H>::N;
     constexpr int SOLVE_WARPS = THREADS / 32;
+    __shared__ double s_scr[SOLVE_WARPS * ReduceScratch<NACC>::PER_WARP];
     __shared__ double s_red[SOLVE_WARPS][NACC];
     __shared__ double s_tot[NACC];
     __shared__ int s_nv[SOLVE_WARPS];
@@ -378,38 +487,19 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
     __shared__ SolverState S;
     __shared__ dvo_pair_info s_info;
 
-    cg::cluster_group cluster = cg::this_cluster();
-    const int rank = (CL > 1) ? (int)cluster.block_rank() : 0;
-    const int b = a.first + blockIdx.x / CL;
+    const int b = a.order[blockIdx.x];
     const int L = a.geom.L;
-    const bool lead = (rank == 0 && threadIdx.x == 0);
+    const bool lead = (threadIdx.x == 0);
     if (lead) {
-        const double* src = a.resume ? a.pose : a.pose0;
-        for (int k = 0; k < 9; ++k) S.cR[k] = src[12 * (long long)b + k];
-        for (int k = 0; k < 3; ++k) S.cT[k] = src[12 * (long long)b + 9 + k];
-        if (a.resume) s_info = a.info[b];
-        else {
-            s_info.status = 0; s_info.laplacian_b = 0.f;
-            for (int l = 0; l < DVO_MAX_LEVELS; ++l) {
-                s_info.npts[l] = (l < L) ? a.npts[(long long)b * L + l] : 0; s_info.best_index[l] = -1; s_info.iterations_run[l] = 0;
-                s_info.best_energy[l] = 0.f; s_info.visible_ratio[l] = 0.f;
-            }
+        for (int k = 0; k < 9; ++k) S.cR[k] = a.pose0[12 * (long long)b + k];
+        for (int k = 0; k < 3; ++k) S.cT[k] = a.pose0[12 * (long long)b + 9 + k];
+        s_info.status = 0; s_info.laplacian_b = 0.f;
+        for (int l = 0; l < DVO_MAX_LEVELS; ++l) {
+            s_info.npts[l] = (l < L) ? a.npts[(long long)b * L + l] : 0; s_info.best_index[l] = -1; s_info.iterations_run[l] = 0;
+            s_info.best_energy[l] = 0.f; s_info.visible_ratio[l] = 0.f;
         }
     }
     __syncthreads();
-
-    // rank 0: publish s_pose / s_stop to every rank of the cluster, then cluster barrier
-    auto publish = [&]() {
-        if (CL > 1) {
-            __syncthreads();
-            if (rank == 0 && threadIdx.x < 13 * (CL - 1)) {
-                const int r = 1 + threadIdx.x / 13, k = threadIdx.x % 13;
-                if (k < 12) { float* dst = cluster.map_shared_rank(reinterpret_cast<float*>(&s_pose), r); dst[k] = reinterpret_cast<float*>(&s_pose)[k]; }
-                else { int* dst = cluster.map_shared_rank(&s_stop, r); *dst = s_stop; }
-            }
-            cluster.sync();
-        } else __syncthreads();
-    };
 
     for (int l = L - 1; l >= 0; --l) {
         const int iters = a.prm.iters[l];
@@ -420,11 +510,7 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
         const long long base = lvl_at(a.geom, l, b);
         const float* X = a.X + base; const float* Y = a.Y + base; const float* Z = a.Z + base;
         const float4* tex = a.texel + base;
-        LevelCam cam;
-        const float scaleFac = (float)ldexp(1.0, -l);                                       // :334
-        cam.M00 = __fmul_rn(scaleFac, a.K.fx); cam.M02 = __fmul_rn(scaleFac, a.K.cx);         // scaleMatrix * K (:344)
-        cam.M11 = __fmul_rn(scaleFac, a.K.fy); cam.M12 = __fmul_rn(scaleFac, a.K.cy);
-        cam.w = a.geom.w[l]; cam.h = a.geom.h[l];
+        const LevelCam cam = make_level_cam(a.K, a.geom, l);
         if (lead) {
             S.bestE = 1.0E10f; S.bestRatio = 1.0f; S.bestItr = -1; S.bestSumEps = 0.0;        // :642-650
             for (int k = 0; k < 9; ++k) S.bestR[k] = (k % 4 == 0) ? 1.0 : 0.0;
@@ -435,7 +521,7 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
             for (int k = 0; k < 3; ++k) s_pose.T[k] = (float)S.cT[k];
             s_stop = 0;
         }
-        publish();
+        __syncthreads();
         for (int itr = 0; itr < iters; ++itr) {
             PoseF P = s_pose;
             double acc[NACC];
@@ -443,20 +529,8 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
             int nvis = 0;
             accumulate_points<ARITH, JAC, NEED_H, THREADS, false>(X, Y, Z, N, P, cam, tex, a.prm.weight, a.prm.huber_k, acc, nvis,
-                                                  nullptr, nullptr, nullptr, nullptr, nullptr, rank * THREADS + (int)threadIdx.x, THREADS * CL);
-            block_reduce<NACC, THREADS>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
-            if (CL > 1) {
-                cluster.sync();                                                               // every rank's partial sums are in place
-                if (rank == 0) {
-                    if (threadIdx.x < NACC) {
-                        double v = s_tot[threadIdx.x];
-                        for (int r = 1; r < CL; ++r) v += cluster.map_shared_rank(s_tot, r)[threadIdx.x];
-                        s_tot[threadIdx.x] = v;
-                    }
-                    if (threadIdx.x == 32) { int n = s_nvtot; for (int r = 1; r < CL; ++r) n += *cluster.map_shared_rank(&s_nvtot, r); s_nvtot = n; }
-                    __syncthreads();
-                }
-            }
+                                                  nullptr, nullptr, nullptr, nullptr, nullptr);
+            block_reduce<NACC, THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
             if (lead) {
                 double* tr = nullptr;
                 if (a.trace && itr < a.trace_iters)
@@ -465,7 +539,7 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
                 for (int k = 0; k < 9; ++k) s_pose.R[k] = (float)S.cR[k];                      // pose of the next iteration (:673-674)
                 for (int k = 0; k < 3; ++k) s_pose.T[k] = (float)S.cT[k];
             }
-            publish();
+            __syncthreads();
             if (s_stop) break;
         }
         if (lead) {
@@ -482,7 +556,6 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
         for (int k = 0; k < 3; ++k) a.pose[12 * (long long)b + 9 + k] = S.cT[k];
         a.info[b] = s_info;
     }
-    if (CL > 1) cluster.sync();            // no CTA may exit while a peer can still touch its shared memory
 }
 
 // ------------------------------------------------------------------ single evaluation (parity inspection)
@@ -498,6 +571,7 @@ template <int ARITH, int JAC>
 __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
     constexpr int NACC = AccN<true>::N;
     constexpr int SOLVE_WARPS = EVAL_THREADS / 32;
+    __shared__ double s_scr[SOLVE_WARPS * ReduceScratch<NACC>::PER_WARP];
     __shared__ double s_red[SOLVE_WARPS][NACC];
     __shared__ double s_tot[NACC];
     __shared__ int s_nv[SOLVE_WARPS];
@@ -508,18 +582,14 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
     PoseF P;
     for (int k = 0; k < 9; ++k) P.R[k] = (float)a.pose[k];
     for (int k = 0; k < 3; ++k) P.T[k] = (float)a.pose[9 + k];
-    LevelCam cam;
-    const float scaleFac = (float)ldexp(1.0, -l);
-    cam.M00 = __fmul_rn(scaleFac, a.K.fx); cam.M02 = __fmul_rn(scaleFac, a.K.cx);
-    cam.M11 = __fmul_rn(scaleFac, a.K.fy); cam.M12 = __fmul_rn(scaleFac, a.K.cy);
-    cam.w = a.geom.w[l]; cam.h = a.geom.h[l];
+    const LevelCam cam = make_level_cam(a.K, a.geom, l);
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     int nvis = 0;
     accumulate_points<ARITH, JAC, true, EVAL_THREADS, true>(a.X + base, a.Y + base, a.Z + base, N, P, cam, a.texel + base, a.weight, a.huber_k,
                                         acc, nvis, a.eps, a.w, a.u, a.v, a.J);
-    block_reduce<NACC, EVAL_THREADS>(acc, nvis, s_red, s_nv, s_tot, &s_nvtot);
+    block_reduce<NACC, EVAL_THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
     if (threadIdx.x == 0) {
         for (int k = 0; k < 6; ++k) a.out[k] = s_tot[k];
         int idx = 8;
@@ -550,79 +620,37 @@ __global__ void gop_kernel(int nseq, int nframes, const int* __restrict__ kind, 
 
 }  // namespace
 
-static int g_solve_cluster = 1;          // CTAs per pair on the fine (large) levels; 1 disables the split
-static int g_solve_cluster_minpix = 65536;
-
-template <int ARITH, int JAC, bool NEED_H, int CL>
-static cudaError_t launch_solve_k(dvo_ctx* c, const SolveArgs& a, int count) {
-    constexpr int THREADS = 256;
-    if (CL == 1) { solve_kernel<ARITH, JAC, NEED_H, THREADS, 1><<<count, THREADS, 0, c->stream>>>(a); return cudaGetLastError(); }
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)count * CL); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, solve_kernel<ARITH, JAC, NEED_H, THREADS, CL>, a);
-}
-
 template <int ARITH, int JAC>
-static cudaError_t launch_solve_t(dvo_ctx* c, const SolveArgs& a, int count, bool need_h, int cl) {
-    if (need_h) {
-        if (cl == 2) return launch_solve_k<ARITH, JAC, true, 2>(c, a, count);
-        if (cl == 4) return launch_solve_k<ARITH, JAC, true, 4>(c, a, count);
-        if (cl == 8) return launch_solve_k<ARITH, JAC, true, 8>(c, a, count);
-        return launch_solve_k<ARITH, JAC, true, 1>(c, a, count);
-    }
-    if (cl == 2) return launch_solve_k<ARITH, JAC, false, 2>(c, a, count);
-    if (cl == 4) return launch_solve_k<ARITH, JAC, false, 4>(c, a, count);
-    if (cl == 8) return launch_solve_k<ARITH, JAC, false, 8>(c, a, count);
-    return launch_solve_k<ARITH, JAC, false, 1>(c, a, count);
+static cudaError_t launch_solve_t(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
+    constexpr int THREADS = 256;
+    if (need_h) solve_kernel<ARITH, JAC, true, THREADS><<<count, THREADS, 0, c->stream>>>(a);
+    else solve_kernel<ARITH, JAC, false, THREADS><<<count, THREADS, 0, c->stream>>>(a);
+    return cudaGetLastError();
 }
 
-static cudaError_t launch_solve_any(dvo_ctx* c, const SolveArgs& a, int count, bool need_h, int cl) {
+static cudaError_t launch_solve_any(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
     const int ar = a.prm.arithmetic == DVO_ARITH_FAST ? DVO_ARITH_FAST : DVO_ARITH_EXACT;
     const int jc = a.prm.jacobian == DVO_JAC_EXACT ? DVO_JAC_EXACT : DVO_JAC_REFERENCE;
-    if (ar == DVO_ARITH_EXACT && jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_REFERENCE>(c, a, count, need_h, cl);
-    if (ar == DVO_ARITH_EXACT) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_EXACT>(c, a, count, need_h, cl);
-    if (jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_REFERENCE>(c, a, count, need_h, cl);
-    return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_EXACT>(c, a, count, need_h, cl);
+    if (ar == DVO_ARITH_EXACT && jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_REFERENCE>(c, a, count, need_h);
+    if (ar == DVO_ARITH_EXACT) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_EXACT>(c, a, count, need_h);
+    if (jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_REFERENCE>(c, a, count, need_h);
+    return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_EXACT>(c, a, count, need_h);
 }
 
 int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
-    if (const char* e = getenv("DVO_SOLVE_CLUSTER")) g_solve_cluster = atoi(e);
-    if (const char* e = getenv("DVO_SOLVE_CLUSTER_MINPIX")) g_solve_cluster_minpix = atoi(e);
     SolveArgs a;
     a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts;
     a.nedge_now = c->nedge + (size_t)DVO_FRAME_NOW * c->geom.Bmax * c->geom.L; a.texel = c->texel;
     a.pose0 = c->pose0; a.pose = c->pose; a.info = c->info; a.trace = c->trace; a.trace_iters = c->cfg.trace_iters;
-    a.prm = *p; a.first = first; a.resume = 0;
+    a.prm = *p; a.first = first;
     // H is needed by GN / LM, and by SUBGRAD_REF only when a trace is kept (parity tests on J^T W J)
     const bool need_h = (p->solver != DVO_SOLVER_SUBGRAD_REF) || (c->trace != nullptr);
     if (c->trace) DVO_CUDA(cudaMemsetAsync(c->trace + (size_t)first * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, 0,
                                            sizeof(double) * (size_t)count * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, c->stream));
-    // Level split: coarse levels (few points, dominated by the serial step) run with one CTA per pair; the large
-    // levels run with a cluster per pair so that fewer pairs are in flight and their texels stay in L2.
-    const int cl = (g_solve_cluster == 2 || g_solve_cluster == 4 || g_solve_cluster == 8) ? g_solve_cluster : 1;
-    bool any_fine = false, any_coarse = false;
-    for (int l = 0; l < c->geom.L; ++l) {
-        if (p->iters[l] <= 0) continue;
-        if (cl > 1 && c->geom.P[l] >= g_solve_cluster_minpix) any_fine = true; else any_coarse = true;
-    }
-    if (!any_fine) {
-        DVO_CUDA(launch_solve_any(c, a, count, need_h, 1));
-        c->launches++;
-        return DVO_OK;
-    }
-    if (any_coarse) {
-        SolveArgs ac = a;
-        for (int l = 0; l < c->geom.L; ++l) if (c->geom.P[l] >= g_solve_cluster_minpix) ac.prm.iters[l] = 0;
-        DVO_CUDA(launch_solve_any(c, ac, count, need_h, 1));
-        c->launches++;
-    }
-    SolveArgs af = a;
-    for (int l = 0; l < c->geom.L; ++l) if (c->geom.P[l] < g_solve_cluster_minpix) af.prm.iters[l] = 0;
-    af.resume = any_coarse ? 1 : 0;
-    DVO_CUDA(launch_solve_any(c, af, count, need_h, cl));
+    solve_order_kernel<<<1, 1024, 0, c->stream>>>(c->npts, c->geom.L, *p, first, count, c->solve_order);
+    a.order = c->solve_order;
+    DVO_CUDA(launch_solve_any(c, a, count, need_h));
+    c->launches++;
     c->launches++;
     return DVO_OK;
 }
