@@ -45,6 +45,10 @@ enum { DVO_WEIGHT_REF_CAUCHY = 0, DVO_WEIGHT_HUBER = 1, DVO_WEIGHT_NONE = 2 };
 /* per-point fp32 arithmetic: EXACT reproduces the oracle's IEEE operation order bit for bit (no FMA
  * contraction, IEEE division); FAST lets the compiler contract and uses approximate reciprocals. */
 enum { DVO_ARITH_EXACT = 0, DVO_ARITH_FAST = 1 };
+/* residual: DT_FLOOR = eps = DT(floor v, floor u), the shipped build (src/SolveDVO.cpp:446); DT_INTERP = the
+ * reference's compiled-out __INTERPOLATE_DISTANCE_TRANSFORM variant (:443-444, SolveDVO::interpolate :1285-1308):
+ * "squared-bilinear" lookup, weights from getWeightOf of the interpolated value.  EXACT arithmetic only. */
+enum { DVO_RESIDUAL_DT_FLOOR = 0, DVO_RESIDUAL_DT_INTERP = 1 };
 /* pyramid flavour: NEAREST = camTopic2PublisherPyD (src/camTopic2PublisherPyD.cpp:338-348);
  * AREA = EPoseEstimator (src/EPoseEstimator.cpp:251-253, 284-286). */
 enum { DVO_PYR_NEAREST = 0, DVO_PYR_AREA = 1 };
@@ -81,6 +85,7 @@ typedef struct dvo_solver_params {
     float huber_k;
     double lm_lambda0;
     int iters[DVO_MAX_LEVELS];  /* iterationsConfig (src/SolveDVO.cpp:30-33); 0 skips the level */
+    int residual;           /* DVO_RESIDUAL_* (0 = the shipped build)                             */
 } dvo_solver_params;
 
 /* per pair result record (what runIterations returns besides the pose, src/SolveDVO.cpp:997-1005, plus the
@@ -158,6 +163,10 @@ int dvo_get_points(dvo_ctx* ctx, int slot, int level, float* X, float* Y, float*
 int dvo_eval_normal_equations(dvo_ctx* ctx, int slot, int level, const double* R9T3, int jacobian, int weight,
                               int arithmetic, float huber_k, double* H36, double* g6, double* sumsq, int* nvis,
                               float* eps, float* w, float* u, float* v, float* J);
+/* same, with every evaluation option taken from a dvo_solver_params (jacobian, weight, arithmetic, huber_k, residual) */
+int dvo_eval_normal_equations_ex(dvo_ctx* ctx, int slot, int level, const double* R9T3, const dvo_solver_params* prm,
+                                 double* H36, double* g6, double* sumsq, int* nvis,
+                                 float* eps, float* w, float* u, float* v, float* J);
 /* per-iteration trace of the last dvo_run (needs cfg.trace_iters > 0): for level `level`, `trace_iters` records of
  * 56 doubles: g[6], H[36], energy, nvis, R[9], T[3] (zero where not executed) */
 int dvo_get_trace(dvo_ctx* ctx, int slot, int level, double* trace);

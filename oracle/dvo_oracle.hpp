@@ -415,6 +415,9 @@ struct LevelImages { int W = 0, H = 0; std::vector<float> dtn, gx, gy; };
 enum JacobianMode { JAC_REFERENCE = 0, JAC_EXACT = 1 };
 enum WeightMode { W_REF_CAUCHY = 0, W_HUBER = 1, W_NONE = 2 };
 enum SolverMode { SOLVER_SUBGRAD_REF = 0, SOLVER_GN = 1, SOLVER_LM = 2 };
+// RES_DT_FLOOR: eps = DT(floor(v), floor(u)), the shipped build (src/SolveDVO.cpp:446).
+// RES_DT_INTERP: the compiled-out __INTERPOLATE_DISTANCE_TRANSFORM variant (:443-444, interpolate() :1285-1308).
+enum ResidualMode { RES_DT_FLOOR = 0, RES_DT_INTERP = 1 };
 
 struct EvalOut {
     double g[6]; double H[36]; double sumsq; int nvis;
@@ -426,12 +429,30 @@ inline float weight_ref(float r) { float rr = r * r; return (float)(6.0 / (6.0 +
 // Huber weight (extension; north_star "Huber/sub-gradient weights"): w = 1 if |r|<=k else k/|r|.
 inline float weight_huber(float r, float k) { float a = std::fabs(r); return a <= k ? 1.0f : k / a; }
 
+// SolveDVO::interpolate (src/SolveDVO.cpp:1285-1308): "squared-bilinear" lookup sqrt((1-a) F0^2 + a F1^2) along x on
+// the floor and ceil rows, then the same along y; all in fp32, products evaluated left to right.  The reference
+// indexes F(ceil(ry), ceil(rx)) without a bound check although its visibility test admits ry up to rows; with its
+// forced-on asserts (include/SolveDVO.h:124-125) that aborts -- here the ceil indices are clamped to the last
+// row / column (documented deviation, only reachable within one pixel of the bottom / right border).
+inline float interpolate_dt(const float* F, int W, int H, float ry, float rx) {
+    int ry_d = (int)std::floor(ry), rx_d = (int)std::floor(rx);
+    int ry_u = (int)std::ceil(ry), rx_u = (int)std::ceil(rx);
+    float inc_x = rx - (float)rx_d, inc_y = ry - (float)ry_d;
+    if (ry_u > H - 1) ry_u = H - 1;
+    if (rx_u > W - 1) rx_u = W - 1;
+    float Fdd = F[(size_t)ry_d * W + rx_d], Fdu = F[(size_t)ry_d * W + rx_u];
+    float Fud = F[(size_t)ry_u * W + rx_d], Fuu = F[(size_t)ry_u * W + rx_u];
+    float f1 = std::sqrt(((1.0f - inc_x) * Fdd) * Fdd + (inc_x * Fdu) * Fdu);
+    float f2 = std::sqrt(((1.0f - inc_x) * Fud) * Fud + (inc_x * Fuu) * Fuu);
+    return std::sqrt(((1.0f - inc_y) * f1) * f1 + (inc_y * f2) * f2);
+}
+
 // computeJacobianOfNowFrame (src/SolveDVO.cpp:306-414) + getReprojectedEpsilons (:425-462) + the normal
 // equation sums of runIterations (:714-720, :777).  cR, cT are the fp64 pose; they are narrowed to fp32
 // exactly as :673-674 does.  H = sum (double)(J_i w_i)^T (double)J_i is the oracle's GN extension.
 inline void evaluate(const PointList& pts, const LevelImages& now, int level, Intrinsics K, const double* cR,
                      const double* cT, JacobianMode jm, WeightMode wm, float huber_k, bool keep_per_point,
-                     EvalOut& out) {
+                     EvalOut& out, ResidualMode rm = RES_DT_FLOOR) {
     const size_t N = pts.size();
     float R[9], T[3];
     for (int i = 0; i < 9; ++i) R[i] = (float)cR[i];
@@ -489,7 +510,7 @@ inline void evaluate(const PointList& pts, const LevelImages& now, int level, In
             Jr[0] = -a; Jr[1] = -b; Jr[2] = -c;
             Jr[3] = b * pz - c * py; Jr[4] = c * px - a * pz; Jr[5] = a * py - b * px;
         }
-        float e = now.dtn[idx];                                      // :446
+        float e = (rm == RES_DT_INTERP) ? interpolate_dt(now.dtn.data(), nCols, nRows, v, u) : now.dtn[idx];   // :443-446
         float w;
         if (wm == W_REF_CAUCHY) w = weight_ref(e); else if (wm == W_HUBER) w = weight_huber(e, huber_k); else w = 1.0f;
         out.nvis++;
@@ -514,6 +535,7 @@ struct SolverConfig {
     double lm_lambda0 = 1e-3;
     float trust_radius = 0.003f;            // trustRegionHyperSphereRadius (src/SolveDVO.cpp:25)
     float psi_term = 1.0E-7f;               // psiNormTerminationThreshold (:24)
+    ResidualMode residual = RES_DT_FLOOR;
 };
 
 struct IterTrace { double g[6]; double H[36]; float energy; int nvis; double R[9], T[3]; };
@@ -540,7 +562,7 @@ inline void run_iterations(const PointList& pts, const LevelImages& now, int lev
     EvalOut ev;
     const size_t N = pts.size();
     for (int itr = 0; itr < maxIterations; ++itr) {
-        evaluate(pts, now, level, K, cR, cT, cfg.jac, cfg.weight, cfg.huber_k, keep_per_point, ev);
+        evaluate(pts, now, level, K, cR, cT, cfg.jac, cfg.weight, cfg.huber_k, keep_per_point, ev, cfg.residual);
         float ratio = N ? (float)ev.nvis / (float)N : 0.f;            // :457
         float energy = (float)std::sqrt(ev.sumsq);                    // aggregateEpsilons :1310-1312
         res.energies[itr] = energy; res.iterations_run = itr + 1;

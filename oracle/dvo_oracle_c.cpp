@@ -15,13 +15,14 @@ struct orc_solver_cfg {
     int weight;        // 0 REF_CAUCHY, 1 HUBER, 2 NONE
     float huber_k;
     double lm_lambda0;
+    int residual;      // 0 DT at floor (shipped), 1 interpolated DT (compiled-out reference variant)
 };
 
 static SolverConfig to_cfg(const orc_solver_cfg* c) {
     SolverConfig s;
     if (c) {
         s.solver = (SolverMode)c->solver; s.jac = (JacobianMode)c->jacobian; s.weight = (WeightMode)c->weight;
-        s.huber_k = c->huber_k; s.lm_lambda0 = c->lm_lambda0;
+        s.huber_k = c->huber_k; s.lm_lambda0 = c->lm_lambda0; s.residual = (ResidualMode)c->residual;
     }
     return s;
 }
@@ -68,13 +69,13 @@ int orc_select_points(const uint8_t* edge, const uint16_t* depth, int W, int H, 
 void orc_evaluate(const float* X, const float* Y, const float* Z, int N, const float* dtn, const float* gx,
                   const float* gy, int W, int H, int level, float fx, float fy, float cx, float cy, const double* R,
                   const double* T, int jac, int weight, float huber_k, double* g6, double* H36, double* sumsq,
-                  int* nvis, float* eps, float* w, float* ru, float* rv, float* J) {
+                  int* nvis, float* eps, float* w, float* ru, float* rv, float* J, int residual) {
     PointList p; p.X.assign(X, X + N); p.Y.assign(Y, Y + N); p.Z.assign(Z, Z + N);
     LevelImages li; li.W = W; li.H = H; size_t P = (size_t)W * H;
     li.dtn.assign(dtn, dtn + P); li.gx.assign(gx, gx + P); li.gy.assign(gy, gy + P);
     EvalOut ev;
     bool pp = eps || w || ru || rv || J;
-    evaluate(p, li, level, Intrinsics{fx, fy, cx, cy}, R, T, (JacobianMode)jac, (WeightMode)weight, huber_k, pp, ev);
+    evaluate(p, li, level, Intrinsics{fx, fy, cx, cy}, R, T, (JacobianMode)jac, (WeightMode)weight, huber_k, pp, ev, (ResidualMode)residual);
     std::memcpy(g6, ev.g, sizeof(ev.g)); std::memcpy(H36, ev.H, sizeof(ev.H)); *sumsq = ev.sumsq; *nvis = ev.nvis;
     if (eps) std::memcpy(eps, ev.eps.data(), sizeof(float) * N);
     if (w) std::memcpy(w, ev.w.data(), sizeof(float) * N);

@@ -5,4 +5,4 @@ from ._lib import Config, PairInfo, SolverParams, PhotoConfig, PhotoInfo, DvoErr
 from .photo import PhotoEstimator  # noqa: F401
 from .batch import BatchAligner, solver_params  # noqa: F401
 from .batch import (SUBGRAD_REF, GN, LM, JAC_REFERENCE, JAC_EXACT, W_REF_CAUCHY, W_HUBER, W_NONE, ARITH_EXACT,  # noqa: F401
-                    ARITH_FAST, FRAME_REF, FRAME_NOW)
+                    ARITH_FAST, FRAME_REF, FRAME_NOW, RES_DT_FLOOR, RES_DT_INTERP)

@@ -15,7 +15,7 @@ class Config(C.Structure):
 
 class SolverParams(C.Structure):
     _fields_ = [("solver", C.c_int), ("jacobian", C.c_int), ("weight", C.c_int), ("arithmetic", C.c_int),
-                ("huber_k", C.c_float), ("lm_lambda0", C.c_double), ("iters", C.c_int * MAX_LEVELS)]
+                ("huber_k", C.c_float), ("lm_lambda0", C.c_double), ("iters", C.c_int * MAX_LEVELS), ("residual", C.c_int)]
 
 
 class PairInfo(C.Structure):
@@ -38,7 +38,7 @@ SYMBOLS = [
     "dvo_last_error", "dvo_device_count", "dvo_create", "dvo_destroy", "dvo_set_stream", "dvo_synchronize",
     "dvo_set_intrinsics", "dvo_set_frames", "dvo_promote_now_to_ref", "dvo_build_pyramids", "dvo_prepare",
     "dvo_set_initial_pose", "dvo_run", "dvo_get_poses", "dvo_align_batch", "dvo_level_dims", "dvo_get_level_buffer",
-    "dvo_get_points", "dvo_eval_normal_equations", "dvo_get_trace", "dvo_enable_timing", "dvo_get_stage_ms",
+    "dvo_get_points", "dvo_eval_normal_equations", "dvo_eval_normal_equations_ex", "dvo_get_trace", "dvo_enable_timing", "dvo_get_stage_ms",
     "dvo_launch_count", "dvo_gop_compose", "dvo_run_sequences",
     "dvo_photo_create", "dvo_photo_destroy", "dvo_photo_set_stream", "dvo_photo_synchronize", "dvo_photo_launch_count",
     "dvo_photo_set_intrinsics", "dvo_photo_set_frames", "dvo_photo_prepare_ref", "dvo_photo_set_pose", "dvo_photo_estimate",
@@ -82,6 +82,9 @@ def load(build_if_missing=True):
     lib.dvo_eval_normal_equations.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dvo_eval_normal_equations_ex.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(SolverParams),
+                                                 C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
+                                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dvo_get_trace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.dvo_enable_timing.argtypes = [C.c_void_p, C.c_int]
     lib.dvo_get_stage_ms.argtypes = [C.c_void_p, C.c_void_p]

@@ -10,6 +10,7 @@ SUBGRAD_REF, GN, LM = 0, 1, 2
 JAC_REFERENCE, JAC_EXACT = 0, 1
 W_REF_CAUCHY, W_HUBER, W_NONE = 0, 1, 2
 ARITH_EXACT, ARITH_FAST = 0, 1
+RES_DT_FLOOR, RES_DT_INTERP = 0, 1
 FRAME_REF, FRAME_NOW = 0, 1
 MEM_HOST, MEM_DEVICE = 0, 1
 BUF = {"gray": (0, np.uint8), "depth": (1, np.uint16), "edge": (2, np.uint8), "d2": (3, np.int32),
@@ -17,9 +18,9 @@ BUF = {"gray": (0, np.uint8), "depth": (1, np.uint16), "edge": (2, np.uint8), "d
 
 
 def solver_params(solver=SUBGRAD_REF, jacobian=JAC_REFERENCE, weight=W_REF_CAUCHY, arithmetic=ARITH_EXACT, huber_k=1.345,
-                  lm_lambda0=1e-3, iters=(50, 50, 50, 50)):
+                  lm_lambda0=1e-3, iters=(50, 50, 50, 50), residual=RES_DT_FLOOR):
     p = SolverParams()
-    p.solver, p.jacobian, p.weight, p.arithmetic = solver, jacobian, weight, arithmetic
+    p.solver, p.jacobian, p.weight, p.arithmetic, p.residual = solver, jacobian, weight, arithmetic, residual
     p.huber_k, p.lm_lambda0 = huber_k, lm_lambda0
     for i in range(_lib.MAX_LEVELS):
         p.iters[i] = int(iters[i]) if i < len(iters) else 0
@@ -147,7 +148,7 @@ class BatchAligner:
         return X[: n.value].copy(), Y[: n.value].copy(), Z[: n.value].copy()
 
     def eval_normal_equations(self, slot, level, R, T, jacobian=JAC_REFERENCE, weight=W_REF_CAUCHY, arithmetic=ARITH_EXACT,
-                              huber_k=1.345, per_point=False, npts=None):
+                              huber_k=1.345, per_point=False, npts=None, residual=RES_DT_FLOOR):
         pose = np.concatenate([np.asarray(R, np.float64).reshape(9), np.asarray(T, np.float64).reshape(3)])
         H = np.empty(36, np.float64)
         g = np.empty(6, np.float64)
@@ -156,9 +157,10 @@ class BatchAligner:
         if per_point:
             pp = {"eps": np.zeros(npts, np.float32), "w": np.zeros(npts, np.float32), "u": np.zeros(npts, np.float32),
                   "v": np.zeros(npts, np.float32), "J": np.zeros((npts, 6), np.float32)}
-        check(self.lib.dvo_eval_normal_equations(self.h, slot, level, _ptr(pose), jacobian, weight, arithmetic, huber_k, _ptr(H), _ptr(g),
-                                                 C.byref(sumsq), C.byref(nvis), _ptr(pp.get("eps")), _ptr(pp.get("w")),
-                                                 _ptr(pp.get("u")), _ptr(pp.get("v")), _ptr(pp.get("J"))), "dvo_eval_normal_equations")
+        prm = solver_params(jacobian=jacobian, weight=weight, arithmetic=arithmetic, huber_k=huber_k, residual=residual)
+        check(self.lib.dvo_eval_normal_equations_ex(self.h, slot, level, _ptr(pose), C.byref(prm), _ptr(H), _ptr(g),
+                                                    C.byref(sumsq), C.byref(nvis), _ptr(pp.get("eps")), _ptr(pp.get("w")),
+                                                    _ptr(pp.get("u")), _ptr(pp.get("v")), _ptr(pp.get("J"))), "dvo_eval_normal_equations_ex")
         out = {"H": H.reshape(6, 6), "g": g, "sumsq": sumsq.value, "nvis": nvis.value}
         out.update(pp)
         return out

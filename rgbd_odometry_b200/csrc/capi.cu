@@ -426,6 +426,15 @@ int dvo_get_points(dvo_ctx* c, int slot, int level, float* X, float* Y, float* Z
 int dvo_eval_normal_equations(dvo_ctx* c, int slot, int level, const double* R9T3, int jacobian, int weight, int arithmetic,
                               float huber_k, double* H36, double* g6, double* sumsq, int* nvis, float* eps, float* w, float* u,
                               float* v, float* J) {
+    dvo_solver_params prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.jacobian = jacobian; prm.weight = weight; prm.arithmetic = arithmetic; prm.huber_k = huber_k;
+    return dvo_eval_normal_equations_ex(c, slot, level, R9T3, &prm, H36, g6, sumsq, nvis, eps, w, u, v, J);
+}
+
+int dvo_eval_normal_equations_ex(dvo_ctx* c, int slot, int level, const double* R9T3, const dvo_solver_params* prm,
+                                 double* H36, double* g6, double* sumsq, int* nvis, float* eps, float* w, float* u, float* v, float* J) {
+    if (!prm) return DVO_ERR_ARG;
     if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !R9T3) return DVO_ERR_ARG;
     if (!c->haveK) { dvo_set_error("intrinsics not set"); return DVO_ERR_STATE; }
     int N = 0;
@@ -440,7 +449,7 @@ int dvo_eval_normal_equations(dvo_ctx* c, int slot, int level, const double* R9T
     DVO_CUDA(cudaMemcpyAsync(d_pose, R9T3, sizeof(double) * 12, cudaMemcpyHostToDevice, c->stream));
     float *de = nullptr, *dw = nullptr, *du = nullptr, *dv = nullptr, *dJ = nullptr;
     if (pp) { de = d_pp; dw = d_pp + n1; du = d_pp + 2 * n1; dv = d_pp + 3 * n1; dJ = d_pp + 4 * n1; }
-    int rc = launch_eval(c, slot, level, d_pose, jacobian, weight, arithmetic, huber_k, d_out, de, dw, du, dv, dJ);
+    int rc = launch_eval(c, slot, level, d_pose, prm->jacobian, prm->weight, prm->arithmetic, prm->huber_k, prm->residual, d_out, de, dw, du, dv, dJ);
     if (rc == DVO_OK) {
         double out[44];
         std::vector<float> host(pp ? n1 * 10 : 0);

@@ -86,7 +86,7 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask);
 int launch_edt_rows(dvo_ctx* c, int first, int count);
 int launch_normgrad(dvo_ctx* c, int first, int count);
 int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p);
-int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k,
+int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k, int residual,
                 double* d_out /* 6 + 36 + 1 + 1 doubles */, float* d_eps, float* d_w, float* d_u, float* d_v, float* d_J);
 int launch_gop(dvo_ctx* c, int nseq, int nframes, const int* d_kind, const double* d_rel, double* d_out);
 int launch_promote(dvo_ctx* c, int first, int count);

@@ -231,12 +231,28 @@ __device__ __forceinline__ void finish_point(const Proj& q, const float4 t, cons
     else wgt = 1.0f;
 }
 
+// SolveDVO::interpolate (src/SolveDVO.cpp:1285-1308) at the reprojection (v = row, u = column): "squared-bilinear"
+// lookup of the normalised DT (texel.x), fp32, products left to right; ceil indices clamped to the image (the
+// reference would trip its own bound assert there).  Three extra 4-byte gathers next to the texel already fetched.
+__device__ __forceinline__ float interpolate_dt(const float4* __restrict__ tex, const LevelCam& cam, const Proj& q, float Fdd) {
+    const int rx_d = __float2int_rz(q.u), ry_d = __float2int_rz(q.v);               // u, v >= 0 here: floor == trunc
+    const float fx_d = (float)rx_d, fy_d = (float)ry_d;
+    const float inc_x = __fsub_rn(q.u, fx_d), inc_y = __fsub_rn(q.v, fy_d);
+    const int rx_u = min(rx_d + (q.u > fx_d ? 1 : 0), cam.w - 1), ry_u = min(ry_d + (q.v > fy_d ? 1 : 0), cam.h - 1);
+    const float Fdu = __ldg(&tex[ry_d * cam.w + rx_u].x);
+    const float Fud = __ldg(&tex[ry_u * cam.w + rx_d].x), Fuu = __ldg(&tex[ry_u * cam.w + rx_u].x);
+    const float ax = __fsub_rn(1.0f, inc_x), ay = __fsub_rn(1.0f, inc_y);
+    const float f1 = __fsqrt_rn(__fadd_rn(__fmul_rn(__fmul_rn(ax, Fdd), Fdd), __fmul_rn(__fmul_rn(inc_x, Fdu), Fdu)));
+    const float f2 = __fsqrt_rn(__fadd_rn(__fmul_rn(__fmul_rn(ax, Fud), Fud), __fmul_rn(__fmul_rn(inc_x, Fuu), Fuu)));
+    return __fsqrt_rn(__fadd_rn(__fmul_rn(__fmul_rn(ay, f1), f1), __fmul_rn(__fmul_rn(inc_y, f2), f2)));
+}
+
 // Accumulator layout: [0..5] g, [6] sum eps^2, [7] sum eps, then (NEED_H) 21 upper-triangle entries of H row by row.
 template <bool NEED_H> struct AccN { static constexpr int N = NEED_H ? 29 : 8; };
 
 // Software-pipelined sweep over a thread's points: the coordinates are loaded two points ahead and the (random)
 // texel gather of the next point is in flight while the current point's Jacobian / fp64 accumulation executes.
-template <int ARITH, int JAC, bool NEED_H, int THREADS, bool OUT>
+template <int ARITH, int JAC, bool NEED_H, int THREADS, bool OUT, int RES = DVO_RESIDUAL_DT_FLOOR>
 __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, const float* __restrict__ Y,
                                                   const float* __restrict__ Z, int N, const PoseF& P, const LevelCam& cam,
                                                   const float4* __restrict__ tex, int weight_mode, float huber_k,
@@ -264,6 +280,11 @@ __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, c
         float Jr[6], e = 0.f, wgt = 0.f;
         if (q.idx >= 0) {
             finish_point<ARITH, JAC>(q, t, P, cam, weight_mode, huber_k, Jr, e, wgt);
+            if (RES == DVO_RESIDUAL_DT_INTERP) {                                     // :443-444, weight from the interpolated value (:450)
+                e = interpolate_dt(tex, cam, q, t.x);
+                if (weight_mode == DVO_WEIGHT_REF_CAUCHY) wgt = A::weight_ref(e);
+                else if (weight_mode == DVO_WEIGHT_HUBER) { const float ae = fabsf(e); wgt = ae <= huber_k ? 1.0f : A::div(huber_k, ae); }
+            }
             ++nvis;
             const double de = (double)e;
             acc[6] = fma(de, de, acc[6]);
@@ -474,7 +495,7 @@ __global__ void __launch_bounds__(1024) solve_order_kernel(const int* __restrict
 // pair's points over 2/4/8 CTAs and combined partial sums through distributed shared memory was measured slower --
 // 4.29 ms -> 4.58 / 5.53 / 8.62 ms per 1024 pairs -- and removed; so was a cp.async shared-memory ring that kept 2..8
 // texel gathers in flight per thread: 4.56 .. 4.72 ms.  See DESIGN.md "measured and rejected".)
-template <int ARITH, int JAC, bool NEED_H, int THREADS>
+template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES>
 __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve_kernel(SolveArgs a) {
     constexpr int NACC = AccN<NEED_H>::N;
     constexpr int SOLVE_WARPS = THREADS / 32;
@@ -528,7 +549,7 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
 #pragma unroll
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
             int nvis = 0;
-            accumulate_points<ARITH, JAC, NEED_H, THREADS, false>(X, Y, Z, N, P, cam, tex, a.prm.weight, a.prm.huber_k, acc, nvis,
+            accumulate_points<ARITH, JAC, NEED_H, THREADS, false, RES>(X, Y, Z, N, P, cam, tex, a.prm.weight, a.prm.huber_k, acc, nvis,
                                                   nullptr, nullptr, nullptr, nullptr, nullptr);
             block_reduce<NACC, THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
             if (lead) {
@@ -567,7 +588,7 @@ struct EvalArgs {
     float *eps, *w, *u, *v, *J;
 };
 
-template <int ARITH, int JAC>
+template <int ARITH, int JAC, int RES>
 __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
     constexpr int NACC = AccN<true>::N;
     constexpr int SOLVE_WARPS = EVAL_THREADS / 32;
@@ -587,7 +608,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     int nvis = 0;
-    accumulate_points<ARITH, JAC, true, EVAL_THREADS, true>(a.X + base, a.Y + base, a.Z + base, N, P, cam, a.texel + base, a.weight, a.huber_k,
+    accumulate_points<ARITH, JAC, true, EVAL_THREADS, true, RES>(a.X + base, a.Y + base, a.Z + base, N, P, cam, a.texel + base, a.weight, a.huber_k,
                                         acc, nvis, a.eps, a.w, a.u, a.v, a.J);
     block_reduce<NACC, EVAL_THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
     if (threadIdx.x == 0) {
@@ -623,8 +644,13 @@ __global__ void gop_kernel(int nseq, int nframes, const int* __restrict__ kind, 
 template <int ARITH, int JAC>
 static cudaError_t launch_solve_t(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
     constexpr int THREADS = 256;
-    if (need_h) solve_kernel<ARITH, JAC, true, THREADS><<<count, THREADS, 0, c->stream>>>(a);
-    else solve_kernel<ARITH, JAC, false, THREADS><<<count, THREADS, 0, c->stream>>>(a);
+    constexpr int F = DVO_RESIDUAL_DT_FLOOR, I = DVO_RESIDUAL_DT_INTERP;
+    if (a.prm.residual == I) {
+        if (ARITH != DVO_ARITH_EXACT) return cudaErrorNotSupported;      // the interpolated variant is built for EXACT arithmetic only
+        if (need_h) solve_kernel<DVO_ARITH_EXACT, JAC, true, THREADS, I><<<count, THREADS, 0, c->stream>>>(a);
+        else solve_kernel<DVO_ARITH_EXACT, JAC, false, THREADS, I><<<count, THREADS, 0, c->stream>>>(a);
+    } else if (need_h) solve_kernel<ARITH, JAC, true, THREADS, F><<<count, THREADS, 0, c->stream>>>(a);
+    else solve_kernel<ARITH, JAC, false, THREADS, F><<<count, THREADS, 0, c->stream>>>(a);
     return cudaGetLastError();
 }
 
@@ -655,17 +681,22 @@ int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
     return DVO_OK;
 }
 
-int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k,
+int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k, int residual,
                 double* d_out, float* d_eps, float* d_w, float* d_u, float* d_v, float* d_J) {
     EvalArgs a;
     a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts; a.texel = c->texel;
     a.pose = d_pose12; a.slot = slot; a.level = level; a.weight = weight; a.huber_k = huber_k; a.out = d_out;
     a.eps = d_eps; a.w = d_w; a.u = d_u; a.v = d_v; a.J = d_J;
     const bool ex = arith != DVO_ARITH_FAST, rj = jac != DVO_JAC_EXACT;
-    if (ex && rj) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_REFERENCE><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-    else if (ex) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_EXACT><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-    else if (rj) eval_kernel<DVO_ARITH_FAST, DVO_JAC_REFERENCE><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-    else eval_kernel<DVO_ARITH_FAST, DVO_JAC_EXACT><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+    constexpr int F = DVO_RESIDUAL_DT_FLOOR, I = DVO_RESIDUAL_DT_INTERP;
+    if (residual == I) {
+        if (!ex) { dvo_set_error("the interpolated-DT residual is built for EXACT arithmetic only"); return DVO_ERR_ARG; }
+        if (rj) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_REFERENCE, I><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+        else eval_kernel<DVO_ARITH_EXACT, DVO_JAC_EXACT, I><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+    } else if (ex && rj) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_REFERENCE, F><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+    else if (ex) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_EXACT, F><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+    else if (rj) eval_kernel<DVO_ARITH_FAST, DVO_JAC_REFERENCE, F><<<1, EVAL_THREADS, 0, c->stream>>>(a);
+    else eval_kernel<DVO_ARITH_FAST, DVO_JAC_EXACT, F><<<1, EVAL_THREADS, 0, c->stream>>>(a);
     c->launches++;
     DVO_CUDA(cudaGetLastError());
     return DVO_OK;

@@ -17,6 +17,7 @@ SolveDVO::SolveDVO(int width, int height, int levels)
     std::memset(&solver, 0, sizeof(solver));
     solver.solver = DVO_SOLVER_SUBGRAD_REF; solver.jacobian = DVO_JAC_REFERENCE; solver.weight = DVO_WEIGHT_REF_CAUCHY;
     solver.arithmetic = DVO_ARITH_EXACT; solver.huber_k = 1.345f; solver.lm_lambda0 = 1e-3;
+    solver.residual = DVO_RESIDUAL_DT_FLOOR;               // set to DVO_RESIDUAL_DT_INTERP for the __INTERPOLATE_DISTANCE_TRANSFORM build (:443)
     std::memset(&lastInfo, 0, sizeof(lastInfo));
     dvo_config cfg = {width, height, levels, 1, 0, /*keep_now_depth*/ 1, /*trace_iters*/ 128};
     const int rc = dvo_create(&cfg, &ctx_);
@@ -112,8 +113,8 @@ void SolveDVO::runIterations(int level, int maxIterations, dvo::Matrix3d& cR, dv
     finalEpsilons.assign(n, 0.f); finalReprojections.rows = 3; finalReprojections.cols = n; finalReprojections.data.assign((size_t)3 * n, 1.f);
     if (n > 0) {
         double H[36], g[6], ss; int nvis;
-        check(dvo_eval_normal_equations(ctx_, 0, level, pose, p.jacobian, p.weight, p.arithmetic, p.huber_k, H, g, &ss, &nvis, finalEpsilons.data(),
-                                        nullptr, finalReprojections.data.data(), finalReprojections.data.data() + n, nullptr), "runIterations");
+        check(dvo_eval_normal_equations_ex(ctx_, 0, level, pose, &p, H, g, &ss, &nvis, finalEpsilons.data(),
+                                           nullptr, finalReprojections.data.data(), finalReprojections.data.data() + n, nullptr), "runIterations");
     }
     bestEnergyIndex = lastInfo.best_index[level]; finalVisibleRatio = lastInfo.visible_ratio[level];
 }

@@ -29,7 +29,7 @@ def build_synth(force=False):
 
 class SolverCfg(C.Structure):
     _fields_ = [("solver", C.c_int), ("jacobian", C.c_int), ("weight", C.c_int), ("huber_k", C.c_float),
-                ("lm_lambda0", C.c_double)]
+                ("lm_lambda0", C.c_double), ("residual", C.c_int)]
 
 
 SUBGRAD_REF, GN, LM = 0, 1, 2
@@ -37,8 +37,11 @@ JAC_REFERENCE, JAC_EXACT = 0, 1
 W_REF_CAUCHY, W_HUBER, W_NONE = 0, 1, 2
 
 
-def cfg(solver=SUBGRAD_REF, jacobian=JAC_REFERENCE, weight=W_REF_CAUCHY, huber_k=1.345, lm_lambda0=1e-3):
-    return SolverCfg(solver, jacobian, weight, huber_k, lm_lambda0)
+RES_DT_FLOOR, RES_DT_INTERP = 0, 1
+
+
+def cfg(solver=SUBGRAD_REF, jacobian=JAC_REFERENCE, weight=W_REF_CAUCHY, huber_k=1.345, lm_lambda0=1e-3, residual=RES_DT_FLOOR):
+    return SolverCfg(solver, jacobian, weight, huber_k, lm_lambda0, residual)
 
 
 def _p(a, t):
@@ -239,7 +242,7 @@ def preprocess_level(gray, depth, level):
 
 
 def evaluate(X, Y, Z, dtn, gx, gy, level, R, T, K=K640, jac=JAC_REFERENCE, weight=W_REF_CAUCHY, huber_k=1.345,
-             per_point=False):
+             per_point=False, residual=RES_DT_FLOOR):
     N = len(X)
     H, W = dtn.shape
     R = np.ascontiguousarray(R, np.float64).reshape(9)
@@ -258,7 +261,7 @@ def evaluate(X, Y, Z, dtn, gx, gy, level, R, T, K=K640, jac=JAC_REFERENCE, weigh
                        C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3]), _p(R, C.c_double), _p(T, C.c_double),
                        jac, weight, C.c_float(huber_k), _p(g, C.c_double), _p(Hm, C.c_double), C.byref(sumsq), C.byref(nvis),
                        _p(pp.get("eps"), C.c_float), _p(pp.get("w"), C.c_float), _p(pp.get("u"), C.c_float),
-                       _p(pp.get("v"), C.c_float), _p(pp.get("J"), C.c_float))
+                       _p(pp.get("v"), C.c_float), _p(pp.get("J"), C.c_float), int(residual))
     out = {"g": g, "H": Hm.reshape(6, 6), "sumsq": sumsq.value, "nvis": nvis.value}
     out.update(pp)
     return out

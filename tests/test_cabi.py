@@ -29,7 +29,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(dvo.Config) == 7 * 4
-    assert C.sizeof(dvo.SolverParams) == 4 * 4 + 4 + 4 + 8 + 6 * 4        # 4 ints, float (+pad), double, 6 ints
+    assert C.sizeof(dvo.SolverParams) == 4 * 4 + 4 + 4 + 8 + 6 * 4 + 4 + 4  # 4 ints, float (+pad), double, 6 ints, residual (+pad)
+    assert dvo.SolverParams.residual.offset == 56 and dvo.SolverParams.iters.offset == 32
     assert C.sizeof(dvo.PairInfo) == 4 + 5 * 6 * 4 + 4
 
 

@@ -209,6 +209,42 @@ def test_gauss_newton_and_lm_pose_parity(prepared, batch, solver, jac, weight):
         assert list(info[i].best_index[:LEVELS]) == list(o["best_index"])
 
 
+def test_interpolated_dt_residual_bit_exact(prepared, oracle_levels, batch):
+    """The reference's compiled-out __INTERPOLATE_DISTANCE_TRANSFORM variant (src/SolveDVO.cpp:443-444, :1285-1308):
+    per-point eps / w / J bit-exact against the oracle's restatement, sums to 1e-12 relative."""
+    for i in range(NPAIR):
+        for l in range(LEVELS):
+            ref, now = oracle_levels[i][0][l], oracle_levels[i][1][l]
+            X, Y, Z, _, _ = O.select_points(ref["edge"], ref["depth"], l)
+            for (R, T) in ((np.eye(3), np.zeros(3)), _true_pose(batch, i)):
+                o = O.evaluate(X, Y, Z, now["dtn"], now["gx"], now["gy"], l, R, T, per_point=True, residual=O.RES_DT_INTERP)
+                g = prepared.eval_normal_equations(i + 1, l, R, T, per_point=True, npts=len(X), residual=dvo.RES_DT_INTERP)
+                f = prepared.eval_normal_equations(i + 1, l, R, T, per_point=True, npts=len(X))
+                assert g["nvis"] == o["nvis"]
+                assert bits_equal(g["eps"], o["eps"]), f"eps pair {i} L{l}: {mismatch(g['eps'], o['eps'])}"
+                assert bits_equal(g["w"], o["w"]), f"w pair {i} L{l}: {mismatch(g['w'], o['w'])}"
+                assert bits_equal(g["J"], o["J"]) and bits_equal(g["J"], f["J"])       # the Jacobian keeps the floor texel (:376-385)
+                assert not np.array_equal(g["eps"], f["eps"])                          # and the residual really is a different one
+                iu = np.triu_indices(6)
+                assert np.allclose(g["H"][iu], o["H"][iu], rtol=1e-12, atol=1e-12 * np.abs(o["H"]).max())
+                assert np.allclose(g["g"], o["g"], rtol=1e-12, atol=1e-12 * np.abs(o["g"]).max())
+
+
+@pytest.mark.parametrize("solver,iters", [(dvo.SUBGRAD_REF, (30, 30, 30, 30)), (dvo.GN, (8, 8, 8, 8))])
+def test_interpolated_dt_residual_pose_parity(prepared, batch, solver, iters):
+    params = dvo.solver_params(solver=solver, iters=iters, residual=dvo.RES_DT_INTERP)
+    poses, info = _run_gpu(prepared, params)
+    for i in range(NPAIR):
+        o = O.align_pair(batch["ref_gray"][i], batch["ref_depth"][i], batch["now_gray"][i], LEVELS, iters,
+                         scfg=O.cfg(solver, residual=O.RES_DT_INTERP))
+        R, T = poses[i, :9].reshape(3, 3), poses[i, 9:]
+        assert rot_angle(R, o["R"]) < 1e-5 and np.linalg.norm(T - o["T"]) < 1e-5, \
+            f"pair {i}: dR {rot_angle(R, o['R'])} dT {np.linalg.norm(T - o['T'])}"
+        assert list(info[i].best_index[:LEVELS]) == list(o["best_index"])
+    with pytest.raises(dvo.DvoError):                                                  # EXACT arithmetic only
+        prepared.run(NPAIR, dvo.solver_params(iters=iters, residual=dvo.RES_DT_INTERP, arithmetic=dvo.ARITH_FAST), first=1)
+
+
 def test_align_batch_end_to_end_matches_staged_calls(batch):
     """dvo_align_batch (host buffers, chunked over max_batch) == staged calls == oracle."""
     al = dvo.BatchAligner(640, 480, LEVELS, max_batch=2)

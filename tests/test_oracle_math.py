@@ -130,3 +130,31 @@ def test_normal_equations_linearity_and_symmetry():
     Jw = (full["J"] * w[:, None]).astype(np.float32).astype(np.float64)
     assert np.allclose(Jw.T @ J, full["H"], rtol=1e-9) and np.allclose(Jw.T @ e, full["g"], rtol=1e-9)
     assert np.allclose(full["H"], full["H"].T, rtol=1e-6)
+
+
+def test_interpolated_dt_lookup_properties():
+    """SolveDVO::interpolate restatement (src/SolveDVO.cpp:1285-1308): exact at integer positions, the stated
+    squared-bilinear formula in fp32 elsewhere, ceil indices clamped at the border."""
+    rng = np.random.default_rng(5)
+    H, W = 12, 16
+    F = (rng.random((H, W)) * 255).astype(np.float32)
+    X = np.array([0.0], np.float32); Y = np.array([0.0], np.float32); Z = np.array([1.0], np.float32)
+    zeros = np.zeros((H, W), np.float32)
+
+    def lookup(u, v):      # a camera with fx = fy = 1 and principal point (u, v) sends the point (0,0,1) to pixel (u, v)
+        o = O.evaluate(X, Y, Z, F, zeros, zeros, 0, np.eye(3), np.zeros(3), K=(1.0, 1.0, u, v), per_point=True, residual=O.RES_DT_INTERP)
+        assert o["nvis"] == 1 and o["u"][0] == np.float32(u) and o["v"][0] == np.float32(v)
+        return o["eps"][0]
+
+    for (u, v) in ((3.0, 4.0), (0.0, 0.0), (15.0, 11.0)):
+        assert lookup(u, v) == F[int(v), int(u)]
+    f32 = np.float32
+    u, v = f32(5.25), f32(7.5)
+    ix, iy = f32(0.25), f32(0.5)
+    f1 = np.sqrt(((f32(1) - ix) * F[7, 5]) * F[7, 5] + (ix * F[7, 6]) * F[7, 6], dtype=np.float32)
+    f2 = np.sqrt(((f32(1) - ix) * F[8, 5]) * F[8, 5] + (ix * F[8, 6]) * F[8, 6], dtype=np.float32)
+    want = np.sqrt(((f32(1) - iy) * f1) * f1 + (iy * f2) * f2, dtype=np.float32)
+    assert lookup(float(u), float(v)) == want
+    # within one pixel of the right / bottom border the ceil index is clamped: the lookup degenerates to the last column / row
+    assert lookup(15.5, 3.0) == F[3, 15]
+    assert lookup(2.0, 11.75) == F[11, 2]
