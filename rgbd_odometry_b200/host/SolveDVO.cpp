@@ -54,6 +54,31 @@ void SolveDVO::setRcvdFrame(const dvo::ImageView& framemono, const dvo::ImageVie
     isFrameAvailable = true;
 }
 
+// SolveDVO::loadFromFile (src/SolveDVO.cpp:154-190).  The dump holds every pyramid level; the device rebuilds levels
+// 1.. from level 0 with the publisher's own rule (NEAREST, src/camTopic2PublisherPyD.cpp:338-348), so only mono_0 /
+// depth_0 are uploaded.  A dump whose stored levels disagree with that rule is reported (it was not written by the
+// reference's publisher) but still loaded from its level 0.
+bool SolveDVO::loadFromFile(const char* xmlFileName) {
+    dvo::RGBDFramePyd pyd;
+    if (!dvo::loadFrameXml(xmlFileName, pyd, levels_)) return false;                     // :158-162: logs, leaves isFrameAvailable untouched
+    const dvo::Image& m0 = pyd.framemono[0]; const dvo::Image& d0 = pyd.dframe[0];
+    if (m0.elem != dvo::ELEM_U8 || m0.channels != 1 || d0.elem != dvo::ELEM_U16 || d0.channels != 1 || m0.rows != height_ || m0.cols != width_ ||
+        d0.rows != height_ || d0.cols != width_) {
+        std::fprintf(stderr, "[SolveDVO::loadFromFile] %s: mono_0 / depth_0 are not %dx%d u8 / u16\n", xmlFileName, width_, height_);
+        return false;
+    }
+    for (int l = 1; l < levels_; ++l) {
+        const dvo::Image& m = pyd.framemono[l];
+        int lw = 0, lh = 0; dvo_level_dims(ctx_, l, &lw, &lh);
+        bool same = (m.rows == lh && m.cols == lw && m.elem == dvo::ELEM_U8);
+        const int s = 1 << l;
+        for (int y = 0; same && y < lh; ++y) for (int x = 0; x < lw; ++x) if (m.data[(size_t)y * lw + x] != m0.data[(size_t)(y * s) * width_ + x * s]) { same = false; break; }
+        if (!same) std::fprintf(stderr, "[SolveDVO::loadFromFile] %s: stored mono_%d is not the NEAREST subsample of mono_0; rebuilt on the device\n", xmlFileName, l);
+    }
+    setRcvdFrame(m0.view(), d0.view());
+    return true;
+}
+
 void SolveDVO::setRcvdFrameAsRefFrame() {
     assert(isFrameAvailable);
     isRefFrameAvailable = false;

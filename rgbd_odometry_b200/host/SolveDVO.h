@@ -6,6 +6,7 @@
 #pragma once
 #include <vector>
 
+#include "FrameIO.h"
 #include "GOP.h"
 #include "dvo_b200.h"
 #include "dvo_types.h"
@@ -20,6 +21,7 @@ public:
 
     // ---- ingest (replaces imageArrivedCallBack :490-534): level-0 mono8 + depth16 (mm); zeros become 1 (:512)
     void setRcvdFrame(const dvo::ImageView& framemono, const dvo::ImageView& dframe);
+    bool loadFromFile(const char* xmlFileName);                        // :154-190 (OpenCV XML frame dump, mono_i / depth_i)
     void setRcvdFrameAsRefFrame();                                     // :537-557  (+ computeDistTransfrmOfRef)
     void setRcvdFrameAsNowFrame();                                     // :588-614  (+ computeDistTransfrmOfNow, keeps p_now_*)
     void setPrevFrameAsRefFrame();                                     // :561-584

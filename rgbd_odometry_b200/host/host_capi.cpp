@@ -2,7 +2,11 @@
 // GOP) through ctypes exactly as a C++ caller of the reference would.
 #include <cstring>
 
+#include <fstream>
+#include <sstream>
+
 #include "EPoseEstimator.h"
+#include "FrameIO.h"
 #include "GOP.h"
 #include "SolveDVO.h"
 
@@ -109,6 +113,107 @@ int hostapi_gop_replay(int n, const int* kind, const int* reason, const double* 
         is_key[i] = g.isKeyFrameAt(i); reason_out[i] = g.getReasonAt(i);
     }
     return g.size();
+}
+
+// ---- FrameIO (formats either side of the path) ----
+// write `levels` mono (u8) / depth (u16) images, level l of size (H >> l) x (W >> l), packed one after the other
+int hostapi_store_frame_xml(const char* file, const uint8_t* mono, const uint16_t* depth, int W, int H, int levels) {
+    dvo::RGBDFramePyd p;
+    size_t off = 0;
+    for (int l = 0; l < levels; ++l) {
+        const int w = W >> l, h = H >> l;
+        dvo::Image m; m.rows = h; m.cols = w; m.elem = dvo::ELEM_U8; m.data.assign(mono + off, mono + off + (size_t)w * h);
+        dvo::Image d; d.rows = h; d.cols = w; d.elem = dvo::ELEM_U16; d.data.resize((size_t)w * h * 2); std::memcpy(d.data.data(), depth + off, (size_t)w * h * 2);
+        p.framemono.push_back(m); p.dframe.push_back(d);
+        off += (size_t)w * h;
+    }
+    return dvo::storeFrameXml(file, p) ? 0 : -1;
+}
+// read them back into the same packed layout; dims[2*l], dims[2*l+1] = rows, cols of level l
+int hostapi_load_frame_xml(const char* file, int levels, uint8_t* mono, uint16_t* depth, size_t capacity, int* dims) {
+    dvo::RGBDFramePyd p;
+    if (!dvo::loadFrameXml(file, p, levels)) return -1;
+    size_t off = 0;
+    for (int l = 0; l < levels; ++l) {
+        const dvo::Image& m = p.framemono[l]; const dvo::Image& d = p.dframe[l];
+        if (m.elem != dvo::ELEM_U8 || d.elem != dvo::ELEM_U16 || m.rows != d.rows || m.cols != d.cols) return -2;
+        const size_t n = (size_t)m.rows * m.cols;
+        if (off + n > capacity) return -3;
+        std::memcpy(mono + off, m.data.data(), n); std::memcpy(depth + off, d.data.data(), n * 2);
+        dims[2 * l] = m.rows; dims[2 * l + 1] = m.cols;
+        off += n;
+    }
+    return 0;
+}
+// one generic node (any dt) as doubles, for checking the reader against files written by cv::FileStorage itself
+int hostapi_read_xml_matrix(const char* file, const char* name, double* out, size_t capacity, int* rows, int* cols, int* channels, int* elem) {
+    std::ifstream f(file, std::ios::binary);
+    if (!f.is_open()) return -1;
+    std::stringstream ss; ss << f.rdbuf();
+    dvo::Image m;
+    if (!dvo::readXmlMatrix(ss.str(), name, m)) return -2;
+    const size_t n = (size_t)m.rows * m.cols * m.channels;
+    if (n > capacity) return -3;
+    for (size_t i = 0; i < n; ++i) {
+        switch (m.elem) {
+            case dvo::ELEM_U8: out[i] = m.data[i]; break;
+            case dvo::ELEM_U16: out[i] = reinterpret_cast<const uint16_t*>(m.data.data())[i]; break;
+            case dvo::ELEM_S16: out[i] = reinterpret_cast<const int16_t*>(m.data.data())[i]; break;
+            case dvo::ELEM_S32: out[i] = reinterpret_cast<const int32_t*>(m.data.data())[i]; break;
+            case dvo::ELEM_F32: out[i] = reinterpret_cast<const float*>(m.data.data())[i]; break;
+            default: out[i] = reinterpret_cast<const double*>(m.data.data())[i]; break;
+        }
+    }
+    *rows = m.rows; *cols = m.cols; *channels = m.channels; *elem = m.elem;
+    return 0;
+}
+// pose text: write n poses (7 doubles each: qx qy qz qw tx ty tz) with SolveDVO::printPose, read them back
+int hostapi_write_pose_file(const char* file, const double* q7, int n) {
+    std::ofstream f(file);
+    if (!f.is_open()) return -1;
+    for (int i = 0; i < n; ++i) {
+        dvo::Pose p;
+        p.orientation.x = q7[7 * i]; p.orientation.y = q7[7 * i + 1]; p.orientation.z = q7[7 * i + 2]; p.orientation.w = q7[7 * i + 3];
+        p.position.x = q7[7 * i + 4]; p.position.y = q7[7 * i + 5]; p.position.z = q7[7 * i + 6];
+        dvo::printPose(p, f);
+    }
+    return 0;
+}
+static int poses_out(const std::vector<dvo::Pose>& v, double* q7, int capacity) {
+    const int n = (int)v.size() < capacity ? (int)v.size() : capacity;
+    for (int i = 0; i < n; ++i) {
+        q7[7 * i] = v[i].orientation.x; q7[7 * i + 1] = v[i].orientation.y; q7[7 * i + 2] = v[i].orientation.z; q7[7 * i + 3] = v[i].orientation.w;
+        q7[7 * i + 4] = v[i].position.x; q7[7 * i + 5] = v[i].position.y; q7[7 * i + 6] = v[i].position.z;
+    }
+    return (int)v.size();
+}
+int hostapi_read_pose_file(const char* file, double* q7, int capacity) {
+    std::vector<dvo::Pose> v;
+    if (!dvo::readPoseFile(file, v)) return -1;
+    return poses_out(v, q7, capacity);
+}
+int hostapi_load_gt_path(const char* file, int skip, double* q7, int capacity) {
+    std::vector<dvo::Pose> v;
+    if (!dvo::loadGTPath(file, v, skip)) return -1;
+    return poses_out(v, q7, capacity);
+}
+// SolveDVO::loadFromFile + one alignment of two dumps (ref, now): the replay path of src/SolveDVO.cpp:154-190
+int hostapi_solvedvo_from_files(const char* ref_xml, const char* now_xml, int W, int H, int levels, float fx, float fy, float cx, float cy,
+                                const int* iters, double* R9, double* T3) {
+    SolveDVO s(W, H, levels);
+    s.setIntrinsics(fx, fy, cx, cy);
+    s.iterationsConfig.assign(iters, iters + levels);
+    if (!s.loadFromFile(ref_xml)) return -1;
+    s.setRcvdFrameAsRefFrame(); s.preProcessRefFrame();
+    if (!s.loadFromFile(now_xml)) return -2;
+    s.setRcvdFrameAsNowFrame();
+    dvo::Matrix3d cR; dvo::Vector3d cT;
+    dvo::VectorXf energy, eps; dvo::MatrixXf reproj; int best; float vis;
+    for (int l = levels - 1; l >= 0; --l)
+        if (s.iterationsConfig[l] > 0) s.runIterations(l, s.iterationsConfig[l], cR, cT, energy, eps, reproj, best, vis);
+    for (int i = 0; i < 9; ++i) R9[i] = cR.m[i];
+    for (int i = 0; i < 3; ++i) T3[i] = cT.v[i];
+    return 0;
 }
 
 }  // extern "C"

@@ -81,6 +81,27 @@ def main():
     out["depth_mm"] = mm16
     np.savez_compressed(os.path.join(HERE, "opencv_stages.npz"), **out)
     print("wrote", os.path.join(HERE, "opencv_stages.npz"), "cv2", cv2.__version__)
+    frame_dump()
+
+
+def frame_dump():
+    """A frame dump exactly as camTopic2PublisherPyD writes it (src/camTopic2PublisherPyD.cpp:325-355): cv::FileStorage XML
+    with mono_i / depth_i, level i = cv::resize(full, 0.5^(i+1), INTER_NEAREST); the test parses it without cv2."""
+    d = O.synth_pair(9, 128, 96, (105.0, 105.0, 63.5, 47.5), bgr=True)
+    bgr, depth = d["ref_bgr"], d["ref_depth"]
+    fs = cv2.FileStorage(os.path.join(HERE, "framemono_0000.xml"), cv2.FILE_STORAGE_WRITE)
+    want = {}
+    scale = 1.0
+    for i in range(4):
+        scale *= 0.5
+        frame = cv2.resize(bgr, None, fx=scale, fy=scale, interpolation=cv2.INTER_NEAREST)
+        dframe = cv2.resize(depth, None, fx=scale, fy=scale, interpolation=cv2.INTER_NEAREST)
+        mono = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY)
+        fs.write(f"mono_{i}", mono); fs.write(f"depth_{i}", dframe)
+        want[f"mono_{i}"] = mono; want[f"depth_{i}"] = dframe
+    fs.release()
+    np.savez_compressed(os.path.join(HERE, "framemono_0000.npz"), **want)
+    print("wrote framemono_0000.xml / .npz")
 
 
 if __name__ == "__main__":

@@ -71,3 +71,60 @@ def eposeestimator(ref_bgr, ref_depth, now_bgr, now_depth, K, compat, level, ite
                                         C.c_double(K[3]), int(compat), level, iters, C.c_double(huber_k), C.c_double(lambda0), _p(R), _p(T), _p(A),
                                         C.byref(vis), C.byref(st), _p(J), _p(X), _p(g))
     return {"R": R.reshape(3, 3), "T": T, "A": A, "visible": vis.value, "status": st.value, "J": J, "X": X, "gray": g, "levels": nlev}
+
+
+# ---- FrameIO ----
+def store_frame_xml(path, mono_levels, depth_levels):
+    H, W = mono_levels[0].shape
+    mono = np.concatenate([np.ascontiguousarray(m, np.uint8).ravel() for m in mono_levels])
+    depth = np.concatenate([np.ascontiguousarray(d, np.uint16).ravel() for d in depth_levels])
+    return lib().hostapi_store_frame_xml(str(path).encode(), _p(mono), _p(depth), W, H, len(mono_levels))
+
+
+def load_frame_xml(path, levels, capacity=1 << 22):
+    mono = np.zeros(capacity, np.uint8); depth = np.zeros(capacity, np.uint16); dims = np.zeros(2 * levels, np.int32)
+    rc = lib().hostapi_load_frame_xml(str(path).encode(), levels, _p(mono), _p(depth), C.c_size_t(capacity), _p(dims))
+    if rc != 0:
+        return rc, None, None
+    ms, ds, off = [], [], 0
+    for l in range(levels):
+        r, c = int(dims[2 * l]), int(dims[2 * l + 1])
+        ms.append(mono[off:off + r * c].reshape(r, c).copy()); ds.append(depth[off:off + r * c].reshape(r, c).copy())
+        off += r * c
+    return 0, ms, ds
+
+
+def read_xml_matrix(path, name, capacity=1 << 20):
+    out = np.zeros(capacity, np.float64)
+    r, c, ch, el = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    rc = lib().hostapi_read_xml_matrix(str(path).encode(), name.encode(), _p(out), C.c_size_t(capacity), C.byref(r), C.byref(c), C.byref(ch), C.byref(el))
+    if rc != 0:
+        return rc, None, None
+    shape = (r.value, c.value, ch.value) if ch.value > 1 else (r.value, c.value)
+    return 0, out[: r.value * c.value * ch.value].reshape(shape).copy(), el.value
+
+
+def write_pose_file(path, q7):
+    q7 = np.ascontiguousarray(q7, np.float64).reshape(-1, 7)
+    return lib().hostapi_write_pose_file(str(path).encode(), _p(q7), len(q7))
+
+
+def read_pose_file(path, capacity=100000):
+    out = np.zeros((capacity, 7), np.float64)
+    n = lib().hostapi_read_pose_file(str(path).encode(), _p(out), capacity)
+    return None if n < 0 else out[:n].copy()
+
+
+def load_gt_path(path, skip=350, capacity=100000):
+    out = np.zeros((capacity, 7), np.float64)
+    n = lib().hostapi_load_gt_path(str(path).encode(), int(skip), _p(out), capacity)
+    return None if n < 0 else out[:n].copy()
+
+
+def solvedvo_from_files(ref_xml, now_xml, W, H, levels, iters, K):
+    it = np.array(iters, np.int32)
+    R = np.zeros(9); T = np.zeros(3)
+    rc = lib().hostapi_solvedvo_from_files(str(ref_xml).encode(), str(now_xml).encode(), W, H, levels, C.c_float(K[0]), C.c_float(K[1]),
+                                           C.c_float(K[2]), C.c_float(K[3]), _p(it), _p(R), _p(T))
+    assert rc == 0, rc
+    return R.reshape(3, 3), T
