@@ -248,6 +248,66 @@ int dvo_photo_get_A(dvo_photo_ctx* ctx, int slot, int level, double* A36);
 int dvo_photo_eval(dvo_photo_ctx* ctx, int slot, int level, const double* R9T3, int compat, double huber_k, double* b6, double* A36,
                    double* sumsq, int* nreproj, int* nused, double* canvas);
 
+/* ================================================================================================================
+ * RGBDOdometry (src/RGBDOdometry.cpp, include/RGBDOdometry.h:96-131): the semi-dense photometric Gauss-Newton --
+ * reference-frame Jacobian at pixels whose forward x-gradient is >= const_gradientThreshold, A = J^T J per level,
+ * three iterations of { eps, b = -J^T eps, psi = A.colPivHouseholderQr().solve(b), T <- T exp(psi)^-1 } with the
+ * ||eps|| < 200 early exit.  Batched like the other paths: slot = one (reference, now) pair.  Poses are row-major
+ * 4x4 affine transforms (TransformRep, include/RGBDOdometry.h:33).  Quirks of the reference are kept.
+ * ================================================================================================================ */
+#define DVO_RGBD_MAX_LEVELS 5
+typedef struct dvo_rgbd_ctx dvo_rgbd_ctx;
+
+typedef struct dvo_rgbd_config {
+    int width, height;   /* level-0 resolution */
+    int levels;          /* 2..5; the reference builds 4 (src/RGBDOdometry.cpp:343) */
+    int max_batch;
+    int device;
+} dvo_rgbd_config;
+
+typedef struct dvo_rgbd_params {
+    int iterations;          /* 3   (src/RGBDOdometry.cpp:541) */
+    int gradient_threshold;  /* 5   const_gradientThreshold   (:32) */
+    int min_points;          /* 100 const_minimumRequiredPts  (:34, assert :497) -> status bit 0 */
+    int max_points;          /* 50000 const_maxJacobianSize   (:33, assert :463) -> status bit 1 */
+    double eps_norm_exit;    /* 200.0 (:556) */
+} dvo_rgbd_params;
+
+typedef struct dvo_rgbd_info {
+    int status;                                  /* bit0: too few selected points at a level that ran; bit1: too many */
+    int npts[DVO_RGBD_MAX_LEVELS];               /* selected pixels (rows of J) */
+    int iters_run[DVO_RGBD_MAX_LEVELS];          /* epsilon evaluations of the last gaussNewtonIterations at the level */
+    int updates[DVO_RGBD_MAX_LEVELS];            /* pose updates applied */
+    int nvis_last[DVO_RGBD_MAX_LEVELS];          /* selected pixels that reprojected inside the now image */
+    double eps_norm_first[DVO_RGBD_MAX_LEVELS];  /* ||eps|| at the first / last evaluation */
+    double eps_norm_last[DVO_RGBD_MAX_LEVELS];
+} dvo_rgbd_info;
+
+int dvo_rgbd_create(const dvo_rgbd_config* cfg, dvo_rgbd_ctx** out);        /* RGBDOdometry::RGBDOdometry */
+int dvo_rgbd_destroy(dvo_rgbd_ctx* ctx);
+int dvo_rgbd_set_stream(dvo_rgbd_ctx* ctx, void* cuda_stream);
+int dvo_rgbd_synchronize(dvo_rgbd_ctx* ctx);
+long long dvo_rgbd_launch_count(dvo_rgbd_ctx* ctx);
+/* setCameraMatrix (:38-60): the same K is used at every level (the reference never rescales it) */
+int dvo_rgbd_set_intrinsics(dvo_rgbd_ctx* ctx, double fx, double fy, double cx, double cy);
+/* setRefFrame (frame 0) / setNowFrame (frame 1) (:330-390): BGR2GRAY at full resolution, INTER_NEAREST pyramids */
+int dvo_rgbd_set_frames(dvo_rgbd_ctx* ctx, int frame, int first, int count, const uint8_t* bgr, const uint16_t* depth, int mem);
+/* computeJacobianAllLevels (:393-415): A = J^T J and the selection count for levels 1..levels-1 of the reference frame */
+int dvo_rgbd_compute_jacobians(dvo_rgbd_ctx* ctx, int first, int count, int gradient_threshold);
+/* T of the next gaussNewtonIterations; NULL = identity.  16 doubles per slot (row-major 4x4), host memory. */
+int dvo_rgbd_set_pose(dvo_rgbd_ctx* ctx, int first, int count, const double* T16);
+/* gaussNewtonIterations(level, T) (:514-597); level 0 is rejected like the reference's assert (:518) */
+int dvo_rgbd_gauss_newton(dvo_rgbd_ctx* ctx, int first, int count, int level, const dvo_rgbd_params* prm);
+int dvo_rgbd_get_poses(dvo_rgbd_ctx* ctx, int first, int count, double* T16, dvo_rgbd_info* info);
+/* inspection */
+int dvo_rgbd_level_dims(dvo_rgbd_ctx* ctx, int level, int* rows, int* cols);
+int dvo_rgbd_get_level(dvo_rgbd_ctx* ctx, int slot, int frame, int level, uint8_t* gray, uint16_t* depth);
+int dvo_rgbd_get_A(dvo_rgbd_ctx* ctx, int slot, int level, double* A36, int* npts);
+/* computeJacobian (:407-505) + computeEpsilon (:602-700) of one slot / level at pose T, in the reference's enumeration
+ * order (column outer, row inner): ij = (row, col), J (n x 6), eps, uv = floor(outu, outv) or (-1, -1) when unseen */
+int dvo_rgbd_eval(dvo_rgbd_ctx* ctx, int slot, int level, const double* T16, int gradient_threshold, int capacity, int* n, int* ij,
+                  double* J, double* eps, int* uv, double* b6, double* sumsq, int* nvis);
+
 #ifdef __cplusplus
 }
 #endif

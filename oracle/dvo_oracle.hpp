@@ -942,4 +942,191 @@ inline void estimate(const RefLevel& L, const uint8_t* now_gray, Cam K, const do
 
 }  // namespace photo
 
+// ======================================================================================================
+// RGBDOdometry: the semi-dense photometric Gauss-Newton (src/RGBDOdometry.cpp).  fp64 like the
+// reference; quirks kept as written and listed where they occur.  Eigen-specific internals that cannot be restated
+// operation for operation (Affine inverse, colPivHouseholderQr) are replaced by the closed forms noted below.
+// ======================================================================================================
+namespace rgbd {
+
+struct Cam { double fx, fy, cx, cy; };                 // NOT scaled per pyramid level (src/RGBDOdometry.cpp:476-478, :606-612)
+
+struct Level { int rows = 0, cols = 0; std::vector<uint8_t> gray; std::vector<uint16_t> depth; };
+
+// setRefFrame / setNowFrame (:330-390): gray = BGR2GRAY at full resolution, then level i = resize(INTER_NEAREST, 2^-i)
+// of gray and depth (the colour pyramid is only drawn on).
+inline void build_pyramid(const uint8_t* bgr, const uint16_t* depth, int W, int H, int levels, std::vector<Level>& out) {
+    std::vector<uint8_t> gray((size_t)W * H);
+    bgr2gray(bgr, (size_t)W * H, gray.data());
+    out.assign(levels, Level());
+    for (int l = 0; l < levels; ++l) {
+        Level& L = out[l];
+        L.cols = level_dim(W, l); L.rows = level_dim(H, l);
+        L.gray.resize((size_t)L.rows * L.cols); L.depth.resize((size_t)L.rows * L.cols);
+        pyr_nearest(gray.data(), W, H, l, L.gray.data(), 1);
+        pyr_nearest(depth, W, H, l, L.depth.data(), 1);
+        for (auto& d : L.depth) if (d == 0) d = 1;        // imageArrivedCallBack: dframe.setTo(1, dframe == 0) (:232), "to avoid zero depth"
+    }
+}
+
+struct RefJacobian {
+    std::vector<int> pi, pj;          // selected pixels (row i, column j) in the reference's order: j outer, i inner (:459-462)
+    std::vector<double> J;            // N x 6
+    double A[36];                     // J^T J (:412)
+    int status = 0;                   // bit0: fewer than const_minimumRequiredPts + 1 points (:497); bit1: more than const_maxJacobianSize (:463)
+};
+
+// computeJacobian (:407-505).  Gradients: filter2D(CV_64F) with [0 -1 1] and its transpose (:425-437), REFLECT_101.
+// Selection: egx >= 5 -- the signed x-gradient only (:465).  X pairs the ROW index with cx and Y the column with cy,
+// depth stays in raw sensor units (mm), column 0 is fx*fx/Z (:474-488): all as written.
+inline void compute_jacobian(const Level& L, Cam K, int gradThresh, int maxJ, int minPts, RefJacobian& out) {
+    const int rows = L.rows, cols = L.cols;
+    out.pi.clear(); out.pj.clear(); out.J.clear(); out.status = 0;
+    for (int k = 0; k < 36; ++k) out.A[k] = 0.0;
+    const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy;
+    for (int j = 0; j < cols; ++j)
+        for (int i = 0; i < rows; ++i) {
+            const size_t p = (size_t)i * cols + j;
+            const int j1 = (j + 1 < cols) ? j + 1 : (cols > 1 ? cols - 2 : j), i1 = (i + 1 < rows) ? i + 1 : (rows > 1 ? rows - 2 : i);
+            const double gx = (double)L.gray[(size_t)i * cols + j1] - (double)L.gray[p];
+            const double gy = (double)L.gray[(size_t)i1 * cols + j] - (double)L.gray[p];
+            if (gx < (double)gradThresh) continue;
+            if ((int)out.pi.size() >= maxJ) { out.status |= 2; continue; }        // the reference asserts (:463)
+            const double Z = (double)L.depth[p];
+            const double X = Z * ((double)i - cx) / fx, Y = Z * ((double)j - cy) / fy;
+            const double invZ = 1 / Z, invZ2 = 1 / (Z * Z);
+            double r[6];
+            r[0] = fx * fx * invZ;
+            r[1] = fy * gy * invZ;
+            r[2] = -fy * gy * Y * invZ2 - fx * gx * X * invZ2;
+            r[3] = gy * (-fy * Y * Y * invZ2 - fy) - fx * gx * X * Y * invZ2;
+            r[4] = gx * (fx * X * X * invZ2 + fx) + fx * gy * X * Y * invZ2;
+            r[5] = fy * gy * X * invZ - fx * gy * Y * invZ;
+            out.pi.push_back(i); out.pj.push_back(j);
+            for (int k = 0; k < 6; ++k) out.J.push_back(r[k]);
+            for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) out.A[6 * a + b] += r[a] * r[b];
+        }
+    if ((int)out.pi.size() <= minPts) out.status |= 1;
+}
+
+// 3x3 inverse by the adjugate (Transform<double,3,Affine>::inverse() inverts the linear part as a general matrix).
+inline void inv3(const double* M, double* Mi) {
+    const double c00 = M[4] * M[8] - M[5] * M[7], c01 = M[5] * M[6] - M[3] * M[8], c02 = M[3] * M[7] - M[4] * M[6];
+    const double det = M[0] * c00 + M[1] * c01 + M[2] * c02, id = 1.0 / det;
+    Mi[0] = c00 * id; Mi[1] = (M[2] * M[7] - M[1] * M[8]) * id; Mi[2] = (M[1] * M[5] - M[2] * M[4]) * id;
+    Mi[3] = c01 * id; Mi[4] = (M[0] * M[8] - M[2] * M[6]) * id; Mi[5] = (M[2] * M[3] - M[0] * M[5]) * id;
+    Mi[6] = c02 * id; Mi[7] = (M[1] * M[6] - M[0] * M[7]) * id; Mi[8] = (M[0] * M[4] - M[1] * M[3]) * id;
+}
+// inverse of the affine transform T (row-major 4x4, last row 0 0 0 1): [L^-1, -L^-1 t]
+inline void affine_inverse(const double* T, double* Ti) {
+    double L[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]}, Li[9];
+    inv3(L, Li);
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c) Ti[4 * r + c] = Li[3 * r + c];
+        Ti[4 * r + 3] = -((Li[3 * r] * T[3] + Li[3 * r + 1] * T[7]) + Li[3 * r + 2] * T[11]);
+    }
+    Ti[12] = Ti[13] = Ti[14] = 0.0; Ti[15] = 1.0;
+}
+
+struct EpsOut { std::vector<double> eps; std::vector<int> u, v; double sumsq = 0; int nvis = 0; double b[6]; };
+
+// computeEpsilon (:602-700): eps_k = ref_gray(i,j) - now_gray(floor(outu), floor(outv)) where (outu, outv) projects
+// T^-1 [X Y Z]; outu is a ROW coordinate (it came from i) and is tested against rows; unseen points keep eps = 0.
+// b = -J^T eps (:562) is accumulated alongside.
+inline void compute_epsilon(const Level& ref, const RefJacobian& jac, const Level& now, Cam K, const double* T, EpsOut& o) {
+    const size_t N = jac.pi.size();
+    o.eps.assign(N, 0.0); o.u.assign(N, -1); o.v.assign(N, -1); o.sumsq = 0; o.nvis = 0;
+    for (int k = 0; k < 6; ++k) o.b[k] = 0.0;
+    double Ti[16]; affine_inverse(T, Ti);
+    const double fx = K.fx, fy = K.fy, cx = K.cx, cy = K.cy;
+    for (size_t k = 0; k < N; ++k) {
+        const int i = jac.pi[k], j = jac.pj[k];
+        const double Z = (double)ref.depth[(size_t)i * ref.cols + j];
+        const double X = Z * ((double)i - cx) / fx, Y = Z * ((double)j - cy) / fy;
+        const double o0 = ((Ti[0] * X + Ti[1] * Y) + Ti[2] * Z) + Ti[3];
+        const double o1 = ((Ti[4] * X + Ti[5] * Y) + Ti[6] * Z) + Ti[7];
+        const double o2 = ((Ti[8] * X + Ti[9] * Y) + Ti[10] * Z) + Ti[11];
+        const double outu = o0 * fx / o2 + cx, outv = o1 * fy / o2 + cy;
+        if (outu >= 0 && outu < (double)now.rows && outv >= 0 && outv < (double)now.cols) {
+            const int fu = (int)std::floor(outu), fv = (int)std::floor(outv);
+            const double e = (double)ref.gray[(size_t)i * ref.cols + j] - (double)now.gray[(size_t)fu * now.cols + fv];
+            o.eps[k] = e; o.u[k] = fu; o.v[k] = fv; o.sumsq += e * e; o.nvis++;
+            for (int c = 0; c < 6; ++c) o.b[c] -= jac.J[6 * k + c] * e;
+        }
+    }
+}
+
+// exponentialMap (:707-745): identity below theta = 1e-12, otherwise Rodrigues + V (no small-angle series).
+inline void exponential_map(const double* psi, double* out16) {
+    const double* t = psi; const double* w = psi + 3;
+    const double theta = std::sqrt((w[0] * w[0] + w[1] * w[1]) + w[2] * w[2]);
+    for (int k = 0; k < 16; ++k) out16[k] = (k % 5 == 0) ? 1.0 : 0.0;
+    if (theta < 1E-12) return;
+    const double wx[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};           // to_se_3 (:752-763)
+    double wx2[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) wx2[3 * r + c] = (wx[3 * r] * wx[c] + wx[3 * r + 1] * wx[3 + c]) + wx[3 * r + 2] * wx[6 + c];
+    const double a = std::sin(theta) / theta, b = (1.0 - std::cos(theta)) / (theta * theta), c3 = (theta - std::sin(theta)) / (theta * theta * theta);
+    double V[9];
+    for (int k = 0; k < 9; ++k) {
+        const double I = (k % 4 == 0) ? 1.0 : 0.0;
+        out16[4 * (k / 3) + (k % 3)] = (I + a * wx[k]) + b * wx2[k];
+        V[k] = (I + b * wx[k]) + c3 * wx2[k];
+    }
+    for (int r = 0; r < 3; ++r) out16[4 * r + 3] = (V[3 * r] * t[0] + V[3 * r + 1] * t[1]) + V[3 * r + 2] * t[2];
+}
+
+// A.colPivHouseholderQr().solve(b) (:563) for 6x6: Householder QR with column pivoting (largest remaining column norm).
+inline void colpiv_qr_solve6(const double* Ain, const double* bin, double* x) {
+    double A[36], b[6]; int perm[6];
+    std::memcpy(A, Ain, sizeof(A)); std::memcpy(b, bin, sizeof(b));
+    for (int k = 0; k < 6; ++k) perm[k] = k;
+    for (int k = 0; k < 6; ++k) {
+        int piv = k; double best = -1.0;
+        for (int c = k; c < 6; ++c) { double n2 = 0; for (int r = k; r < 6; ++r) n2 += A[6 * r + c] * A[6 * r + c]; if (n2 > best) { best = n2; piv = c; } }
+        if (piv != k) { for (int r = 0; r < 6; ++r) std::swap(A[6 * r + k], A[6 * r + piv]); std::swap(perm[k], perm[piv]); }
+        const double nrm = std::sqrt(best);
+        if (nrm == 0.0) continue;
+        const double alpha = (A[6 * k + k] > 0) ? -nrm : nrm;
+        double v[6] = {0, 0, 0, 0, 0, 0};
+        for (int r = k; r < 6; ++r) v[r] = A[6 * r + k];
+        v[k] -= alpha;
+        double vv = 0; for (int r = k; r < 6; ++r) vv += v[r] * v[r];
+        if (vv == 0.0) continue;
+        for (int c = k; c < 6; ++c) { double d = 0; for (int r = k; r < 6; ++r) d += v[r] * A[6 * r + c]; d = 2.0 * d / vv; for (int r = k; r < 6; ++r) A[6 * r + c] -= d * v[r]; }
+        { double d = 0; for (int r = k; r < 6; ++r) d += v[r] * b[r]; d = 2.0 * d / vv; for (int r = k; r < 6; ++r) b[r] -= d * v[r]; }
+    }
+    double y[6];
+    for (int r = 5; r >= 0; --r) {
+        double sacc = b[r]; for (int c = r + 1; c < 6; ++c) sacc -= A[6 * r + c] * y[c];
+        y[r] = (A[6 * r + r] != 0.0) ? sacc / A[6 * r + r] : 0.0;
+    }
+    for (int k = 0; k < 6; ++k) x[perm[k]] = y[k];
+}
+
+inline void mat4_mul_affine(const double* A, const double* B, double* C) {
+    double r[16];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) r[4 * i + j] = ((A[4 * i] * B[j] + A[4 * i + 1] * B[4 + j]) + A[4 * i + 2] * B[8 + j]) + A[4 * i + 3] * B[12 + j];
+    std::memcpy(C, r, sizeof(r));
+}
+
+struct GnInfo { int npts = 0, iters_run = 0, updates = 0, nvis_last = 0; double eps_norm_first = 0, eps_norm_last = 0; };
+
+// gaussNewtonIterations (:514-597): up to 3 x { eps; stop if ||eps|| < 200; b = -J^T eps; psi = A^-1 b; T <- T * exp(psi)^-1 }.
+inline void gauss_newton(const Level& ref, const RefJacobian& jac, const Level& now, Cam K, double* T, int iters, double epsExit, GnInfo& info) {
+    info = GnInfo(); info.npts = (int)jac.pi.size();
+    for (int itr = 0; itr < iters; ++itr) {
+        EpsOut e; compute_epsilon(ref, jac, now, K, T, e);
+        const double nrm = std::sqrt(e.sumsq);
+        if (itr == 0) info.eps_norm_first = nrm;
+        info.eps_norm_last = nrm; info.nvis_last = e.nvis; info.iters_run = itr + 1;
+        if (nrm < epsExit) break;                                                    // :556
+        double psi[6]; colpiv_qr_solve6(jac.A, e.b, psi);
+        double E[16], Ei[16]; exponential_map(psi, E); affine_inverse(E, Ei);
+        mat4_mul_affine(T, Ei, T);                                                   // :579
+        info.updates++;
+    }
+}
+
+}  // namespace rgbd
+
 }  // namespace orc

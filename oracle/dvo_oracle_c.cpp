@@ -253,4 +253,50 @@ void orc_photo_estimate(const uint8_t* now_gray_l, const double* K4, const doubl
 
 void orc_photo_exp_map(const double* psi, int compat, double* T16) { photo::exp_map(psi, compat != 0, T16); }
 
+// ---- RGBDOdometry (semi-dense photometric GN, src/RGBDOdometry.cpp) ----
+void orc_rgbd_level(const uint8_t* bgr, const uint16_t* depth, int W, int H, int level, uint8_t* gray_l, uint16_t* depth_l) {
+    std::vector<rgbd::Level> pyr; rgbd::build_pyramid(bgr, depth, W, H, level + 1, pyr);
+    std::memcpy(gray_l, pyr[level].gray.data(), pyr[level].gray.size());
+    std::memcpy(depth_l, pyr[level].depth.data(), pyr[level].depth.size() * 2);
+}
+// computeJacobian at one level; returns the number of selected points (J: cap x 6, ij: cap x 2 as (row, col))
+int orc_rgbd_jacobian(const uint8_t* bgr, const uint16_t* depth, int W, int H, int level, const double* K4, int thresh, int maxJ, int minPts,
+                      double* J, int* ij, int capacity, double* A36, int* status) {
+    std::vector<rgbd::Level> pyr; rgbd::build_pyramid(bgr, depth, W, H, level + 1, pyr);
+    rgbd::RefJacobian jac; rgbd::compute_jacobian(pyr[level], rgbd::Cam{K4[0], K4[1], K4[2], K4[3]}, thresh, maxJ, minPts, jac);
+    const int n = (int)jac.pi.size();
+    for (int k = 0; k < n && k < capacity; ++k) { if (ij) { ij[2 * k] = jac.pi[k]; ij[2 * k + 1] = jac.pj[k]; } if (J) std::memcpy(J + 6 * (size_t)k, &jac.J[6 * (size_t)k], 48); }
+    if (A36) std::memcpy(A36, jac.A, sizeof(jac.A));
+    if (status) *status = jac.status;
+    return n;
+}
+// computeEpsilon at one level and pose T (row-major 4x4)
+int orc_rgbd_epsilon(const uint8_t* ref_bgr, const uint16_t* ref_depth, const uint8_t* now_bgr, const uint16_t* now_depth, int W, int H, int level,
+                     const double* K4, int thresh, const double* T16, double* eps, int* uv, int capacity, double* b6, double* sumsq, int* nvis) {
+    std::vector<rgbd::Level> rp, np; rgbd::build_pyramid(ref_bgr, ref_depth, W, H, level + 1, rp); rgbd::build_pyramid(now_bgr, now_depth, W, H, level + 1, np);
+    const rgbd::Cam K{K4[0], K4[1], K4[2], K4[3]};
+    rgbd::RefJacobian jac; rgbd::compute_jacobian(rp[level], K, thresh, 1 << 30, 0, jac);
+    rgbd::EpsOut e; rgbd::compute_epsilon(rp[level], jac, np[level], K, T16, e);
+    const int n = (int)jac.pi.size();
+    for (int k = 0; k < n && k < capacity; ++k) { if (eps) eps[k] = e.eps[k]; if (uv) { uv[2 * k] = e.u[k]; uv[2 * k + 1] = e.v[k]; } }
+    if (b6) std::memcpy(b6, e.b, sizeof(e.b));
+    if (sumsq) *sumsq = e.sumsq;
+    if (nvis) *nvis = e.nvis;
+    return n;
+}
+void orc_rgbd_exponential_map(const double* psi6, double* out16) { rgbd::exponential_map(psi6, out16); }
+void orc_rgbd_qr_solve6(const double* A36, const double* b6, double* x6) { rgbd::colpiv_qr_solve6(A36, b6, x6); }
+// eventLoop body (:147-160): gaussNewtonIterations over `levels[]` in order, T carried; info: per level npts, iters_run, updates, nvis_last, eps_first, eps_last
+void orc_rgbd_gauss_newton(const uint8_t* ref_bgr, const uint16_t* ref_depth, const uint8_t* now_bgr, const uint16_t* now_depth, int W, int H,
+                           const double* K4, int thresh, const int* levels, int nlevels, int iters, double eps_exit, double* T16, double* info6) {
+    int maxl = 0; for (int k = 0; k < nlevels; ++k) if (levels[k] > maxl) maxl = levels[k];
+    std::vector<rgbd::Level> rp, np; rgbd::build_pyramid(ref_bgr, ref_depth, W, H, maxl + 1, rp); rgbd::build_pyramid(now_bgr, now_depth, W, H, maxl + 1, np);
+    const rgbd::Cam K{K4[0], K4[1], K4[2], K4[3]};
+    for (int k = 0; k < nlevels; ++k) {
+        rgbd::RefJacobian jac; rgbd::compute_jacobian(rp[levels[k]], K, thresh, 1 << 30, 0, jac);
+        rgbd::GnInfo gi; rgbd::gauss_newton(rp[levels[k]], jac, np[levels[k]], K, T16, iters, eps_exit, gi);
+        if (info6) { double* o = info6 + 6 * k; o[0] = gi.npts; o[1] = gi.iters_run; o[2] = gi.updates; o[3] = gi.nvis_last; o[4] = gi.eps_norm_first; o[5] = gi.eps_norm_last; }
+    }
+}
+
 }  // extern "C"

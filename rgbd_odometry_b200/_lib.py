@@ -33,6 +33,24 @@ class PhotoInfo(C.Structure):
                 ("sumsq_last", C.c_double), ("visible", C.c_double), ("A", C.c_double * 36), ("b", C.c_double * 6)]
 
 
+RGBD_MAX_LEVELS = 5
+
+
+class RgbdConfig(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("levels", C.c_int), ("max_batch", C.c_int), ("device", C.c_int)]
+
+
+class RgbdParams(C.Structure):
+    _fields_ = [("iterations", C.c_int), ("gradient_threshold", C.c_int), ("min_points", C.c_int), ("max_points", C.c_int),
+                ("eps_norm_exit", C.c_double)]
+
+
+class RgbdInfo(C.Structure):
+    _fields_ = [("status", C.c_int), ("npts", C.c_int * RGBD_MAX_LEVELS), ("iters_run", C.c_int * RGBD_MAX_LEVELS),
+                ("updates", C.c_int * RGBD_MAX_LEVELS), ("nvis_last", C.c_int * RGBD_MAX_LEVELS),
+                ("eps_norm_first", C.c_double * RGBD_MAX_LEVELS), ("eps_norm_last", C.c_double * RGBD_MAX_LEVELS)]
+
+
 # every symbol include/dvo_b200.h declares
 SYMBOLS = [
     "dvo_last_error", "dvo_device_count", "dvo_create", "dvo_destroy", "dvo_set_stream", "dvo_synchronize",
@@ -43,6 +61,9 @@ SYMBOLS = [
     "dvo_photo_create", "dvo_photo_destroy", "dvo_photo_set_stream", "dvo_photo_synchronize", "dvo_photo_launch_count",
     "dvo_photo_set_intrinsics", "dvo_photo_set_frames", "dvo_photo_prepare_ref", "dvo_photo_set_pose", "dvo_photo_estimate",
     "dvo_photo_get_poses", "dvo_photo_get_level", "dvo_photo_get_A", "dvo_photo_eval",
+    "dvo_rgbd_create", "dvo_rgbd_destroy", "dvo_rgbd_set_stream", "dvo_rgbd_synchronize", "dvo_rgbd_launch_count",
+    "dvo_rgbd_set_intrinsics", "dvo_rgbd_set_frames", "dvo_rgbd_compute_jacobians", "dvo_rgbd_set_pose", "dvo_rgbd_gauss_newton",
+    "dvo_rgbd_get_poses", "dvo_rgbd_level_dims", "dvo_rgbd_get_level", "dvo_rgbd_get_A", "dvo_rgbd_eval",
 ]
 
 _lib = None
@@ -107,6 +128,23 @@ def load(build_if_missing=True):
     lib.dvo_photo_get_A.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.dvo_photo_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    lib.dvo_rgbd_create.argtypes = [C.POINTER(RgbdConfig), C.POINTER(C.c_void_p)]
+    lib.dvo_rgbd_destroy.argtypes = [C.c_void_p]
+    lib.dvo_rgbd_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    lib.dvo_rgbd_synchronize.argtypes = [C.c_void_p]
+    lib.dvo_rgbd_launch_count.restype = C.c_longlong
+    lib.dvo_rgbd_launch_count.argtypes = [C.c_void_p]
+    lib.dvo_rgbd_set_intrinsics.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+    lib.dvo_rgbd_set_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.dvo_rgbd_compute_jacobians.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.dvo_rgbd_set_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dvo_rgbd_gauss_newton.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(RgbdParams)]
+    lib.dvo_rgbd_get_poses.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.dvo_rgbd_level_dims.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    lib.dvo_rgbd_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    lib.dvo_rgbd_get_A.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int)]
+    lib.dvo_rgbd_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]
     _lib = lib
     return lib
 

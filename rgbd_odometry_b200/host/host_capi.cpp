@@ -8,6 +8,7 @@
 #include "EPoseEstimator.h"
 #include "FrameIO.h"
 #include "GOP.h"
+#include "RGBDOdometry.h"
 #include "SolveDVO.h"
 
 extern "C" {
@@ -214,6 +215,43 @@ int hostapi_solvedvo_from_files(const char* ref_xml, const char* now_xml, int W,
     for (int i = 0; i < 9; ++i) R9[i] = cR.m[i];
     for (int i = 0; i < 3; ++i) T3[i] = cT.v[i];
     return 0;
+}
+
+// RGBDOdometry::eventLoop body over an in-memory sequence of BGR / depth frames: out = nframes * 16 doubles (base * T)
+int hostapi_rgbdodometry_sequence(const uint8_t* bgr, const uint16_t* depth, int nframes, int W, int H, double fx, double fy, double cx, double cy,
+                                  int ref_every, double* out16, int* npts_l2, double* eps_last_l2) {
+    RGBDOdometry o;
+    o.setCameraMatrix(fx, fy, cx, cy);
+    const size_t P = (size_t)W * H;
+    for (int t = 0; t < nframes; ++t) {
+        o.setRcvdFrame(dvo::ImageView(bgr + 3 * P * t, H, W, dvo::U8C3), dvo::ImageView(depth + P * t, H, W, dvo::U16C1));
+        const TransformRep g = o.processFrame(ref_every);
+        std::memcpy(out16 + 16 * (size_t)t, g.m, sizeof(g.m));
+        if (npts_l2) npts_l2[t] = o.lastInfo.npts[2];
+        if (eps_last_l2) eps_last_l2[t] = o.lastInfo.eps_norm_last[2];
+    }
+    return 0;
+}
+// computeJacobian / computeEpsilon materialised through the class (level, T) for one pair
+int hostapi_rgbdodometry_materialise(const uint8_t* ref_bgr, const uint16_t* ref_depth, const uint8_t* now_bgr, const uint16_t* now_depth, int W, int H,
+                                     double fx, double fy, double cx, double cy, int level, const double* T16, double* J, int* marks, double* eps,
+                                     int* newroi, int capacity) {
+    RGBDOdometry o;
+    o.setCameraMatrix(fx, fy, cx, cy);
+    const dvo::ImageView rf(ref_bgr, H, W, dvo::U8C3), rd(ref_depth, H, W, dvo::U16C1), nf(now_bgr, H, W, dvo::U8C3), nd(now_depth, H, W, dvo::U16C1);
+    o.setRcvdFrame(rf, rd); o.setRefFrame(rf, rd); o.computeJacobianAllLevels();
+    o.setRcvdFrame(nf, nd); o.setNowFrame(nf, nd);
+    dvo::MatrixXd Jm; MatrixXi mk;
+    o.computeJacobian(level, Jm, mk);
+    if (Jm.rows > capacity) return -1;
+    std::memcpy(J, Jm.data.data(), sizeof(double) * Jm.data.size());
+    std::memcpy(marks, mk.data.data(), sizeof(int) * mk.data.size());
+    TransformRep T; std::memcpy(T.m, T16, sizeof(T.m));
+    std::vector<double> e; MatrixXi roi;
+    o.computeEpsilon(level, T, e, roi);
+    std::memcpy(eps, e.data(), sizeof(double) * e.size());
+    std::memcpy(newroi, roi.data.data(), sizeof(int) * roi.data.size());
+    return Jm.rows;
 }
 
 }  // extern "C"

@@ -128,3 +128,27 @@ def solvedvo_from_files(ref_xml, now_xml, W, H, levels, iters, K):
                                            C.c_float(K[2]), C.c_float(K[3]), _p(it), _p(R), _p(T))
     assert rc == 0, rc
     return R.reshape(3, 3), T
+
+
+# ---- RGBDOdometry host class ----
+def rgbdodometry_sequence(bgr, depth, K, ref_every=10000):
+    n, H, W = depth.shape
+    bgr = np.ascontiguousarray(bgr, np.uint8); depth = np.ascontiguousarray(depth, np.uint16)
+    out = np.empty((n, 4, 4)); npts = np.empty(n, np.int32); eps = np.empty(n, np.float64)
+    rc = lib().hostapi_rgbdodometry_sequence(_p(bgr), _p(depth), n, W, H, C.c_double(K[0]), C.c_double(K[1]), C.c_double(K[2]), C.c_double(K[3]),
+                                             int(ref_every), _p(out), _p(npts), _p(eps))
+    assert rc == 0
+    return out, npts, eps
+
+
+def rgbdodometry_materialise(ref_bgr, ref_depth, now_bgr, now_depth, K, level, T):
+    H, W = ref_depth.shape
+    h, w = H >> level, W >> level
+    cap = h * w
+    J = np.zeros((cap, 6)); marks = np.zeros((h, w), np.int32); eps = np.zeros(cap); roi = np.zeros((h, w), np.int32)
+    T = np.ascontiguousarray(T, np.float64).reshape(16)
+    n = lib().hostapi_rgbdodometry_materialise(_p(np.ascontiguousarray(ref_bgr)), _p(np.ascontiguousarray(ref_depth)), _p(np.ascontiguousarray(now_bgr)),
+                                               _p(np.ascontiguousarray(now_depth)), W, H, C.c_double(K[0]), C.c_double(K[1]), C.c_double(K[2]),
+                                               C.c_double(K[3]), level, _p(T), _p(J), _p(marks), _p(eps), _p(roi), cap)
+    assert n >= 0
+    return J[:n].copy(), marks, eps[:n].copy(), roi

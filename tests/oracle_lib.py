@@ -434,3 +434,58 @@ def photo_estimate(now_gray_l, R0, T0, iters, K=K640, compat=False, huber_k=0.0,
                              C.byref(ir), C.byref(st), C.byref(vis))
     return {"R": R.reshape(3, 3), "T": T, "sumsq_first": s0.value, "sumsq_last": s1.value, "iters_run": ir.value, "status": st.value,
             "visible": vis.value}
+
+
+# ---- RGBDOdometry (semi-dense photometric GN) ----
+def rgbd_level(bgr, depth, level):
+    H, W = depth.shape
+    h, w = level_dim(H, level), level_dim(W, level)
+    g = np.empty((h, w), np.uint8); d = np.empty((h, w), np.uint16)
+    lib().orc_rgbd_level(_p(np.ascontiguousarray(bgr), C.c_uint8), _p(np.ascontiguousarray(depth), C.c_uint16), W, H, level, _p(g, C.c_uint8), _p(d, C.c_uint16))
+    return g, d
+
+
+def rgbd_jacobian(bgr, depth, level, K, thresh=5, max_j=1 << 30, min_pts=100):
+    H, W = depth.shape
+    cap = level_dim(H, level) * level_dim(W, level)
+    J = np.empty((cap, 6), np.float64); ij = np.empty((cap, 2), np.int32); A = np.empty(36, np.float64); st = C.c_int()
+    K4 = np.array(K, np.float64)
+    lib().orc_rgbd_jacobian.restype = C.c_int
+    n = lib().orc_rgbd_jacobian(_p(np.ascontiguousarray(bgr), C.c_uint8), _p(np.ascontiguousarray(depth), C.c_uint16), W, H, level, _p(K4, C.c_double),
+                                thresh, max_j, min_pts, _p(J, C.c_double), _p(ij, C.c_int32), cap, _p(A, C.c_double), C.byref(st))
+    return {"J": J[:n].copy(), "ij": ij[:n].copy(), "A": A.reshape(6, 6), "status": st.value}
+
+
+def rgbd_epsilon(ref_bgr, ref_depth, now_bgr, now_depth, level, K, T, thresh=5):
+    H, W = ref_depth.shape
+    cap = level_dim(H, level) * level_dim(W, level)
+    eps = np.empty(cap, np.float64); uv = np.empty((cap, 2), np.int32); b = np.empty(6, np.float64); ss = C.c_double(); nv = C.c_int()
+    K4 = np.array(K, np.float64); T16 = np.ascontiguousarray(T, np.float64).reshape(16)
+    lib().orc_rgbd_epsilon.restype = C.c_int
+    n = lib().orc_rgbd_epsilon(_p(np.ascontiguousarray(ref_bgr), C.c_uint8), _p(np.ascontiguousarray(ref_depth), C.c_uint16),
+                               _p(np.ascontiguousarray(now_bgr), C.c_uint8), _p(np.ascontiguousarray(now_depth), C.c_uint16), W, H, level,
+                               _p(K4, C.c_double), thresh, _p(T16, C.c_double), _p(eps, C.c_double), _p(uv, C.c_int32), cap, _p(b, C.c_double),
+                               C.byref(ss), C.byref(nv))
+    return {"eps": eps[:n].copy(), "uv": uv[:n].copy(), "b": b, "sumsq": ss.value, "nvis": nv.value}
+
+
+def rgbd_exponential_map(psi):
+    out = np.empty(16, np.float64)
+    lib().orc_rgbd_exponential_map(_p(np.ascontiguousarray(psi, np.float64), C.c_double), _p(out, C.c_double))
+    return out.reshape(4, 4)
+
+
+def rgbd_qr_solve6(A, b):
+    x = np.empty(6, np.float64)
+    lib().orc_rgbd_qr_solve6(_p(np.ascontiguousarray(A, np.float64).reshape(36), C.c_double), _p(np.ascontiguousarray(b, np.float64), C.c_double), _p(x, C.c_double))
+    return x
+
+
+def rgbd_gauss_newton(ref_bgr, ref_depth, now_bgr, now_depth, K, levels=(3, 2), iters=3, eps_exit=200.0, thresh=5, T0=None):
+    H, W = ref_depth.shape
+    T = np.eye(4).reshape(16).copy() if T0 is None else np.array(T0, np.float64).reshape(16).copy()
+    lv = np.array(levels, np.int32); info = np.zeros((len(levels), 6), np.float64); K4 = np.array(K, np.float64)
+    lib().orc_rgbd_gauss_newton(_p(np.ascontiguousarray(ref_bgr), C.c_uint8), _p(np.ascontiguousarray(ref_depth), C.c_uint16),
+                                _p(np.ascontiguousarray(now_bgr), C.c_uint8), _p(np.ascontiguousarray(now_depth), C.c_uint16), W, H, _p(K4, C.c_double),
+                                thresh, _p(lv, C.c_int32), len(levels), iters, C.c_double(eps_exit), _p(T, C.c_double), _p(info, C.c_double))
+    return T.reshape(4, 4), info

@@ -65,3 +65,27 @@ def test_eposeestimator_class(compat):
         oe = O.photo_estimate(O.photo_now_level(d["now_bgr"], level), np.eye(3), np.zeros(3), 6, K, compat=False, huber_k=10.0, lambda0=1e-3)
         assert g["status"] == oe["status"]
         assert rot_angle(g["R"], oe["R"]) < 1e-7 and np.linalg.norm(g["T"] - oe["T"]) < 1e-9
+
+
+def test_rgbdodometry_class_matches_oracle():
+    """RGBDOdometry (host class over dvo_rgbd_*): eventLoop's schedule over a short sequence and the materialised
+    computeJacobian / computeEpsilon outputs against the oracle's restatement of src/RGBDOdometry.cpp."""
+    Wd, Hd, Kd = 320, 240, (262.5, 262.5, 159.5, 119.5)
+    gray, depth, _, _ = O.synth_sequence(77, 4, Wd, Hd, Kd)
+    bgr = np.repeat(gray[..., None], 3, axis=3)                      # BGR2GRAY(g, g, g) == g exactly
+    out, npts, eps = Hh.rgbdodometry_sequence(bgr, depth, Kd)
+    T = np.eye(4)
+    for t in range(4):
+        T, info = O.rgbd_gauss_newton(bgr[0], depth[0], bgr[t], depth[t], Kd, levels=(3, 2), T0=T)
+        assert np.allclose(out[t], T, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(T).max())), f"frame {t}: {np.abs(out[t] - T).max()}"
+        assert npts[t] == int(info[1, 0]) and abs(eps[t] - info[1, 5]) <= 1e-9 * max(1.0, info[1, 5])
+    assert np.abs(out[3] - np.eye(4)).max() > 1e-6
+    J, marks, e, roi = Hh.rgbdodometry_materialise(bgr[0], depth[0], bgr[2], depth[2], Kd, 2, out[2])
+    oj = O.rgbd_jacobian(bgr[0], depth[0], 2, Kd)
+    oe = O.rgbd_epsilon(bgr[0], depth[0], bgr[2], depth[2], 2, Kd, out[2])
+    assert np.array_equal(J, oj["J"]) and np.array_equal(e, oe["eps"])
+    want = np.zeros_like(marks); want[oj["ij"][:, 0], oj["ij"][:, 1]] = 1
+    assert np.array_equal(marks, want)
+    seen = oe["uv"][oe["uv"][:, 0] >= 0]
+    wroi = np.zeros_like(roi); wroi[seen[:, 0], seen[:, 1]] = 1
+    assert np.array_equal(roi, wroi)

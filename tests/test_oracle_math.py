@@ -158,3 +158,22 @@ def test_interpolated_dt_lookup_properties():
     # within one pixel of the right / bottom border the ceil index is clamped: the lookup degenerates to the last column / row
     assert lookup(15.5, 3.0) == F[3, 15]
     assert lookup(2.0, 11.75) == F[11, 2]
+
+
+def test_rgbd_exponential_map_and_qr_solve():
+    """RGBDOdometry::exponentialMap (src/RGBDOdometry.cpp:707-745) against scipy's matrix exponential of the twist, and the
+    pivoted Householder QR solve (:563) against numpy on well- and ill-scaled SPD systems."""
+    from scipy.linalg import expm
+    rng = np.random.default_rng(11)
+    for _ in range(20):
+        psi = np.concatenate([rng.standard_normal(3), rng.standard_normal(3) * 0.3])
+        w = psi[3:]
+        tw = np.zeros((4, 4)); tw[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]; tw[:3, 3] = psi[:3]
+        assert np.allclose(O.rgbd_exponential_map(psi), expm(tw), atol=1e-12)
+    assert np.array_equal(O.rgbd_exponential_map(np.array([1.0, 2.0, 3.0, 0, 0, 1e-13])), np.eye(4))     # theta < 1e-12 -> identity, translation dropped (:718-722)
+    for scale in (1.0, 1e6):
+        J = rng.standard_normal((200, 6)) * np.array([scale, 1, 1, 1e-3, 1, 1])
+        A = J.T @ J; b = rng.standard_normal(6)
+        x = O.rgbd_qr_solve6(A, b)
+        assert np.allclose(A @ x, b, rtol=1e-8, atol=1e-8 * np.abs(b).max())
+        assert np.allclose(x, np.linalg.solve(A, b), rtol=1e-6)
