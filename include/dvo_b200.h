@@ -153,6 +153,27 @@ int dvo_align_batch(dvo_ctx* ctx, int count, const uint8_t* ref_gray, const uint
 int dvo_run_sequences(dvo_ctx* ctx, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* params,
                       int keyframe_every, double* rel_poses, int* kind, double* global_poses);
 
+/* Key-frame policy of SolveDVO::loop (src/SolveDVO.cpp:2117-2160): after a frame is solved against the current
+ * reference, the residual statistic b = mean(eps_best) (processResidueHistogram :1398-1483), the visible ratio and the
+ * number of reprojected points of the finest level decide whether the PREVIOUS frame becomes the new reference (pose
+ * reset, re-solve; :2192-2233).  The reference ships with the three quality gates commented out (:2129-2151) and only
+ * the periodic rule (:2155-2160); use_quality_gates = 1 evaluates them as designed, in source order, OR-ed with the
+ * periodic rule.  Reasons as the reference numbers them: 2 laplacian b, 3 visible ratio, 4 too few points, 5 periodic. */
+typedef struct dvo_keyframe_policy {
+    int keyframe_every;           /* 5 (:2156); <= 0 disables the periodic rule                 */
+    int use_quality_gates;        /* 0 = as shipped                                             */
+    float laplacian_thresh;       /* laplacianThreshExitCond = 3.0 (:23)                        */
+    float visible_ratio_thresh;   /* ratio_of_visible_pts_thresh = 0.8 (:22)                    */
+    int min_reprojections;        /* 50 (:2145)                                                 */
+} dvo_keyframe_policy;
+/* dvo_run_sequences with the decision taken per sequence ON THE DEVICE from the solver's own outputs: the gate kernel
+ * writes a per-slot switch mask and the promote / pyramid / edge / solve kernels of the switch pass skip the other
+ * slots, so no pose or statistic crosses PCIe between frames.  reason [nseq][nframes] receives the reference's reason
+ * code at the frames that were promoted to key frames (0 elsewhere; frame 0 is a key frame with reason 1, :2016). */
+int dvo_run_sequences_gated(dvo_ctx* ctx, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth,
+                            const dvo_solver_params* params, const dvo_keyframe_policy* policy, double* rel_poses, int* kind,
+                            int* reason, double* global_poses);
+
 /* ---- inspection (parity tests; not on the hot path) ---- */
 int dvo_level_dims(dvo_ctx* ctx, int level, int* w, int* h);
 int dvo_get_level_buffer(dvo_ctx* ctx, int slot, int frame, int level, int which, void* host_dst, size_t bytes);

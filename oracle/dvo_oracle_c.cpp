@@ -118,10 +118,14 @@ int orc_run_iterations(const float* X, const float* Y, const float* Z, int N, co
 int orc_align_pair(const uint8_t* ref_gray, const uint16_t* ref_depth, const uint8_t* now_gray, int W, int H,
                    int levels, float fx, float fy, float cx, float cy, const int* iters, const orc_solver_cfg* cfg,
                    const double* R0, const double* T0, double* R9, double* T3, int* npts, int* best_index,
-                   int* iterations_run, float* best_energy, float* visible_ratio, double* trace, int trace_max_iter) {
+                   int* iterations_run, float* best_energy, float* visible_ratio, double* trace, int trace_max_iter, float* b_cap) {
     PairResult pr;
     align_pair(ref_gray, ref_depth, now_gray, W, H, levels, Intrinsics{fx, fy, cx, cy}, iters, to_cfg(cfg), R0, T0, pr,
-               trace != nullptr, false);
+               trace != nullptr, b_cap != nullptr);
+    if (b_cap) {          // processResidueHistogram of the last runIterations call, i.e. the finest level run (src/SolveDVO.cpp:2117-2120)
+        *b_cap = 0.f;
+        for (int l = 0; l < levels; ++l) if (iters[l] > 0) { *b_cap = laplacian_b(pr.levels[l].best_eps); break; }
+    }
     std::memcpy(R9, pr.R, sizeof(pr.R)); std::memcpy(T3, pr.T, sizeof(pr.T));
     for (int l = 0; l < levels; ++l) {
         if (npts) npts[l] = (int)pr.npts[l];

@@ -33,6 +33,11 @@ class PhotoInfo(C.Structure):
                 ("sumsq_last", C.c_double), ("visible", C.c_double), ("A", C.c_double * 36), ("b", C.c_double * 6)]
 
 
+class KeyframePolicy(C.Structure):
+    _fields_ = [("keyframe_every", C.c_int), ("use_quality_gates", C.c_int), ("laplacian_thresh", C.c_float),
+                ("visible_ratio_thresh", C.c_float), ("min_reprojections", C.c_int)]
+
+
 RGBD_MAX_LEVELS = 5
 
 
@@ -57,7 +62,7 @@ SYMBOLS = [
     "dvo_set_intrinsics", "dvo_set_frames", "dvo_promote_now_to_ref", "dvo_build_pyramids", "dvo_prepare",
     "dvo_set_initial_pose", "dvo_run", "dvo_get_poses", "dvo_align_batch", "dvo_level_dims", "dvo_get_level_buffer",
     "dvo_get_points", "dvo_eval_normal_equations", "dvo_eval_normal_equations_ex", "dvo_get_trace", "dvo_enable_timing", "dvo_get_stage_ms",
-    "dvo_launch_count", "dvo_gop_compose", "dvo_run_sequences",
+    "dvo_launch_count", "dvo_gop_compose", "dvo_run_sequences", "dvo_run_sequences_gated",
     "dvo_photo_create", "dvo_photo_destroy", "dvo_photo_set_stream", "dvo_photo_synchronize", "dvo_photo_launch_count",
     "dvo_photo_set_intrinsics", "dvo_photo_set_frames", "dvo_photo_prepare_ref", "dvo_photo_set_pose", "dvo_photo_estimate",
     "dvo_photo_get_poses", "dvo_photo_get_level", "dvo_photo_get_A", "dvo_photo_eval",
@@ -112,6 +117,8 @@ def load(build_if_missing=True):
     lib.dvo_gop_compose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.dvo_run_sequences.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(SolverParams), C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dvo_run_sequences_gated.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(SolverParams),
+                                            C.POINTER(KeyframePolicy), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dvo_photo_create.argtypes = [C.POINTER(PhotoConfig), C.POINTER(C.c_void_p)]
     lib.dvo_photo_destroy.argtypes = [C.c_void_p]
     lib.dvo_photo_set_stream.argtypes = [C.c_void_p, C.c_void_p]

@@ -4,7 +4,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import Config, PairInfo, SolverParams, check
+from ._lib import Config, KeyframePolicy, PairInfo, SolverParams, check
 
 SUBGRAD_REF, GN, LM = 0, 1, 2
 JAC_REFERENCE, JAC_EXACT = 0, 1
@@ -25,6 +25,11 @@ def solver_params(solver=SUBGRAD_REF, jacobian=JAC_REFERENCE, weight=W_REF_CAUCH
     for i in range(_lib.MAX_LEVELS):
         p.iters[i] = int(iters[i]) if i < len(iters) else 0
     return p
+
+
+def keyframe_policy(keyframe_every=5, use_quality_gates=False, laplacian_thresh=3.0, visible_ratio_thresh=0.8, min_reprojections=50):
+    """Defaults are the reference's constants (src/SolveDVO.cpp:22-23, :2145, :2156); the gates ship disabled there."""
+    return KeyframePolicy(keyframe_every, int(use_quality_gates), laplacian_thresh, visible_ratio_thresh, min_reprojections)
 
 
 def _ptr(a):
@@ -126,6 +131,19 @@ class BatchAligner:
         check(self.lib.dvo_run_sequences(self.h, nseq, nframes, _ptr(gray), _ptr(depth), C.byref(params), keyframe_every, _ptr(rel),
                                          _ptr(kind), _ptr(glob)), "dvo_run_sequences")
         return rel, kind, glob
+
+    def run_sequences_gated(self, gray, depth, params, policy):
+        """SolveDVO::loop with the key-frame decision (periodic rule and / or the quality gates) taken per sequence on the device."""
+        gray = np.ascontiguousarray(gray, np.uint8)
+        depth = np.ascontiguousarray(depth, np.uint16)
+        nseq, nframes = gray.shape[:2]
+        rel = np.empty((nseq, nframes, 12), np.float64)
+        kind = np.empty((nseq, nframes), np.int32)
+        reason = np.empty((nseq, nframes), np.int32)
+        glob = np.empty((nseq, nframes, 19), np.float64)
+        check(self.lib.dvo_run_sequences_gated(self.h, nseq, nframes, _ptr(gray), _ptr(depth), C.byref(params), C.byref(policy), _ptr(rel),
+                                               _ptr(kind), _ptr(reason), _ptr(glob)), "dvo_run_sequences_gated")
+        return rel, kind, reason, glob
 
     def level_dims(self, level):
         w, h = C.c_int(), C.c_int()

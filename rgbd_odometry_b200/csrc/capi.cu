@@ -103,7 +103,7 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     c->now_valid = (unsigned char*)calloc(B, 1); c->prev_valid = (unsigned char*)calloc(B, 1);
     A(dalloc(&c->gcol, T)); A(dalloc(&c->d2, T)); A(dalloc(&c->texel, T));
     A(dalloc(&c->ptsX, T)); A(dalloc(&c->ptsY, T)); A(dalloc(&c->ptsZ, T)); A(dalloc(&c->ptsPix, T));
-    A(dalloc(&c->npts, B * g.L)); A(dalloc(&c->solve_order, B)); A(dalloc(&c->nedge, 2 * B * g.L)); A(dalloc(&c->maxd2, B * g.L));
+    A(dalloc(&c->npts, B * g.L)); A(dalloc(&c->solve_order, B)); A(dalloc(&c->seq_mask, B)); A(dalloc(&c->seq_state, B)); A(dalloc(&c->nedge, 2 * B * g.L)); A(dalloc(&c->maxd2, B * g.L));
     A(dalloc(&c->pose0, B * 12)); A(dalloc(&c->pose, B * 12)); A(dalloc(&c->info, B));
     if (cfg->trace_iters > 0) A(dalloc(&c->trace, B * g.L * cfg->trace_iters * DVO_TRACE_DOUBLES));
     // hysteresis bitmaps that do not fit in shared memory live in a global scratch (one pair of bitmaps per CTA)
@@ -132,7 +132,7 @@ int dvo_destroy(dvo_ctx* c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int f = 0; f < 2; ++f) { cudaFree(c->gray[f]); cudaFree(c->depth[f]); cudaFree(c->edge[f]); }
     cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ); cudaFree(c->ptsPix);
-    cudaFree(c->npts); cudaFree(c->solve_order); cudaFree(c->nedge); cudaFree(c->maxd2); cudaFree(c->pose0); cudaFree(c->pose); cudaFree(c->info);
+    cudaFree(c->npts); cudaFree(c->solve_order); cudaFree(c->seq_mask); cudaFree(c->seq_state); cudaFree(c->nedge); cudaFree(c->maxd2); cudaFree(c->pose0); cudaFree(c->pose); cudaFree(c->info);
     cudaFree(c->trace); cudaFree(c->bitmap_scratch); cudaFree(c->prev_gray); cudaFree(c->prev_depth);
     free(c->now_valid); free(c->prev_valid);
     if (c->h_pose) cudaFreeHost(c->h_pose);
@@ -341,6 +341,124 @@ int dvo_run_sequences(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, co
     }
     if (global_poses) return dvo_gop_compose(c, nseq, nframes, kind, rel_poses, global_poses, DVO_MEM_HOST);
     return DVO_OK;
+}
+
+// ---- gated sequence loop: the key-frame decision of SolveDVO::loop (:2117-2233) taken per slot on the device ----
+}  // extern "C"
+
+namespace {
+__global__ void seq_gate_kernel(int nseq, int nframes, int t, dvo_keyframe_policy pol, int finest, const dvo_pair_info* __restrict__ info,
+                                const double* __restrict__ pose, double* __restrict__ pose0, int* __restrict__ lastRef,
+                                unsigned char* __restrict__ mask, double* __restrict__ rel, int* __restrict__ kind, int* __restrict__ reason) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseq) return;
+    const dvo_pair_info& I = info[s];
+    int signal = 0, why = 0;
+    if (pol.use_quality_gates) {                                                             // :2129-2151, in source order
+        if (I.laplacian_b > pol.laplacian_thresh) { signal = 1; why = 2; }
+        if (I.visible_ratio[finest] < pol.visible_ratio_thresh) { signal = 1; why = 3; }
+        if (I.npts[finest] < pol.min_reprojections) { signal = 1; why = 4; }
+    }
+    if (pol.keyframe_every > 0 && (t - lastRef[s]) == pol.keyframe_every) { signal = 1; why = 5; }   // :2155-2160
+    const long long cur = (long long)s * nframes + t;
+    if (signal && lastRef[s] != t - 1) {                                                     // :2192
+        mask[s] = 1; lastRef[s] = t - 1;
+        kind[cur - 1] = 2; reason[cur - 1] = why;                                            // gop.updateMostRecentToKeyFrame(reasonForChange)
+        for (int k = 0; k < 12; ++k) pose0[12 * (long long)s + k] = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0;   // cR_64 = I, cT_64 = 0 (:2203-2204)
+    } else {
+        mask[s] = 0;
+        for (int k = 0; k < 12; ++k) { const double v = pose[12 * (long long)s + k]; rel[12 * cur + k] = v; pose0[12 * (long long)s + k] = v; }
+        kind[cur] = 0; reason[cur] = 0;                                                      // gop.pushAsOrdinaryFrame (:2232)
+    }
+}
+__global__ void seq_finish_kernel(int nseq, int nframes, int t, const unsigned char* __restrict__ mask, const double* __restrict__ pose,
+                                  double* __restrict__ pose0, double* __restrict__ rel, int* __restrict__ kind, int* __restrict__ reason) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseq || !mask[s]) return;
+    const long long cur = (long long)s * nframes + t;
+    for (int k = 0; k < 12; ++k) { const double v = pose[12 * (long long)s + k]; rel[12 * cur + k] = v; pose0[12 * (long long)s + k] = v; }
+    kind[cur] = 0; reason[cur] = 0;                                                          // pushAsOrdinaryFrame after the re-run (:2224)
+}
+__global__ void seq_init_kernel(int nseq, int nframes, double* __restrict__ pose0, int* __restrict__ lastRef, double* __restrict__ rel,
+                                int* __restrict__ kind, int* __restrict__ reason) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nseq) return;
+    lastRef[s] = 0;
+    for (int k = 0; k < 12; ++k) { const double v = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0; pose0[12 * (long long)s + k] = v; rel[12 * (long long)s * nframes + k] = v; }
+    kind[(long long)s * nframes] = 1; reason[(long long)s * nframes] = 1;                    // gop.pushAsKeyFrame(nFrame, 1, I, 0) (:2016)
+}
+}  // namespace
+
+extern "C" {
+
+int dvo_run_sequences_gated(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* p,
+                            const dvo_keyframe_policy* pol, double* rel_poses, int* kind, int* reason, double* global_poses) {
+    if (!c || nseq < 1 || nseq > c->cfg.max_batch || nframes < 1 || !gray || !depth || !p || !pol || !rel_poses || !kind) { dvo_set_error("dvo_run_sequences_gated: bad argument"); return DVO_ERR_ARG; }
+    if (!c->prev_gray) { dvo_set_error("dvo_run_sequences_gated: create the context with keep_now_depth = 1"); return DVO_ERR_STATE; }
+    if (!c->haveK) { dvo_set_error("dvo_run_sequences_gated: intrinsics not set"); return DVO_ERR_STATE; }
+    int finest = -1;
+    for (int l = 0; l < c->geom.L; ++l) if (p->iters[l] > 0) { finest = l; break; }
+    if (finest < 0) { dvo_set_error("dvo_run_sequences_gated: no level has iterations"); return DVO_ERR_ARG; }
+    const size_t P0 = c->geom.P[0], n = (size_t)nseq * nframes;
+    double* d_rel = nullptr; int* d_kind = nullptr; int* d_reason = nullptr; double* d_glob = nullptr;
+    int rc = DVO_OK;
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DVO_OK) { dvo_set_error("dvo_run_sequences_gated: %s", cudaGetErrorString(e)); rc = DVO_ERR_CUDA; } return rc != DVO_OK; };
+    if (fail(cudaMalloc((void**)&d_rel, sizeof(double) * 12 * n)) || fail(cudaMalloc((void**)&d_kind, sizeof(int) * n)) || fail(cudaMalloc((void**)&d_reason, sizeof(int) * n))) {
+        cudaFree(d_rel); cudaFree(d_kind); cudaFree(d_reason); return rc;
+    }
+    fail(cudaMemsetAsync(d_rel, 0, sizeof(double) * 12 * n, c->stream));
+    fail(cudaMemsetAsync(d_kind, 0, sizeof(int) * n, c->stream));
+    fail(cudaMemsetAsync(d_reason, 0, sizeof(int) * n, c->stream));
+    auto upload = [&](int frame, int t) -> int {          // frame t of every sequence -> slots [0, nseq)
+        for (int s = 0; s < nseq; ++s) {
+            const size_t src = ((size_t)s * nframes + t) * P0;
+            int r = dvo_set_frames(c, frame, s, 1, gray + src, depth + src, DVO_MEM_HOST);
+            if (r) return r;
+        }
+        return DVO_OK;
+    };
+    const int blk = (nseq + 127) / 128;
+    for (int s = 0; s < nseq; ++s) { c->now_valid[s] = 0; c->prev_valid[s] = 0; }
+    if (rc == DVO_OK) rc = upload(DVO_FRAME_REF, 0);
+    if (rc == DVO_OK) rc = dvo_build_pyramids(c, 0, nseq, 1);
+    if (rc == DVO_OK) rc = dvo_prepare(c, 0, nseq, 1);
+    if (rc == DVO_OK) { seq_init_kernel<<<blk, 128, 0, c->stream>>>(nseq, nframes, c->pose0, c->seq_state, d_rel, d_kind, d_reason); c->launches++; fail(cudaGetLastError()); }
+    for (int t = 1; t < nframes && rc == DVO_OK; ++t) {
+        if ((rc = upload(DVO_FRAME_NOW, t))) break;                                          // setRcvdFrameAsNowFrame
+        if ((rc = dvo_build_pyramids(c, 0, nseq, 2))) break;
+        if ((rc = dvo_prepare(c, 0, nseq, 2))) break;
+        if ((rc = dvo_run(c, 0, nseq, p))) break;                                            // warm start: pose0 holds the previous frame's pose (:1931-1932)
+        seq_gate_kernel<<<blk, 128, 0, c->stream>>>(nseq, nframes, t, *pol, finest, c->info, c->pose, c->pose0, c->seq_state, c->seq_mask, d_rel, d_kind, d_reason);
+        c->launches++;
+        if (fail(cudaGetLastError())) break;
+        if (t >= 2) {                                                                        // a previous now frame exists from t = 2 on (lastRef != t-1 excludes t = 1)
+            c->active = c->seq_mask;                                                         // switch pass: only the flagged slots do any work
+            rc = dvo_promote_now_to_ref(c, 0, nseq);                                         // setPrevFrameAsRefFrame (:2196)
+            if (rc == DVO_OK) rc = dvo_build_pyramids(c, 0, nseq, 1);
+            if (rc == DVO_OK) rc = dvo_prepare(c, 0, nseq, 1);                               // computeDistTransfrmOfRef + preProcessRefFrame (:2197)
+            if (rc == DVO_OK) rc = dvo_run(c, 0, nseq, p);                                   // re-run from identity (:2213-2220)
+            c->active = nullptr;
+            if (rc != DVO_OK) break;
+            seq_finish_kernel<<<blk, 128, 0, c->stream>>>(nseq, nframes, t, c->seq_mask, c->pose, c->pose0, d_rel, d_kind, d_reason);
+            c->launches++;
+            if (fail(cudaGetLastError())) break;
+        }
+    }
+    c->active = nullptr;
+    if (rc == DVO_OK && global_poses) {
+        if (!fail(cudaMalloc((void**)&d_glob, sizeof(double) * 19 * n))) {
+            rc = launch_gop(c, nseq, nframes, d_kind, d_rel, d_glob);
+            if (rc == DVO_OK) fail(cudaMemcpyAsync(global_poses, d_glob, sizeof(double) * 19 * n, cudaMemcpyDeviceToHost, c->stream));
+        }
+    }
+    if (rc == DVO_OK) {
+        fail(cudaMemcpyAsync(rel_poses, d_rel, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, c->stream));
+        fail(cudaMemcpyAsync(kind, d_kind, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+        if (reason) fail(cudaMemcpyAsync(reason, d_reason, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+        fail(cudaStreamSynchronize(c->stream));
+    } else cudaStreamSynchronize(c->stream);
+    cudaFree(d_rel); cudaFree(d_kind); cudaFree(d_reason); cudaFree(d_glob);
+    return rc;
 }
 
 int dvo_level_dims(dvo_ctx* c, int level, int* w, int* h) {

@@ -50,6 +50,9 @@ struct dvo_ctx {
     int* ptsPix;                 // ref: pixel index y*w+x of every point (restores the reference's column-major order)
     int* npts;               // [Bmax][L]
     int* solve_order;        // [Bmax] pair slots of the current solve launch, heaviest first
+    unsigned char* seq_mask; // [Bmax] per-slot switch flags of the gated sequence loop (device)
+    const unsigned char* active;   // when non-null, kernels skip slots whose flag is 0 (masked key-frame switch pass)
+    int* seq_state;          // [Bmax] lastRefFrame per slot (device)
     unsigned* nedge;         // [2][Bmax][L]
     unsigned* maxd2;         // [Bmax][L]
     double* pose0;           // [Bmax][12]

@@ -15,10 +15,12 @@ struct PyrArgs {
     uint16_t* depth;   // may be null
     int first;
     int sub_total;     // sum_{l>=1} P[l]
+    const unsigned char* active;   // optional per-slot mask
 };
 
 __global__ void __launch_bounds__(256) pyramid_nearest_kernel(PyrArgs a) {
     const int b = a.first + blockIdx.y;
+    if (a.active && !a.active[b]) return;
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.sub_total) return;
     int l = 1;
@@ -38,7 +40,7 @@ int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
     for (int l = 1; l < c->geom.L; ++l) sub += c->geom.P[l];
     for (int f = 0; f < 2; ++f) {
         if (!(frames_mask & (1 << f))) continue;
-        PyrArgs a; a.g = c->geom; a.gray = c->gray[f]; a.depth = c->depth[f]; a.first = first; a.sub_total = sub;
+        PyrArgs a; a.g = c->geom; a.gray = c->gray[f]; a.depth = c->depth[f]; a.first = first; a.sub_total = sub; a.active = c->active;
         dim3 grid((sub + 255) / 256, count);
         pyramid_nearest_kernel<<<grid, 256, 0, c->stream>>>(a);
         c->launches++;
@@ -84,6 +86,7 @@ struct CannyArgs {
     int first;
     int low, high;         // squared thresholds (10000, 22500)
     int bm_words;          // words per bitmap region
+    const unsigned char* active;   // optional per-slot mask
 };
 
 __device__ __forceinline__ void sobel3(const uint8_t* __restrict__ g, int w, int h, int y, int x, int& dx, int& dy) {
@@ -124,6 +127,7 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     const int T = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = a.first + blockIdx.x;
+    if (a.active && !a.active[b]) return;
     const int w = a.w, h = a.h;
     const int wd = (w + 31) >> 5, pitch = wd + 2;
     const int nwords = a.bm_words;
@@ -458,7 +462,7 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
             a.tmpcx = scaleFac * c->K.cx; a.tmpcy = scaleFac * c->K.cy;                    // :234-235
             a.gscratch = use_global ? c->bitmap_scratch : nullptr;
             a.gscratch_stride = (long long)c->bitmap_scratch_words;
-            a.first = first; a.low = 10000; a.high = 22500; a.bm_words = words;
+            a.first = first; a.low = 10000; a.high = 22500; a.bm_words = words; a.active = c->active;
             const size_t dyn = use_global ? 0 : smem;
             if (use_global) canny_kernel<true><<<count, T, 0, c->stream>>>(a);
             else {
@@ -719,12 +723,30 @@ int launch_normgrad(dvo_ctx* c, int first, int count) {
 // frame's level-0 images (saved by dvo_set_frames) become the reference frame's level 0; the caller rebuilds the
 // reference pyramid, edges and point list exactly as the reference does (computeDistTransfrmOfRef, preProcessRefFrame).
 // =====================================================================================================
+__global__ void __launch_bounds__(256) promote_masked_kernel(PyrGeom g, const uint8_t* __restrict__ prev_gray, const uint16_t* __restrict__ prev_depth,
+                                                             uint8_t* __restrict__ gray, uint16_t* __restrict__ depth, int first,
+                                                             const unsigned char* __restrict__ active) {
+    const int b = first + blockIdx.y;
+    if (!active[b]) return;
+    const int P0 = g.P[0];
+    const int q = (blockIdx.x * blockDim.x + threadIdx.x) * 4;          // P0 is a multiple of 4 for every supported size? no: tail handled below
+    const long long src = (long long)P0 * b, dst = lvl_at(g, 0, b);
+    for (int k = q; k < min(q + 4, P0); ++k) { gray[dst + k] = prev_gray[src + k]; depth[dst + k] = prev_depth[src + k]; }
+}
+
 int launch_promote(dvo_ctx* c, int first, int count) {
     const PyrGeom& g = c->geom;
     if (!c->prev_gray) { dvo_set_error("promote: context was created without keep_now_depth"); return DVO_ERR_STATE; }
     for (int i = first; i < first + count; ++i)
         if (!c->prev_valid[i]) { dvo_set_error("promote: slot %d has no previous now frame (isPrevFrameAvailable)", i); return DVO_ERR_STATE; }
     const size_t P0 = g.P[0];
+    if (c->active) {
+        dim3 grid((unsigned)((P0 + 1023) / 1024), (unsigned)count);
+        promote_masked_kernel<<<grid, 256, 0, c->stream>>>(g, c->prev_gray, c->prev_depth, c->gray[0], c->depth[0], first, c->active);
+        c->launches++;
+        DVO_CUDA(cudaGetLastError());
+        return DVO_OK;
+    }
     DVO_CUDA(cudaMemcpyAsync(c->gray[0] + lvl_at(g, 0, first), c->prev_gray + P0 * first, P0 * count, cudaMemcpyDeviceToDevice, c->stream));
     DVO_CUDA(cudaMemcpyAsync(c->depth[0] + lvl_at(g, 0, first), c->prev_depth + P0 * first, P0 * count * 2, cudaMemcpyDeviceToDevice, c->stream));
     return DVO_OK;

@@ -384,7 +384,7 @@ struct SolverState {
 struct SolveArgs {
     PyrGeom geom; Intr K;
     const float *X, *Y, *Z; const int* npts; const unsigned* nedge_now; const float4* texel;
-    const double* pose0; double* pose; dvo_pair_info* info; double* trace; int trace_iters; const int* order;
+    const double* pose0; double* pose; dvo_pair_info* info; double* trace; int trace_iters; const int* order; const unsigned char* active;
     dvo_solver_params prm; int first;
 };
 
@@ -509,6 +509,7 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
     __shared__ dvo_pair_info s_info;
 
     const int b = a.order[blockIdx.x];
+    if (a.active && !a.active[b]) return;                 // masked pass (gated key-frame switch): pose / info of the slot stay as they are
     const int L = a.geom.L;
     const bool lead = (threadIdx.x == 0);
     if (lead) {
@@ -674,7 +675,7 @@ int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
     if (c->trace) DVO_CUDA(cudaMemsetAsync(c->trace + (size_t)first * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, 0,
                                            sizeof(double) * (size_t)count * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, c->stream));
     solve_order_kernel<<<1, 1024, 0, c->stream>>>(c->npts, c->geom.L, *p, first, count, c->solve_order);
-    a.order = c->solve_order;
+    a.order = c->solve_order; a.active = c->active;
     DVO_CUDA(launch_solve_any(c, a, count, need_h));
     c->launches++;
     c->launches++;

@@ -298,7 +298,7 @@ def run_iterations(X, Y, Z, dtn, gx, gy, level, max_iter, R0=None, T0=None, K=K6
 
 
 def align_pair(ref_gray, ref_depth, now_gray, levels=4, iters=(50, 50, 50, 50), K=K640, scfg=None, R0=None, T0=None,
-               trace=False):
+               trace=False, stats=False):
     H, W = ref_gray.shape
     scfg = scfg or cfg()
     it = np.array(iters, np.int32)
@@ -309,13 +309,17 @@ def align_pair(ref_gray, ref_depth, now_gray, levels=4, iters=(50, 50, 50, 50), 
     tr = np.zeros((levels, mi, 56), np.float64) if trace else None
     R0p = None if R0 is None else np.ascontiguousarray(R0, np.float64).reshape(9)
     T0p = None if T0 is None else np.ascontiguousarray(T0, np.float64).reshape(3)
+    bcap = C.c_float()
     st = lib().orc_align_pair(_p(np.ascontiguousarray(ref_gray), C.c_uint8), _p(np.ascontiguousarray(ref_depth), C.c_uint16),
                               _p(np.ascontiguousarray(now_gray), C.c_uint8), W, H, levels, C.c_float(K[0]), C.c_float(K[1]),
                               C.c_float(K[2]), C.c_float(K[3]), _p(it, C.c_int32), C.byref(scfg), _p(R0p, C.c_double),
                               _p(T0p, C.c_double), _p(R, C.c_double), _p(T, C.c_double), _p(npts, C.c_int32), _p(bi, C.c_int32),
-                              _p(ir, C.c_int32), _p(be, C.c_float), _p(vr, C.c_float), _p(tr, C.c_double), mi)
+                              _p(ir, C.c_int32), _p(be, C.c_float), _p(vr, C.c_float), _p(tr, C.c_double), mi,
+                              C.byref(bcap) if stats else None)
     out = {"R": R.reshape(3, 3), "T": T, "npts": npts, "best_index": bi, "iterations_run": ir, "best_energy": be,
            "visible_ratio": vr, "status": st}
+    if stats:
+        out["b_cap"] = bcap.value
     if trace:
         out["trace"] = parse_trace(tr)
     return out

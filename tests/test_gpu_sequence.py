@@ -63,3 +63,63 @@ def test_promote_requires_a_previous_now_frame():
     with pytest.raises(dvo.DvoError, match="keep_now_depth"):
         al2.promote_now_to_ref(1)
     al.close(); al2.close()
+
+
+def oracle_sequence_gated(gray, depth, levels, iters, K, every, gates, b_thr, vis_thr, min_reproj):
+    """SolveDVO::loop with the key-frame policy of src/SolveDVO.cpp:2117-2233 (quality gates as designed, OR periodic)."""
+    n = gray.shape[0]
+    rel = np.zeros((n, 12)); kind = np.zeros(n, np.int32); reason = np.zeros(n, np.int32)
+    rel[0, [0, 4, 8]] = 1.0; kind[0] = 1; reason[0] = 1
+    ref = 0; last_ref = 0
+    finest = [l for l in range(levels) if iters[l] > 0][0]
+    R, T = np.eye(3), np.zeros(3)
+    stats = []
+    for t in range(1, n):
+        o = O.align_pair(gray[ref], depth[ref], gray[t], levels, iters, K, R0=R, T0=T, stats=True)
+        stats.append((o["b_cap"], float(o["visible_ratio"][finest]), int(o["npts"][finest])))
+        signal, why = False, 0
+        if gates:
+            if o["b_cap"] > b_thr: signal, why = True, 2
+            if o["visible_ratio"][finest] < vis_thr: signal, why = True, 3
+            if o["npts"][finest] < min_reproj: signal, why = True, 4
+        if every > 0 and (t - last_ref) == every: signal, why = True, 5
+        if signal and last_ref != t - 1:
+            last_ref = t - 1; ref = t - 1; kind[t - 1] = 2; reason[t - 1] = why
+            o = O.align_pair(gray[ref], depth[ref], gray[t], levels, iters, K, R0=np.eye(3), T0=np.zeros(3))
+        R, T = o["R"], o["T"]
+        rel[t, :9] = R.reshape(9); rel[t, 9:] = T
+    glob, _, _ = O.gop_replay(kind, np.maximum(reason, 1), rel)
+    return rel, kind, reason, glob, stats
+
+
+def test_gated_keyframe_policy_on_device():
+    """dvo_run_sequences_gated: (a) with the shipped policy it reproduces dvo_run_sequences; (b) with the quality gates
+    enabled every sequence switches key frames where ITS OWN residual statistic / visible ratio says so, matching the
+    oracle-driven loop frame by frame (switch frames, reasons, relative and global poses)."""
+    W, H, L, K = 320, 240, 4, (262.5, 262.5, 159.5, 119.5)
+    nseq, nframes = 3, 10
+    seqs = [O.synth_sequence(70 + s, nframes, W, H, K, max_angle_deg=0.4, max_trans_m=0.008) for s in range(nseq)]
+    gray = np.stack([s[0] for s in seqs]); depth = np.stack([s[1] for s in seqs])
+    iters = (8, 8, 8, 8)
+    prm = dvo.solver_params(iters=iters)
+    al = dvo.BatchAligner(W, H, L, max_batch=nseq, keep_now_depth=True, intrinsics=K)
+    rel0, kind0, glob0 = al.run_sequences(gray, depth, prm)
+    rel1, kind1, reason1, glob1 = al.run_sequences_gated(gray, depth, prm, dvo.keyframe_policy())
+    assert np.array_equal(kind0, kind1) and np.array_equal(rel0, rel1) and np.array_equal(glob0, glob1)
+    assert sorted(set(reason1[kind1 == 2].tolist())) == [5] and (reason1[:, 0] == 1).all()
+    b_thr, vis_thr = 9.5, 0.95
+    pol = dvo.keyframe_policy(keyframe_every=0, use_quality_gates=True, laplacian_thresh=b_thr, visible_ratio_thresh=vis_thr)
+    rel, kind, reason, glob = al.run_sequences_gated(gray, depth, prm, pol)
+    switches = []
+    for s in range(nseq):
+        orel, okind, oreason, oglob, stats = oracle_sequence_gated(gray[s], depth[s], L, iters, K, 0, True, b_thr, vis_thr, 50)
+        # the thresholds sit well away from every statistic the decision saw, so fp32-vs-fp64 means cannot flip a gate
+        assert min(abs(b - b_thr) for b, _, _ in stats) > 1e-3 and min(abs(v - vis_thr) for _, v, _ in stats) > 1e-4
+        assert np.array_equal(kind[s], okind), (s, kind[s], okind)
+        assert np.array_equal(reason[s], oreason), (s, reason[s], oreason)
+        for t in range(nframes):
+            assert rot_angle(rel[s, t, :9].reshape(3, 3), orel[t, :9].reshape(3, 3)) < 1e-5 and np.linalg.norm(rel[s, t, 9:] - orel[t, 9:]) < 1e-5
+            assert rot_angle(glob[s, t, :9].reshape(3, 3), oglob[t, :9].reshape(3, 3)) < 1e-5 and np.linalg.norm(glob[s, t, 9:12] - oglob[t, 9:12]) < 1e-5
+        switches.append(tuple(np.nonzero(okind == 2)[0]))
+    assert any(len(sw) for sw in switches) and len(set(switches)) > 1, switches      # the sequences really diverged
+    al.close()
