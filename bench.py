@@ -155,6 +155,7 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None      # host buffers of the e2e leg next to this rank's GPU
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     iters, code, ocfg = solver_setup(args)
@@ -284,12 +285,40 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64",
                 "data": "synthetic", "config": config_dict(args, iters), "clocks": sampler.summary(), "gpu_launches": int(launches),
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "synth_seconds": t_synth,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "numa": numa, "synth_seconds": t_synth,
                 "status_nonzero_pairs": int(sum(1 for inf in info if inf.status != 0))}
         print(json.dumps(line))
     al.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's threads (and so the first touch of its pinned host buffers) to the NUMA node its GPU hangs off:
+    with 8 ranks uploading 1.26 GB per step each, buffers on the far socket halve the aggregate H2D rate.  Best effort:
+    returns None when the topology is not visible (containers without /sys NUMA info)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bdf = bus.lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return {"node": node, "cpus": len(cpus)}
+    except Exception:
+        return None
 
 
 def main():
