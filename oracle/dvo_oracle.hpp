@@ -917,7 +917,7 @@ inline void estimate(const RefLevel& L, const uint8_t* now_gray, Cam K, const do
     for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) Tr[4 * i + j] = R0[3 * i + j]; Tr[4 * i + 3] = T0[i]; }
     Tr[15] = 1.0;
     out.status = 0; out.iters_run = 0; out.sumsq_first = out.sumsq_last = 0; out.visible = 0;
-    double lambda = lambda0, accTr[16], accA[36], accb[6], accE = 0; bool have = false;
+    double lambda = lambda0, accTr[16] = {0}, accA[36] = {0}, accb[6] = {0}, accE = 0; bool have = false;
     for (int itr = 0; itr < iters; ++itr) {
         IterOut ev; evaluate(L, now_gray, K, Tr, compat, huber_k, ev);
         out.visible = (double)ev.nreproj / ((double)L.rows * L.cols);
