@@ -14,7 +14,8 @@ struct PyrArgs {
     uint8_t* gray;
     uint16_t* depth;   // may be null
     int first;
-    int sub_total;     // sum_{l>=1} P[l]
+    int sub_total;     // sum_{l>=l0} P[l]
+    int l0;            // first level this launch produces
     const unsigned char* active;   // optional per-slot mask
 };
 
@@ -23,7 +24,7 @@ __global__ void __launch_bounds__(256) pyramid_nearest_kernel(PyrArgs a) {
     if (a.active && !a.active[b]) return;
     int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= a.sub_total) return;
-    int l = 1;
+    int l = a.l0;
     while (l < a.g.L - 1 && q >= a.g.P[l]) { q -= a.g.P[l]; ++l; }
     const int w = a.g.w[l], W0 = a.g.w[0], H0 = a.g.h[0];
     const int y = q / w, x = q - y * w;
@@ -34,16 +35,50 @@ __global__ void __launch_bounds__(256) pyramid_nearest_kernel(PyrArgs a) {
     if (a.depth) { uint16_t d = a.depth[src]; a.depth[dst] = d == 0 ? (uint16_t)1 : d; }
 }
 
+// Level 1 holds three quarters of the pyramid's pixels below level 0.  When the widths allow it (W0 = 2 w1, w1 % 4 == 0)
+// a thread produces four consecutive level-1 pixels from one 8-byte gray load and one 16-byte depth load and writes
+// them with one 4-byte / one 8-byte store, instead of four byte-wide round trips.
+__global__ void __launch_bounds__(256) pyramid_level1_vec4_kernel(PyrArgs a) {
+    const int b = a.first + blockIdx.y;
+    if (a.active && !a.active[b]) return;
+    const int w1 = a.g.w[1], W0 = a.g.w[0], H0 = a.g.h[0];
+    const int q4 = blockIdx.x * blockDim.x + threadIdx.x;          // group of 4 output pixels
+    if (q4 * 4 >= a.g.P[1]) return;
+    const int y = (q4 * 4) / w1, x = q4 * 4 - y * w1;
+    const int sy = min(2 * y, H0 - 1);
+    const long long src = lvl_at(a.g, 0, b) + (long long)sy * W0 + 2 * x;
+    const long long dst = lvl_at(a.g, 1, b) + (long long)q4 * 4;
+    const uint2 gv = *reinterpret_cast<const uint2*>(a.gray + src);
+    const uint32_t gout = (gv.x & 0xFFu) | ((gv.x >> 8) & 0xFF00u) | ((gv.y & 0xFFu) << 16) | ((gv.y << 8) & 0xFF000000u);   // bytes 0, 2, 4, 6
+    *reinterpret_cast<uint32_t*>(a.gray + dst) = gout;
+    if (a.depth) {
+        const uint4 dv = *reinterpret_cast<const uint4*>(a.depth + src);
+        uint32_t d0 = dv.x & 0xFFFFu, d1 = dv.y & 0xFFFFu, d2 = dv.z & 0xFFFFu, d3 = dv.w & 0xFFFFu;                        // elements 0, 2, 4, 6
+        d0 = d0 ? d0 : 1u; d1 = d1 ? d1 : 1u; d2 = d2 ? d2 : 1u; d3 = d3 ? d3 : 1u;
+        *reinterpret_cast<uint2*>(a.depth + dst) = make_uint2(d0 | (d1 << 16), d2 | (d3 << 16));
+    }
+}
+
 int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
-    if (c->geom.L < 2) return DVO_OK;
+    const PyrGeom& g = c->geom;
+    if (g.L < 2) return DVO_OK;
+    const bool vec1 = (g.w[0] == 2 * g.w[1]) && (g.w[1] % 4 == 0);
+    const int l0 = vec1 ? 2 : 1;
     int sub = 0;
-    for (int l = 1; l < c->geom.L; ++l) sub += c->geom.P[l];
+    for (int l = l0; l < g.L; ++l) sub += g.P[l];
     for (int f = 0; f < 2; ++f) {
         if (!(frames_mask & (1 << f))) continue;
-        PyrArgs a; a.g = c->geom; a.gray = c->gray[f]; a.depth = c->depth[f]; a.first = first; a.sub_total = sub; a.active = c->active;
-        dim3 grid((sub + 255) / 256, count);
-        pyramid_nearest_kernel<<<grid, 256, 0, c->stream>>>(a);
-        c->launches++;
+        PyrArgs a; a.g = g; a.gray = c->gray[f]; a.depth = c->depth[f]; a.first = first; a.sub_total = sub; a.l0 = l0; a.active = c->active;
+        if (vec1) {
+            dim3 grid1((g.P[1] / 4 + 255) / 256, count);
+            pyramid_level1_vec4_kernel<<<grid1, 256, 0, c->stream>>>(a);
+            c->launches++;
+        }
+        if (sub > 0) {
+            dim3 grid((sub + 255) / 256, count);
+            pyramid_nearest_kernel<<<grid, 256, 0, c->stream>>>(a);
+            c->launches++;
+        }
     }
     DVO_CUDA(cudaGetLastError());
     return DVO_OK;
