@@ -142,6 +142,19 @@ int dvo_get_poses(dvo_ctx* ctx, int first, int count, double* R9T3, dvo_pair_inf
 /* One call for a whole batch with host buffers: upload, pyramids, prepare, run, download (the end-to-end path
  * SolveDVO::loop executes per frame, src/SolveDVO.cpp:2017-2104).  count may exceed max_batch; the batch is
  * processed in chunks.  now_depth may be NULL. */
+/* Whole hot path on frames ALREADY RESIDENT in slots [first, first+count): dvo_build_pyramids(3) + dvo_prepare(3) +
+ * dvo_run.  Large ranges are processed as two half batches on two internal streams, staggered so that one half's
+ * solve (DRAM-transaction bound, a third of the issue slots used) overlaps the other half's Canny / EDT (issue bound);
+ * across back-to-back calls the second half's solve overlaps the next call's first preprocessing.  The call returns
+ * without joining: every other entry point joins first, dvo_join does it explicitly (device-side wait, no host block).
+ * Results are bit-identical to the staged calls.
+ * d_poses (optional, DEVICE memory, count x 12 doubles): every half copies its poses there on its own stream, so a
+ * caller that only needs the poses on the device never has to join between back-to-back calls. */
+int dvo_process(dvo_ctx* ctx, int first, int count, const dvo_solver_params* params, double* d_poses);
+int dvo_join(dvo_ctx* ctx);
+/* make another CUDA stream (e.g. the one a collective runs on) wait for the work dvo_process left in flight */
+int dvo_join_stream(dvo_ctx* ctx, void* cuda_stream);
+
 int dvo_align_batch(dvo_ctx* ctx, int count, const uint8_t* ref_gray, const uint16_t* ref_depth,
                     const uint8_t* now_gray, const uint16_t* now_depth, const dvo_solver_params* params,
                     double* R9T3, dvo_pair_info* info);

@@ -60,7 +60,7 @@ class RgbdInfo(C.Structure):
 SYMBOLS = [
     "dvo_last_error", "dvo_device_count", "dvo_create", "dvo_destroy", "dvo_set_stream", "dvo_synchronize",
     "dvo_set_intrinsics", "dvo_set_frames", "dvo_promote_now_to_ref", "dvo_build_pyramids", "dvo_prepare",
-    "dvo_set_initial_pose", "dvo_run", "dvo_get_poses", "dvo_align_batch", "dvo_level_dims", "dvo_get_level_buffer",
+    "dvo_set_initial_pose", "dvo_run", "dvo_process", "dvo_join", "dvo_join_stream", "dvo_get_poses", "dvo_align_batch", "dvo_level_dims", "dvo_get_level_buffer",
     "dvo_get_points", "dvo_eval_normal_equations", "dvo_eval_normal_equations_ex", "dvo_get_trace", "dvo_enable_timing", "dvo_get_stage_ms",
     "dvo_launch_count", "dvo_gop_compose", "dvo_run_sequences", "dvo_run_sequences_gated",
     "dvo_photo_create", "dvo_photo_destroy", "dvo_photo_set_stream", "dvo_photo_synchronize", "dvo_photo_launch_count",
@@ -99,6 +99,9 @@ def load(build_if_missing=True):
     lib.dvo_prepare.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.dvo_set_initial_pose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.dvo_run.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SolverParams)]
+    lib.dvo_process.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(SolverParams), C.c_void_p]
+    lib.dvo_join.argtypes = [C.c_void_p]
+    lib.dvo_join_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.dvo_get_poses.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     lib.dvo_align_batch.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(SolverParams), C.c_void_p, C.c_void_p]

@@ -99,6 +99,17 @@ class BatchAligner:
     def run(self, count, params, first=0):
         check(self.lib.dvo_run(self.h, first, count, C.byref(params)), "dvo_run")
 
+    def process(self, count, params, first=0, poses_out=None):
+        """build_pyramids + prepare + run on resident frames; large ranges run as two staggered half batches (dvo_process).
+        poses_out: optional raw device pointer (count x 12 doubles) the poses are copied to without joining."""
+        check(self.lib.dvo_process(self.h, first, count, C.byref(params), C.c_void_p(poses_out) if poses_out else None), "dvo_process")
+
+    def join(self):
+        check(self.lib.dvo_join(self.h), "dvo_join")
+
+    def join_stream(self, stream_ptr):
+        check(self.lib.dvo_join_stream(self.h, C.c_void_p(stream_ptr)), "dvo_join_stream")
+
     def get_poses(self, count, first=0, want_info=True):
         poses = np.empty((count, 12), np.float64)
         info = (PairInfo * count)() if want_info else None

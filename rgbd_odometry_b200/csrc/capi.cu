@@ -37,6 +37,13 @@ template <typename T> int dalloc(T** p, size_t n) {
     return DVO_OK;
 }
 bool range_ok(dvo_ctx* c, int first, int count) { return c && first >= 0 && count >= 0 && first + count <= c->cfg.max_batch; }
+// make the context stream wait for whatever dvo_process left running on the internal streams
+int join_aux(dvo_ctx* c) {
+    if (!c || !c->aux_pending) return DVO_OK;
+    c->aux_pending = false;
+    for (int k = 0; k < 2; ++k) DVO_CUDA(cudaStreamWaitEvent(c->stream, c->ev_aux_done[k], 0));
+    return DVO_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -89,6 +96,12 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     DVO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) DVO_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
     DVO_CUDA(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) {
+        DVO_CUDA(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
+        DVO_CUDA(cudaEventCreateWithFlags(&c->ev_pre[k], cudaEventDisableTiming));
+        DVO_CUDA(cudaEventCreateWithFlags(&c->ev_aux_done[k], cudaEventDisableTiming));
+    }
+    DVO_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     c->e2e_chunk = 256;
     if (const char* e = getenv("DVO_E2E_CHUNK")) { const int v = atoi(e); if (v > 0) c->e2e_chunk = v; }
     DVO_CUDA(cudaEventCreate(&c->ev_a));
@@ -140,6 +153,12 @@ int dvo_destroy(dvo_ctx* c) {
     if (c->ev_a) cudaEventDestroy(c->ev_a);
     if (c->ev_b) cudaEventDestroy(c->ev_b);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    for (int k = 0; k < 2; ++k) {
+        if (c->aux[k]) { cudaStreamSynchronize(c->aux[k]); cudaStreamDestroy(c->aux[k]); }
+        if (c->ev_pre[k]) cudaEventDestroy(c->ev_pre[k]);
+        if (c->ev_aux_done[k]) cudaEventDestroy(c->ev_aux_done[k]);
+    }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     for (int i = 0; i < 16; ++i) if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
     if (c->ev_entry) cudaEventDestroy(c->ev_entry);
@@ -149,12 +168,14 @@ int dvo_destroy(dvo_ctx* c) {
 
 int dvo_set_stream(dvo_ctx* c, void* s) {
     if (!c) return DVO_ERR_ARG;
+    { int rc = join_aux(c); if (rc) return rc; }
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return DVO_OK;
 }
 
 int dvo_synchronize(dvo_ctx* c) {
     if (!c) return DVO_ERR_ARG;
+    { int rc = join_aux(c); if (rc) return rc; }
     DVO_CUDA(cudaStreamSynchronize(c->stream));
     return DVO_OK;
 }
@@ -166,6 +187,7 @@ int dvo_set_intrinsics(dvo_ctx* c, float fx, float fy, float cx, float cy) {
 }
 
 int dvo_set_frames(dvo_ctx* c, int frame, int first, int count, const uint8_t* gray, const uint16_t* depth, int mem) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, first, count) || (frame != DVO_FRAME_REF && frame != DVO_FRAME_NOW) || !gray) { dvo_set_error("dvo_set_frames: bad argument"); return DVO_ERR_ARG; }
     if (frame == DVO_FRAME_REF && !depth) { dvo_set_error("dvo_set_frames: the reference frame needs depth"); return DVO_ERR_ARG; }
     StageTimer t(c, DVO_STAGE_H2D);
@@ -191,11 +213,13 @@ int dvo_set_frames(dvo_ctx* c, int frame, int first, int count, const uint8_t* g
 }
 
 int dvo_promote_now_to_ref(dvo_ctx* c, int first, int count) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, first, count)) return DVO_ERR_ARG;
     return launch_promote(c, first, count);
 }
 
 int dvo_build_pyramids(dvo_ctx* c, int first, int count, int frames_mask) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, first, count)) { dvo_set_error("dvo_build_pyramids: bad range"); return DVO_ERR_ARG; }
     if (count == 0) return DVO_OK;
     StageTimer t(c, DVO_STAGE_PYRAMID);
@@ -203,6 +227,7 @@ int dvo_build_pyramids(dvo_ctx* c, int first, int count, int frames_mask) {
 }
 
 int dvo_prepare(dvo_ctx* c, int first, int count, int frames_mask) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, first, count)) { dvo_set_error("dvo_prepare: bad range"); return DVO_ERR_ARG; }
     if (!c->haveK) { dvo_set_error("dvo_prepare: intrinsics not set (SolveDVO asserts isCameraIntrinsicsAvailable)"); return DVO_ERR_STATE; }
     if (count == 0) return DVO_OK;
@@ -216,6 +241,7 @@ int dvo_prepare(dvo_ctx* c, int first, int count, int frames_mask) {
 }
 
 int dvo_set_initial_pose(dvo_ctx* c, int first, int count, const double* R9T3, int mem) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, first, count)) return DVO_ERR_ARG;
     if (R9T3) {
         DVO_CUDA(cudaMemcpyAsync(c->pose0 + 12 * (size_t)first, R9T3, sizeof(double) * 12 * count,
@@ -231,6 +257,7 @@ int dvo_set_initial_pose(dvo_ctx* c, int first, int count, const double* R9T3, i
 }
 
 int dvo_run(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, first, count) || !p) { dvo_set_error("dvo_run: bad argument"); return DVO_ERR_ARG; }
     if (!c->haveK) { dvo_set_error("dvo_run: intrinsics not set"); return DVO_ERR_STATE; }
     if (count == 0) return DVO_OK;
@@ -238,7 +265,68 @@ int dvo_run(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
     return launch_solve(c, first, count, p);
 }
 
+// pyramids + Canny / EDT / normalise + solve of one slot range on the CURRENT c->stream, no stage timers, no join
+static int process_range(dvo_ctx* c, int first, int count, const dvo_solver_params* p, cudaEvent_t pre_done) {
+    int rc;
+    if ((rc = launch_pyramid(c, first, count, 3))) return rc;
+    if ((rc = launch_canny(c, first, count, 3))) return rc;
+    if ((rc = launch_edt_rows(c, first, count))) return rc;
+    if ((rc = launch_normgrad(c, first, count))) return rc;
+    if (pre_done) DVO_CUDA(cudaEventRecord(pre_done, c->stream));
+    return launch_solve(c, first, count, p);
+}
+
+int dvo_process(dvo_ctx* c, int first, int count, const dvo_solver_params* p, double* d_poses) {
+    if (!range_ok(c, first, count) || !p) { dvo_set_error("dvo_process: bad argument"); return DVO_ERR_ARG; }
+    if (!c->haveK) { dvo_set_error("dvo_process: intrinsics not set"); return DVO_ERR_STATE; }
+    if (count == 0) return DVO_OK;
+    // Per-stage timers synchronise, and a half batch must still fill the chip for the overlap to pay: otherwise run staged.
+    if (c->timing || count < 4 * c->sm_count) {
+        int rc = join_aux(c); if (rc) return rc;
+        if ((rc = dvo_build_pyramids(c, first, count, 3))) return rc;
+        if ((rc = dvo_prepare(c, first, count, 3))) return rc;
+        if ((rc = dvo_run(c, first, count, p))) return rc;
+        if (d_poses) DVO_CUDA(cudaMemcpyAsync(d_poses, c->pose + 12 * (size_t)first, sizeof(double) * 12 * count, cudaMemcpyDeviceToDevice, c->stream));
+        return DVO_OK;
+    }
+    // Fork: both internal streams start after everything issued on the context stream so far.  Half 1's preprocessing
+    // additionally waits for half 0's, so it runs beside half 0's solve; each internal stream is in order with its own
+    // work of the previous call, which is all the dependency there is (the halves own disjoint slots).
+    DVO_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    const cudaStream_t user = c->stream;
+    const int n0 = count / 2;
+    const int starts[2] = {first, first + n0}, counts[2] = {n0, count - n0};
+    int rc = DVO_OK;
+    for (int k = 0; k < 2 && rc == DVO_OK; ++k) {
+        cudaError_t e = cudaStreamWaitEvent(c->aux[k], c->ev_fork, 0);
+        if (e == cudaSuccess && k == 1) e = cudaStreamWaitEvent(c->aux[1], c->ev_pre[0], 0);
+        if (e != cudaSuccess) { dvo_set_error("dvo_process: %s", cudaGetErrorString(e)); rc = DVO_ERR_CUDA; break; }
+        c->stream = c->aux[k];
+        rc = process_range(c, starts[k], counts[k], p, c->ev_pre[k]);
+        if (rc == DVO_OK && d_poses && cudaMemcpyAsync(d_poses + 12 * (size_t)(starts[k] - first), c->pose + 12 * (size_t)starts[k], sizeof(double) * 12 * counts[k],
+                                                       cudaMemcpyDeviceToDevice, c->aux[k]) != cudaSuccess) rc = DVO_ERR_CUDA;
+        if (rc == DVO_OK && cudaEventRecord(c->ev_aux_done[k], c->aux[k]) != cudaSuccess) rc = DVO_ERR_CUDA;
+    }
+    c->stream = user;
+    c->aux_pending = true;
+    if (rc != DVO_OK) join_aux(c);
+    return rc;
+}
+
+int dvo_join(dvo_ctx* c) {
+    if (!c) return DVO_ERR_ARG;
+    return join_aux(c);
+}
+
+int dvo_join_stream(dvo_ctx* c, void* s) {
+    if (!c) return DVO_ERR_ARG;
+    if (!c->aux_pending) return DVO_OK;
+    for (int k = 0; k < 2; ++k) DVO_CUDA(cudaStreamWaitEvent((cudaStream_t)s, c->ev_aux_done[k], 0));
+    return DVO_OK;
+}
+
 int dvo_get_poses(dvo_ctx* c, int first, int count, double* R9T3, dvo_pair_info* info, int mem) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, first, count)) return DVO_ERR_ARG;
     StageTimer t(c, DVO_STAGE_D2H);
     const cudaMemcpyKind k = mem == DVO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
@@ -250,6 +338,7 @@ int dvo_get_poses(dvo_ctx* c, int first, int count, double* R9T3, dvo_pair_info*
 
 int dvo_align_batch(dvo_ctx* c, int count, const uint8_t* ref_gray, const uint16_t* ref_depth, const uint8_t* now_gray,
                     const uint16_t* now_depth, const dvo_solver_params* p, double* R9T3, dvo_pair_info* info) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!c || count < 0 || !ref_gray || !ref_depth || !now_gray || !p) { dvo_set_error("dvo_align_batch: bad argument"); return DVO_ERR_ARG; }
     if (!c->haveK) { dvo_set_error("dvo_align_batch: intrinsics not set"); return DVO_ERR_STATE; }
     const size_t P0 = c->geom.P[0];
@@ -299,6 +388,7 @@ int dvo_align_batch(dvo_ctx* c, int count, const uint8_t* ref_gray, const uint16
 // reference performs against the outgoing key frame right before a switch is discarded there (:2210-2227) and is skipped.
 int dvo_run_sequences(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* p,
                       int keyframe_every, double* rel_poses, int* kind, double* global_poses) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!c || nseq < 1 || nseq > c->cfg.max_batch || nframes < 1 || !gray || !depth || !p || !rel_poses || !kind) { dvo_set_error("dvo_run_sequences: bad argument"); return DVO_ERR_ARG; }
     if (!c->prev_gray) { dvo_set_error("dvo_run_sequences: create the context with keep_now_depth = 1"); return DVO_ERR_STATE; }
     if (!c->haveK) { dvo_set_error("dvo_run_sequences: intrinsics not set"); return DVO_ERR_STATE; }
@@ -393,6 +483,7 @@ extern "C" {
 
 int dvo_run_sequences_gated(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* p,
                             const dvo_keyframe_policy* pol, double* rel_poses, int* kind, int* reason, double* global_poses) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!c || nseq < 1 || nseq > c->cfg.max_batch || nframes < 1 || !gray || !depth || !p || !pol || !rel_poses || !kind) { dvo_set_error("dvo_run_sequences_gated: bad argument"); return DVO_ERR_ARG; }
     if (!c->prev_gray) { dvo_set_error("dvo_run_sequences_gated: create the context with keep_now_depth = 1"); return DVO_ERR_STATE; }
     if (!c->haveK) { dvo_set_error("dvo_run_sequences_gated: intrinsics not set"); return DVO_ERR_STATE; }
@@ -469,6 +560,7 @@ int dvo_level_dims(dvo_ctx* c, int level, int* w, int* h) {
 }
 
 int dvo_get_level_buffer(dvo_ctx* c, int slot, int frame, int level, int which, void* dst, size_t bytes) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || (frame != 0 && frame != 1) || !dst) { dvo_set_error("dvo_get_level_buffer: bad argument"); return DVO_ERR_ARG; }
     const size_t P = c->geom.P[level];
     const long long o = lvl_at(c->geom, level, slot);
@@ -519,6 +611,7 @@ static int reference_order(dvo_ctx* c, int slot, int level, int n, std::vector<i
 }
 
 int dvo_get_points(dvo_ctx* c, int slot, int level, float* X, float* Y, float* Z, int capacity, int* n) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !n) return DVO_ERR_ARG;
     int cnt = 0;
     DVO_CUDA(cudaMemcpyAsync(&cnt, c->npts + (size_t)slot * c->geom.L + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -552,6 +645,7 @@ int dvo_eval_normal_equations(dvo_ctx* c, int slot, int level, const double* R9T
 
 int dvo_eval_normal_equations_ex(dvo_ctx* c, int slot, int level, const double* R9T3, const dvo_solver_params* prm,
                                  double* H36, double* g6, double* sumsq, int* nvis, float* eps, float* w, float* u, float* v, float* J) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!prm) return DVO_ERR_ARG;
     if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !R9T3) return DVO_ERR_ARG;
     if (!c->haveK) { dvo_set_error("intrinsics not set"); return DVO_ERR_STATE; }
@@ -600,6 +694,7 @@ int dvo_eval_normal_equations_ex(dvo_ctx* c, int slot, int level, const double* 
 }
 
 int dvo_get_trace(dvo_ctx* c, int slot, int level, double* trace) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !trace) return DVO_ERR_ARG;
     if (!c->trace) { dvo_set_error("dvo_get_trace: context created with trace_iters = 0"); return DVO_ERR_STATE; }
     const size_t n = (size_t)c->cfg.trace_iters * DVO_TRACE_DOUBLES;
@@ -624,6 +719,7 @@ int dvo_get_stage_ms(dvo_ctx* c, float* ms) {
 long long dvo_launch_count(dvo_ctx* c) { return c ? c->launches : 0; }
 
 int dvo_gop_compose(dvo_ctx* c, int nseq, int nframes, const int* kind, const double* rel, double* out, int mem) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
     if (!c || nseq < 1 || nframes < 1 || !kind || !rel || !out) return DVO_ERR_ARG;
     const size_t n = (size_t)nseq * nframes;
     if (mem == DVO_MEM_DEVICE) return launch_gop(c, nseq, nframes, kind, rel, out);

@@ -32,6 +32,9 @@ struct dvo_ctx {
     bool haveK;
     cudaStream_t own_stream, stream, copy_stream;
     cudaEvent_t ev_chunk[16], ev_entry;
+    cudaStream_t aux[2];            // internal streams of dvo_process (two half batches, staggered)
+    cudaEvent_t ev_fork, ev_pre[2], ev_aux_done[2];
+    bool aux_pending;               // work is in flight on aux[] that the context stream has not joined yet
     int e2e_chunk;           // frame pairs per upload/compute pipeline stage in dvo_align_batch
     int sm_count;
     size_t smem_optin;

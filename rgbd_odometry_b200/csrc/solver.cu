@@ -674,8 +674,9 @@ int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
     const bool need_h = (p->solver != DVO_SOLVER_SUBGRAD_REF) || (c->trace != nullptr);
     if (c->trace) DVO_CUDA(cudaMemsetAsync(c->trace + (size_t)first * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, 0,
                                            sizeof(double) * (size_t)count * c->geom.L * c->cfg.trace_iters * DVO_TRACE_DOUBLES, c->stream));
-    solve_order_kernel<<<1, 1024, 0, c->stream>>>(c->npts, c->geom.L, *p, first, count, c->solve_order);
-    a.order = c->solve_order; a.active = c->active;
+    // the order list of slots [first, first + count) lives at solve_order + first, so launches on disjoint ranges never share it
+    solve_order_kernel<<<1, 1024, 0, c->stream>>>(c->npts, c->geom.L, *p, first, count, c->solve_order + first);
+    a.order = c->solve_order + first; a.active = c->active;
     DVO_CUDA(launch_solve_any(c, a, count, need_h));
     c->launches++;
     c->launches++;

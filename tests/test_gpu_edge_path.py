@@ -259,6 +259,35 @@ def test_align_batch_end_to_end_matches_staged_calls(batch):
     al.close()
 
 
+def test_process_two_stream_schedule_is_bit_identical():
+    """dvo_process (two staggered half batches on internal streams, poses copied per half, deferred join) gives exactly
+    the staged calls' results, also across back-to-back calls and when other entry points are interleaved."""
+    import torch
+    n = 600                                   # >= 4 x 148 SMs, so the overlapped path is taken
+    d = O.synth_batch(900, 8, 160, 120, (131.25, 131.25, 79.5, 59.5))
+    rep = lambda a: np.ascontiguousarray(np.tile(a, (n // 8, 1, 1)))
+    rg, rd, ng = rep(d["ref_gray"]), rep(d["ref_depth"]), rep(d["now_gray"])
+    ng[1::2] = np.roll(ng[1::2], 1, axis=2)                       # make the odd pairs different problems
+    al = dvo.BatchAligner(160, 120, 3, max_batch=n, intrinsics=(131.25, 131.25, 79.5, 59.5))
+    al.set_frames(dvo.FRAME_REF, rg, rd); al.set_frames(dvo.FRAME_NOW, ng, None)
+    prm = dvo.solver_params(solver=dvo.GN, iters=(6, 6, 6))
+    al.build_pyramids(n); al.prepare(n); al.run(n, prm)
+    want, winfo = al.get_poses(n)
+    out = torch.zeros((n, 12), dtype=torch.float64, device="cuda")
+    al.set_frames(dvo.FRAME_NOW, ng[::-1].copy(), None)            # scramble, then restore: process must rebuild everything
+    al.process(n, prm)
+    al.set_frames(dvo.FRAME_NOW, ng, None)                         # joins before it touches the slots
+    for _ in range(3):
+        al.process(n, prm, poses_out=out.data_ptr())               # back to back, no join in between
+    al.join(); al.synchronize()
+    got, ginfo = al.get_poses(n)
+    assert np.array_equal(got, want) and np.array_equal(out.cpu().numpy(), want)
+    assert all(list(ginfo[i].iterations_run[:3]) == list(winfo[i].iterations_run[:3]) for i in range(n))
+    al.process(100, prm, first=7)                                  # small range: staged fallback
+    assert np.array_equal(al.get_poses(100, first=7)[0], want[7:107])
+    al.close()
+
+
 def test_blank_and_degenerate_inputs():
     """No edges anywhere: the reference asserts nSelectedPts > 0 (src/SolveDVO.cpp:282); here status bit 0 is set, the
     pose stays at its initial value, d2 is the EDT_INF sentinel and DTn is 0 -- exactly what the oracle produces."""
