@@ -177,3 +177,34 @@ def test_rgbd_exponential_map_and_qr_solve():
         x = O.rgbd_qr_solve6(A, b)
         assert np.allclose(A @ x, b, rtol=1e-8, atol=1e-8 * np.abs(b).max())
         assert np.allclose(x, np.linalg.solve(A, b), rtol=1e-6)
+
+
+def test_exact_jacobian_is_the_derivative_of_the_reprojection():
+    """JAC_EXACT (the oracle's analytic Jacobian wrt the right-multiplicative update cT += cR*ups, cR <- cR*exp(om)) against
+    central finite differences of the oracle's own reprojection: with gradient images (gx, gy) = (1, 0) / (0, 1) the
+    Jacobian row is du/dpsi / dv/dpsi.  Ties the Jacobian convention to the pose update the solver actually applies."""
+    rng = np.random.default_rng(21)
+    H, W, level = 60, 80, 1
+    N = 40
+    Z = rng.uniform(1.0, 4.0, N).astype(np.float32)
+    X = (rng.uniform(-0.3, 0.3, N) * Z).astype(np.float32); Y = (rng.uniform(-0.2, 0.2, N) * Z).astype(np.float32)
+    K = (120.0, 118.0, 79.5, 59.5)             # level-0 intrinsics; level 1 halves them
+    R0 = O.se3_exp(np.array([0, 0, 0, 0.02, -0.015, 0.01]))[0]; T0 = np.array([0.01, -0.02, 0.015])
+    ones, zeros = np.ones((H, W), np.float32), np.zeros((H, W), np.float32)
+
+    def reproj(R, T):
+        o = O.evaluate(X, Y, Z, zeros, zeros, zeros, level, R, T, K=K, jac=O.JAC_EXACT, weight=O.W_NONE, per_point=True)
+        return o["u"].astype(np.float64), o["v"].astype(np.float64)
+
+    Ju = O.evaluate(X, Y, Z, zeros, ones, zeros, level, R0, T0, K=K, jac=O.JAC_EXACT, weight=O.W_NONE, per_point=True)
+    Jv = O.evaluate(X, Y, Z, zeros, zeros, ones, level, R0, T0, K=K, jac=O.JAC_EXACT, weight=O.W_NONE, per_point=True)
+    assert Ju["nvis"] == N
+    h = 1e-3
+    for k in range(6):
+        d = np.zeros(6); d[k] = h
+        Rp, tp = O.se3_exp(d); Rm, tm = O.se3_exp(-d)
+        up, vp = reproj(R0 @ Rp, T0 + R0 @ tp)
+        um, vm = reproj(R0 @ Rm, T0 + R0 @ tm)
+        fu, fv = (up - um) / (2 * h), (vp - vm) / (2 * h)
+        assert np.allclose(Ju["J"][:, k], fu, rtol=2e-2, atol=2e-2), (k, np.abs(Ju["J"][:, k] - fu).max())
+        assert np.allclose(Jv["J"][:, k], fv, rtol=2e-2, atol=2e-2), (k, np.abs(Jv["J"][:, k] - fv).max())
