@@ -40,6 +40,7 @@ struct dvo_rgbd_ctx {
     double* A;            // [Bmax][L][36]
     int* npts;            // [Bmax][L]
     RgState* st;          // [Bmax]
+    double* pose_stage;   // [Bmax][16] device staging for dvo_rgbd_set_pose
     long long launches;
 };
 
@@ -367,6 +368,7 @@ int dvo_rgbd_create(const dvo_rgbd_config* cfg, dvo_rgbd_ctx** out) {
     if (e == cudaSuccess) e = rg_alloc(&c->A, B * g.L * 36);
     if (e == cudaSuccess) e = rg_alloc(&c->npts, B * g.L);
     if (e == cudaSuccess) e = rg_alloc(&c->st, B);
+    if (e == cudaSuccess) e = rg_alloc(&c->pose_stage, B * 16);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->npts, 0, sizeof(int) * B * g.L, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->st, 0, sizeof(RgState) * B, c->stream);
     if (e == cudaSuccess) e = cudaMemsetAsync(c->A, 0, sizeof(double) * B * g.L * 36, c->stream);
@@ -379,7 +381,7 @@ int dvo_rgbd_destroy(dvo_rgbd_ctx* c) {
     if (!c) return DVO_OK;
     cudaFree(c->bgr); cudaFree(c->depth_in);
     for (int f = 0; f < 2; ++f) { cudaFree(c->gray[f]); cudaFree(c->depth[f]); }
-    cudaFree(c->A); cudaFree(c->npts); cudaFree(c->st);
+    cudaFree(c->A); cudaFree(c->npts); cudaFree(c->st); cudaFree(c->pose_stage);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return DVO_OK;
@@ -427,12 +429,13 @@ int dvo_rgbd_set_pose(dvo_rgbd_ctx* c, int first, int count, const double* T16) 
     if (!rg_range_ok(c, first, count)) return DVO_ERR_ARG;
     if (count == 0) return DVO_OK;
     double* d = nullptr;
-    if (T16) { DVO_CUDA(cudaMalloc((void**)&d, sizeof(double) * 16 * count)); DVO_CUDA(cudaMemcpyAsync(d, T16, sizeof(double) * 16 * count, cudaMemcpyHostToDevice, c->stream)); }
+    if (T16) {      // pageable host memory: the copy is staged by the runtime before the call returns, so T16 may be reused at once
+        d = c->pose_stage + 16 * (size_t)first;
+        DVO_CUDA(cudaMemcpyAsync(d, T16, sizeof(double) * 16 * count, cudaMemcpyHostToDevice, c->stream));
+    }
     rg_set_pose_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(c->st, first, count, d);
     c->launches++;
-    cudaError_t e = cudaGetLastError();
-    if (d) { cudaStreamSynchronize(c->stream); cudaFree(d); }
-    DVO_CUDA(e);
+    DVO_CUDA(cudaGetLastError());
     return DVO_OK;
 }
 
