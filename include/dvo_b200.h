@@ -282,6 +282,15 @@ int dvo_photo_get_A(dvo_photo_ctx* ctx, int slot, int level, double* A36);
 int dvo_photo_eval(dvo_photo_ctx* ctx, int slot, int level, const double* R9T3, int compat, double huber_k, double* b6, double* A36,
                    double* sumsq, int* nreproj, int* nused, double* canvas);
 
+/* ---- undistortion front-end of the publisher (src/camTopic2PublisherPyD.cpp:86-117: cv::undistort of the BGR frame and of
+ * the 16-bit depth frame before the pyramid is built).  `count` images of `type`, tightly packed; K4 = fx, fy, cx, cy;
+ * D5 = k1, k2, p1, p2, k3 (sensor_msgs/CameraInfo.D, :55-61).  Bilinear, BORDER_CONSTANT 0, bit-exact against
+ * cv2.undistort 4.13.  mem = DVO_MEM_DEVICE: both pointers are device memory and the call is asynchronous on
+ * `cuda_stream`; DVO_MEM_HOST: staged through temporary device buffers, synchronous. ---- */
+enum { DVO_IMG_U8C1 = 0, DVO_IMG_U8C3 = 1, DVO_IMG_U16C1 = 2 };
+int dvo_undistort(const void* src, void* dst, int width, int height, int type, int count, const double* K4, const double* D5, int mem,
+                  void* cuda_stream);
+
 /* ================================================================================================================
  * RGBDOdometry (src/RGBDOdometry.cpp, include/RGBDOdometry.h:96-131): the semi-dense photometric Gauss-Newton --
  * reference-frame Jacobian at pixels whose forward x-gradient is >= const_gradientThreshold, A = J^T J per level,

@@ -943,6 +943,48 @@ inline void estimate(const RefLevel& L, const uint8_t* now_gray, Cam K, const do
 }  // namespace photo
 
 // ======================================================================================================
+// Undistortion front-end of the publisher (src/camTopic2PublisherPyD.cpp:86-117: cv::undistort(src, dst, K, D) for the
+// BGR frame and for the 16-bit depth frame).  cv::undistort = initUndistortRectifyMap (fp64 forward distortion model,
+// map quantised to 1/32 pixel: CV_16SC2 + 5-bit fractions) + remap(INTER_LINEAR, BORDER_CONSTANT 0).  8-bit images use
+// 15-bit fixed-point weights, w = (32-a)(32-b)*32 etc., value = (sum + 2^14) >> 15; 16-bit images use fp32 weights
+// (32-a)(32-b)/1024 and saturate_cast<ushort>(cvRound(sum)) with the four products added left to right.  Pinned
+// against cv2.undistort 4.13 (tests/golden/undistort_*.npz, tests/test_oracle_golden.py).  D = (k1, k2, p1, p2, k3).
+// ======================================================================================================
+template <typename T>
+void undistort(const T* src, int W, int H, int cn, const double* K4, const double* D5, T* dst) {
+    const double fx = K4[0], fy = K4[1], cx = K4[2], cy = K4[3];
+    const double k1 = D5[0], k2 = D5[1], p1 = D5[2], p2 = D5[3], k3 = D5[4];
+    const double ir0 = 1.0 / fx, ir2 = -cx / fx, ir4 = 1.0 / fy, ir5 = -cy / fy;
+    for (int i = 0; i < H; ++i)
+        for (int j = 0; j < W; ++j) {
+            const double x = (double)j * ir0 + ir2, y = (double)i * ir4 + ir5;
+            const double x2 = x * x, y2 = y * y, r2 = x2 + y2, _2xy = 2 * x * y;
+            const double kr = 1 + ((k3 * r2 + k2) * r2 + k1) * r2;
+            const double xd = x * kr + p1 * _2xy + p2 * (r2 + 2 * x2), yd = y * kr + p1 * (r2 + 2 * y2) + p2 * _2xy;
+            const double u = fx * xd + cx, v = fy * yd + cy;
+            const long long iu = (long long)std::nearbyint(u * 32.0), iv = (long long)std::nearbyint(v * 32.0);
+            const long long sx = iu >> 5, sy = iv >> 5; const int a = (int)(iu & 31), b = (int)(iv & 31);
+            auto at = [&](long long yy, long long xx, int c) -> T {
+                return (yy >= 0 && yy < H && xx >= 0 && xx < W) ? src[((size_t)yy * W + (size_t)xx) * cn + c] : (T)0;
+            };
+            for (int c = 0; c < cn; ++c) {
+                const T s00 = at(sy, sx, c), s01 = at(sy, sx + 1, c), s10 = at(sy + 1, sx, c), s11 = at(sy + 1, sx + 1, c);
+                if (sizeof(T) == 1) {
+                    const int w00 = (32 - a) * (32 - b) * 32, w01 = a * (32 - b) * 32, w10 = (32 - a) * b * 32, w11 = a * b * 32;
+                    int r = ((int)s00 * w00 + (int)s01 * w01 + (int)s10 * w10 + (int)s11 * w11 + (1 << 14)) >> 15;
+                    dst[((size_t)i * W + j) * cn + c] = (T)(r < 0 ? 0 : (r > 255 ? 255 : r));
+                } else {
+                    const float w00 = (float)((32 - a) * (32 - b)) / 1024.f, w01 = (float)(a * (32 - b)) / 1024.f;
+                    const float w10 = (float)((32 - a) * b) / 1024.f, w11 = (float)(a * b) / 1024.f;
+                    const float f = (((float)s00 * w00 + (float)s01 * w01) + (float)s10 * w10) + (float)s11 * w11;
+                    int r = (int)std::nearbyintf(f);
+                    dst[((size_t)i * W + j) * cn + c] = (T)(r < 0 ? 0 : (r > 65535 ? 65535 : r));
+                }
+            }
+        }
+}
+
+// ======================================================================================================
 // RGBDOdometry: the semi-dense photometric Gauss-Newton (src/RGBDOdometry.cpp).  fp64 like the
 // reference; quirks kept as written and listed where they occur.  Eigen-specific internals that cannot be restated
 // operation for operation (Affine inverse, colPivHouseholderQr) are replaced by the closed forms noted below.

@@ -303,4 +303,10 @@ void orc_rgbd_gauss_newton(const uint8_t* ref_bgr, const uint16_t* ref_depth, co
     }
 }
 
+// cv::undistort restatement (publisher front-end): type 0 = u8 (cn channels), 1 = u16 (1 channel)
+void orc_undistort(const void* src, int W, int H, int cn, int type, const double* K4, const double* D5, void* dst) {
+    if (type == 0) undistort<uint8_t>((const uint8_t*)src, W, H, cn, K4, D5, (uint8_t*)dst);
+    else undistort<uint16_t>((const uint16_t*)src, W, H, cn, K4, D5, (uint16_t*)dst);
+}
+
 }  // extern "C"

@@ -66,6 +66,7 @@ SYMBOLS = [
     "dvo_photo_create", "dvo_photo_destroy", "dvo_photo_set_stream", "dvo_photo_synchronize", "dvo_photo_launch_count",
     "dvo_photo_set_intrinsics", "dvo_photo_set_frames", "dvo_photo_prepare_ref", "dvo_photo_set_pose", "dvo_photo_estimate",
     "dvo_photo_get_poses", "dvo_photo_get_level", "dvo_photo_get_A", "dvo_photo_eval",
+    "dvo_undistort",
     "dvo_rgbd_create", "dvo_rgbd_destroy", "dvo_rgbd_set_stream", "dvo_rgbd_synchronize", "dvo_rgbd_launch_count",
     "dvo_rgbd_set_intrinsics", "dvo_rgbd_set_frames", "dvo_rgbd_compute_jacobians", "dvo_rgbd_set_pose", "dvo_rgbd_gauss_newton",
     "dvo_rgbd_get_poses", "dvo_rgbd_level_dims", "dvo_rgbd_get_level", "dvo_rgbd_get_A", "dvo_rgbd_eval",
@@ -138,6 +139,7 @@ def load(build_if_missing=True):
     lib.dvo_photo_get_A.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.dvo_photo_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
+    lib.dvo_undistort.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.dvo_rgbd_create.argtypes = [C.POINTER(RgbdConfig), C.POINTER(C.c_void_p)]
     lib.dvo_rgbd_destroy.argtypes = [C.c_void_p]
     lib.dvo_rgbd_set_stream.argtypes = [C.c_void_p, C.c_void_p]

@@ -32,6 +32,19 @@ def keyframe_policy(keyframe_every=5, use_quality_gates=False, laplacian_thresh=
     return KeyframePolicy(keyframe_every, int(use_quality_gates), laplacian_thresh, visible_ratio_thresh, min_reprojections)
 
 
+def undistort(img, K, D):
+    """cv::undistort of a batch of images (N, H, W[, 3]) u8 or (N, H, W) u16 on the GPU (dvo_undistort, host buffers)."""
+    lib = _lib.load()
+    img = np.ascontiguousarray(img)
+    n, h, w = img.shape[:3]
+    typ = 2 if img.dtype == np.uint16 else (1 if img.ndim == 4 and img.shape[3] == 3 else 0)
+    out = np.empty_like(img)
+    K4 = np.array(K, np.float64); D5 = np.array(D, np.float64)
+    check(lib.dvo_undistort(img.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), w, h, typ, n, K4.ctypes.data_as(C.c_void_p),
+                            D5.ctypes.data_as(C.c_void_p), MEM_HOST, None), "dvo_undistort")
+    return out
+
+
 def _ptr(a):
     if a is None:
         return None

@@ -39,7 +39,7 @@ def cuda_sources():
 
 
 # per-file extra flags: the photometric path mirrors the oracle's fp64 operation order, so no FMA contraction there
-PER_FILE_FLAGS = {"photometric.cu": ["-fmad=false"], "rgbd.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"photometric.cu": ["-fmad=false"], "rgbd.cu": ["-fmad=false"], "frontend.cu": ["-fmad=false"]}
 COMPILE_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off"]
 OBJ_DIR = os.path.join(PKG, "build")
 

@@ -1,0 +1,82 @@
+// frontend.cu -- the publisher's undistortion front-end (src/camTopic2PublisherPyD.cpp:86-117: cv::undistort of the BGR
+// frame and of the 16-bit depth frame before the pyramid is built).  cv::undistort = initUndistortRectifyMap (fp64
+// forward distortion model; map quantised to 1/32 pixel) + remap(INTER_LINEAR, BORDER_CONSTANT 0): a pure gather, one
+// thread per output pixel, batched over `count` images.  8-bit: 15-bit fixed-point weights, (sum + 2^14) >> 15;
+// 16-bit: fp32 weights, products added left to right, cvRound + saturate.  Compiled with -fmad=false like the oracle
+// (-ffp-contract=off); bit-exact against cv2.undistort 4.13 through the oracle (tests/golden/undistort_*.npz).
+#include <math.h>
+#include <string.h>
+
+#include "common.cuh"
+
+struct UndArgs { double fx, fy, cx, cy, k1, k2, p1, p2, k3; int W, H, cn; };
+
+template <typename T>
+__global__ void __launch_bounds__(256) undistort_kernel(UndArgs a, const T* __restrict__ src, T* __restrict__ dst) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= a.W * a.H) return;
+    const int i = p / a.W, j = p - i * a.W;
+    const size_t img = (size_t)blockIdx.y * a.W * a.H * a.cn;
+    src += img; dst += img;
+    const double ir0 = 1.0 / a.fx, ir2 = -a.cx / a.fx, ir4 = 1.0 / a.fy, ir5 = -a.cy / a.fy;
+    const double x = (double)j * ir0 + ir2, y = (double)i * ir4 + ir5;
+    const double x2 = x * x, y2 = y * y, r2 = x2 + y2, _2xy = 2 * x * y;
+    const double kr = 1 + ((a.k3 * r2 + a.k2) * r2 + a.k1) * r2;
+    const double xd = x * kr + a.p1 * _2xy + a.p2 * (r2 + 2 * x2), yd = y * kr + a.p1 * (r2 + 2 * y2) + a.p2 * _2xy;
+    const double u = a.fx * xd + a.cx, v = a.fy * yd + a.cy;
+    const long long iu = (long long)rint(u * 32.0), iv = (long long)rint(v * 32.0);
+    const long long sx = iu >> 5, sy = iv >> 5;
+    const int fa = (int)(iu & 31), fb = (int)(iv & 31);
+    const bool x0 = sx >= 0 && sx < a.W, x1 = sx + 1 >= 0 && sx + 1 < a.W, y0 = sy >= 0 && sy < a.H, y1 = sy + 1 >= 0 && sy + 1 < a.H;
+    const size_t o00 = ((size_t)(y0 ? sy : 0) * a.W + (size_t)(x0 ? sx : 0)) * a.cn, o01 = ((size_t)(y0 ? sy : 0) * a.W + (size_t)(x1 ? sx + 1 : 0)) * a.cn;
+    const size_t o10 = ((size_t)(y1 ? sy + 1 : 0) * a.W + (size_t)(x0 ? sx : 0)) * a.cn, o11 = ((size_t)(y1 ? sy + 1 : 0) * a.W + (size_t)(x1 ? sx + 1 : 0)) * a.cn;
+    for (int c = 0; c < a.cn; ++c) {
+        const T s00 = (y0 && x0) ? src[o00 + c] : (T)0, s01 = (y0 && x1) ? src[o01 + c] : (T)0;
+        const T s10 = (y1 && x0) ? src[o10 + c] : (T)0, s11 = (y1 && x1) ? src[o11 + c] : (T)0;
+        if (sizeof(T) == 1) {
+            const int w00 = (32 - fa) * (32 - fb) * 32, w01 = fa * (32 - fb) * 32, w10 = (32 - fa) * fb * 32, w11 = fa * fb * 32;
+            int r = ((int)s00 * w00 + (int)s01 * w01 + (int)s10 * w10 + (int)s11 * w11 + (1 << 14)) >> 15;
+            dst[(size_t)p * a.cn + c] = (T)min(max(r, 0), 255);
+        } else {
+            const float w00 = (float)((32 - fa) * (32 - fb)) / 1024.f, w01 = (float)(fa * (32 - fb)) / 1024.f;
+            const float w10 = (float)((32 - fa) * fb) / 1024.f, w11 = (float)(fa * fb) / 1024.f;
+            const float f = (((float)s00 * w00 + (float)s01 * w01) + (float)s10 * w10) + (float)s11 * w11;
+            const int r = (int)rintf(f);
+            dst[(size_t)p * a.cn + c] = (T)min(max(r, 0), 65535);
+        }
+    }
+}
+
+extern "C" int dvo_undistort(const void* src, void* dst, int width, int height, int type, int count, const double* K4, const double* D5, int mem,
+                             void* cuda_stream) {
+    if (!src || !dst || width < 2 || height < 2 || count < 0 || !K4 || !D5 || (type != DVO_IMG_U8C1 && type != DVO_IMG_U8C3 && type != DVO_IMG_U16C1)) {
+        dvo_set_error("dvo_undistort: bad argument"); return DVO_ERR_ARG;
+    }
+    if (count == 0) return DVO_OK;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { dvo_set_error("dvo_undistort: no usable CUDA device (there is no CPU fallback)"); return DVO_ERR_CUDA; }
+    UndArgs a;
+    a.fx = K4[0]; a.fy = K4[1]; a.cx = K4[2]; a.cy = K4[3]; a.k1 = D5[0]; a.k2 = D5[1]; a.p1 = D5[2]; a.p2 = D5[3]; a.k3 = D5[4];
+    a.W = width; a.H = height; a.cn = (type == DVO_IMG_U8C3) ? 3 : 1;
+    const size_t bytes = (size_t)width * height * a.cn * (type == DVO_IMG_U16C1 ? 2 : 1) * count;
+    const cudaStream_t s = (cudaStream_t)cuda_stream;
+    const void* d_src = src; void* d_dst = dst;
+    void *t_src = nullptr, *t_dst = nullptr;
+    if (mem != DVO_MEM_DEVICE) {
+        DVO_CUDA(cudaMalloc(&t_src, bytes));
+        if (cudaMalloc(&t_dst, bytes) != cudaSuccess) { cudaFree(t_src); dvo_set_error("dvo_undistort: out of device memory"); return DVO_ERR_NOMEM; }
+        cudaMemcpyAsync(t_src, src, bytes, cudaMemcpyHostToDevice, s);
+        d_src = t_src; d_dst = t_dst;
+    }
+    dim3 grid((unsigned)(((size_t)width * height + 255) / 256), (unsigned)count);
+    if (type == DVO_IMG_U16C1) undistort_kernel<uint16_t><<<grid, 256, 0, s>>>(a, (const uint16_t*)d_src, (uint16_t*)d_dst);
+    else undistort_kernel<uint8_t><<<grid, 256, 0, s>>>(a, (const uint8_t*)d_src, (uint8_t*)d_dst);
+    cudaError_t e = cudaGetLastError();
+    if (mem != DVO_MEM_DEVICE) {
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dst, t_dst, bytes, cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaFree(t_src); cudaFree(t_dst);
+    }
+    if (e != cudaSuccess) { dvo_set_error("dvo_undistort: %s", cudaGetErrorString(e)); return DVO_ERR_CUDA; }
+    return DVO_OK;
+}

@@ -2,6 +2,8 @@
 // reference uses (opencv-matrix nodes), the pose text lines and the TUM ground-truth file.
 #include "FrameIO.h"
 
+#include "dvo_b200.h"
+
 #include <cctype>
 #include <cmath>
 #include <cstdio>
@@ -170,6 +172,13 @@ bool storeFrameXml(const char* xmlFileName, const RGBDFramePyd& in) {
     }
     f << "</opencv_storage>\n";
     return f.good();
+}
+
+bool undistortFrame(const ImageView& src, Image& dst, const double* K4, const double* D5) {
+    dst.rows = src.rows; dst.cols = src.cols; dst.channels = src.channels(); dst.elem = (src.type == U16C1) ? ELEM_U16 : ELEM_U8;
+    dst.data.resize(src.bytes());
+    const int type = (src.type == U16C1) ? DVO_IMG_U16C1 : (src.type == U8C3 ? DVO_IMG_U8C3 : DVO_IMG_U8C1);
+    return dvo_undistort(src.data, dst.data.data(), src.cols, src.rows, type, 1, K4, D5, DVO_MEM_HOST, nullptr) == DVO_OK;
 }
 
 void printPose(const Pose& p, std::ostream& stream) {                             // src/SolveDVO.cpp:1346-1350

@@ -40,6 +40,11 @@ bool loadFrameXml(const char* xmlFileName, RGBDFramePyd& out, int levels = 4);
 // the writer side (src/camTopic2PublisherPyD.cpp:315-365): fs << "mono_i" << framemono << "depth_i" << dframe per level
 bool storeFrameXml(const char* xmlFileName, const RGBDFramePyd& in);
 
+// undistortFrame / undistortDFrame of the publisher (src/camTopic2PublisherPyD.cpp:86-117): cv::undistort(src, dst,
+// cameraMatrix, distCoeff) on the GPU (dvo_undistort; bilinear, constant border, bit-exact against OpenCV 4.13).  K = fx, fy,
+// cx, cy; D = k1, k2, p1, p2, k3.  Returns false when the device call fails (the reference copies src when it has no camera info).
+bool undistortFrame(const ImageView& src, Image& dst, const double* K4, const double* D5);
+
 // SolveDVO::printPose's file line (src/SolveDVO.cpp:1346-1350): default ostream formatting, space separated, '\n'.
 void printPose(const Pose& p, std::ostream& stream);
 bool readPoseFile(const char* fileName, std::vector<Pose>& out);

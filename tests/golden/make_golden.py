@@ -82,6 +82,26 @@ def main():
     np.savez_compressed(os.path.join(HERE, "opencv_stages.npz"), **out)
     print("wrote", os.path.join(HERE, "opencv_stages.npz"), "cv2", cv2.__version__)
     frame_dump()
+    undistort_golden()
+
+
+UND_K = (262.5, 262.5, 159.5, 119.5)
+UND_D = (0.2312, -0.7849, -0.0033, -0.0001, 0.9172)        # k1 k2 p1 p2 k3, a Kinect-class lens
+
+
+def undistort_golden():
+    """cv2.undistort of the publisher's two inputs (BGR u8 and 16-bit depth, src/camTopic2PublisherPyD.cpp:86-117) and of a
+    gray image, 320x240, so that the oracle's restatement is pinned without cv2 at test time."""
+    rng = np.random.default_rng(77)
+    d = O.synth_pair(11, 320, 240, UND_K, bgr=True)
+    Km = np.array([[UND_K[0], 0, UND_K[2]], [0, UND_K[1], UND_K[3]], [0, 0, 1]]); Dm = np.array(UND_D)
+    out = {"K": np.array(UND_K), "D": np.array(UND_D)}
+    for name, img in (("bgr", d["ref_bgr"]), ("depth", d["ref_depth"]), ("gray", d["ref_gray"]),
+                      ("noise_u8", rng.integers(0, 256, (240, 320), dtype=np.uint8)), ("noise_u16", rng.integers(0, 65536, (240, 320), dtype=np.uint16))):
+        out[name + "_in"] = img
+        out[name + "_out"] = cv2.undistort(img, Km, Dm)
+    np.savez_compressed(os.path.join(HERE, "undistort_320x240.npz"), **out)
+    print("wrote undistort_320x240.npz")
 
 
 def frame_dump():

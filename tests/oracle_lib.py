@@ -493,3 +493,15 @@ def rgbd_gauss_newton(ref_bgr, ref_depth, now_bgr, now_depth, K, levels=(3, 2), 
                                 _p(np.ascontiguousarray(now_bgr), C.c_uint8), _p(np.ascontiguousarray(now_depth), C.c_uint16), W, H, _p(K4, C.c_double),
                                 thresh, _p(lv, C.c_int32), len(levels), iters, C.c_double(eps_exit), _p(T, C.c_double), _p(info, C.c_double))
     return T.reshape(4, 4), info
+
+
+# ---- publisher front-end ----
+def undistort(img, K, D):
+    img = np.ascontiguousarray(img)
+    H, W = img.shape[:2]
+    cn = 1 if img.ndim == 2 else img.shape[2]
+    out = np.empty_like(img)
+    K4 = np.array(K, np.float64); D5 = np.array(D, np.float64)
+    lib().orc_undistort(img.ctypes.data_as(C.c_void_p), W, H, cn, 0 if img.dtype == np.uint8 else 1, _p(K4, C.c_double), _p(D5, C.c_double),
+                        out.ctypes.data_as(C.c_void_p))
+    return out

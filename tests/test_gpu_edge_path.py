@@ -415,3 +415,19 @@ def test_gop_compose_matches_oracle():
         o, is_key, _ = O.gop_replay(kind[s], np.full(nframes, 5, np.int32), rel[s])
         assert np.allclose(out[s], o, rtol=0, atol=1e-12)
     al.close()
+
+
+def test_undistort_front_end_bit_exact():
+    """dvo_undistort (cv::undistort of the publisher, src/camTopic2PublisherPyD.cpp:86-117) against the oracle, which is itself
+    pinned against cv2.undistort: BGR u8, gray u8 and 16-bit depth, batched, including an odd size and strong distortion."""
+    rng = np.random.default_rng(8)
+    for (W, H), K, D in (((640, 480), (525.0, 525.0, 319.5, 239.5), (0.2312, -0.7849, -0.0033, -0.0001, 0.9172)),
+                         ((101, 77), (90.0, 88.0, 50.0, 38.0), (-0.35, 0.15, 0.002, -0.001, 0.0))):
+        for img in (rng.integers(0, 256, (3, H, W, 3), dtype=np.uint8), rng.integers(0, 256, (2, H, W), dtype=np.uint8),
+                    rng.integers(0, 65536, (3, H, W), dtype=np.uint16)):
+            got = dvo.undistort(img, K, D)
+            for n in range(img.shape[0]):
+                assert np.array_equal(got[n], O.undistort(img[n], K, D)), (W, H, img.dtype, img.shape, n)
+    # identity lens: an exact copy
+    img = rng.integers(0, 256, (1, 48, 64), dtype=np.uint8)
+    assert np.array_equal(dvo.undistort(img, (60.0, 60.0, 31.5, 23.5), (0, 0, 0, 0, 0)), img)
