@@ -66,6 +66,8 @@ class ClockSampler(threading.Thread):
         self.index, self.stop_flag, self.samples = index, False, []
 
     def run(self):
+        if self._run_nvml():
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
@@ -75,6 +77,27 @@ class ClockSampler(threading.Thread):
             except Exception:
                 pass
             time.sleep(0.1)
+
+    def _run_nvml(self):
+        """Same fields through NVML (a sample every 5 ms instead of one nvidia-smi process per ~100 ms); False -> fall back."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = (0x8, 0x40, 0x20, 0x4)      # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM); get_reasons(h)
+        except Exception:
+            return False
+        while not self.stop_flag:
+            try:
+                r = int(get_reasons(h))
+                self.samples.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+            except Exception:
+                pass
+            time.sleep(0.005)
+        return True
 
     def summary(self):
         sm, mx, reasons = [], 0, set()
