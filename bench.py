@@ -288,6 +288,8 @@ def run_ours(args):
         pass
     roofline = {"bound": "hbm", "kernel": "solve_kernel", "achieved": dom_gbs, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": dom_gbs / peak, "traffic": traffic,
+                "timing": "CUDA events around each stage on the launching stream, 3 staged steps run right after the timed region "
+                          "(inside it the two half batches overlap on internal streams, so a kernel cannot be bracketed there)",
                 "algorithmic_bytes_per_launch": alg[dom], "kernel_ms": stage[dom],
                 "whole_path": {"bytes_per_pair": bytes_pair, "achieved_gbs": bytes_pair * B / (ms_max * 1e-3) / 1e9,
                                "frac": bytes_pair * B / (ms_max * 1e-3) / 1e9 / peak},
