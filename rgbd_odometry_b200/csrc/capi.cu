@@ -87,10 +87,20 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
         if (g.P[l] > maxP) maxP = g.P[l];
     }
     g.total = acc * g.Bmax;
+    long long acct = 0;
+    for (int l = 0; l < g.L; ++l) {
+        g.tw[l] = (g.w[l] + 3) >> 2; g.Pt[l] = g.tw[l] * ((g.h[l] + 3) >> 2) * 16;
+        g.offt[l] = acct * g.Bmax; acct += g.Pt[l];
+    }
+    g.total_t = acct * g.Bmax;
     cudaDeviceProp prop;
     DVO_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->solve_shape = (cfg->max_batch <= c->sm_count) ? 512 : 256;
+    if (const char* e = getenv("DVO_SOLVE_SHAPE")) { const int v = atoi(e); if (v == 256 || v == 512) c->solve_shape = v; }   // experiment knob
+    c->texel_mode = 1;
+    if (const char* e = getenv("DVO_TEXEL_MODE")) c->texel_mode = atoi(e) ? 1 : 0;                                           // experiment knob (A/B)
     DVO_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     DVO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
@@ -114,7 +124,8 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     A(dalloc(&c->depth[0], T));
     if (cfg->keep_now_depth) { A(dalloc(&c->depth[1], T)); A(dalloc(&c->prev_gray, B * (size_t)g.P[0])); A(dalloc(&c->prev_depth, B * (size_t)g.P[0])); }
     c->now_valid = (unsigned char*)calloc(B, 1); c->prev_valid = (unsigned char*)calloc(B, 1);
-    A(dalloc(&c->gcol, T)); A(dalloc(&c->d2, T)); A(dalloc(&c->texel, T));
+    A(dalloc(&c->gcol, T)); A(dalloc(&c->d2, T));
+    if (c->texel_mode) A(dalloc(&c->tex8, (size_t)g.total_t)); else A(dalloc(&c->texel, T));
     A(dalloc(&c->ptsX, T)); A(dalloc(&c->ptsY, T)); A(dalloc(&c->ptsZ, T)); A(dalloc(&c->ptsPix, T));
     A(dalloc(&c->npts, B * g.L)); A(dalloc(&c->solve_order, B)); A(dalloc(&c->seq_mask, B)); A(dalloc(&c->seq_state, B)); A(dalloc(&c->nedge, 2 * B * g.L)); A(dalloc(&c->maxd2, B * g.L));
     A(dalloc(&c->pose0, B * 12)); A(dalloc(&c->pose, B * 12)); A(dalloc(&c->info, B));
@@ -144,7 +155,7 @@ int dvo_destroy(dvo_ctx* c) {
     cudaSetDevice(c->cfg.device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int f = 0; f < 2; ++f) { cudaFree(c->gray[f]); cudaFree(c->depth[f]); cudaFree(c->edge[f]); }
-    cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ); cudaFree(c->ptsPix);
+    cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->tex8); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ); cudaFree(c->ptsPix);
     cudaFree(c->npts); cudaFree(c->solve_order); cudaFree(c->seq_mask); cudaFree(c->seq_state); cudaFree(c->nedge); cudaFree(c->maxd2); cudaFree(c->pose0); cudaFree(c->pose); cudaFree(c->info);
     cudaFree(c->trace); cudaFree(c->bitmap_scratch); cudaFree(c->prev_gray); cudaFree(c->prev_depth);
     free(c->now_valid); free(c->prev_valid);
@@ -235,7 +246,7 @@ int dvo_prepare(dvo_ctx* c, int first, int count, int frames_mask) {
     { StageTimer t(c, DVO_STAGE_CANNY); rc = launch_canny(c, first, count, frames_mask); if (rc) return rc; }
     if (frames_mask & 2) {
         { StageTimer t(c, DVO_STAGE_EDT_ROWS); rc = launch_edt_rows(c, first, count); if (rc) return rc; }
-        { StageTimer t(c, DVO_STAGE_NORMGRAD); rc = launch_normgrad(c, first, count); if (rc) return rc; }
+        { StageTimer t(c, DVO_STAGE_NORMGRAD); rc = c->texel_mode ? launch_pack(c, first, count) : launch_normgrad(c, first, count); if (rc) return rc; }
     }
     return DVO_OK;
 }
@@ -271,7 +282,7 @@ static int process_range(dvo_ctx* c, int first, int count, const dvo_solver_para
     if ((rc = launch_pyramid(c, first, count, 3))) return rc;
     if ((rc = launch_canny(c, first, count, 3))) return rc;
     if ((rc = launch_edt_rows(c, first, count))) return rc;
-    if ((rc = launch_normgrad(c, first, count))) return rc;
+    if ((rc = c->texel_mode ? launch_pack(c, first, count) : launch_normgrad(c, first, count))) return rc;
     if (pre_done) DVO_CUDA(cudaEventRecord(pre_done, c->stream));
     return launch_solve(c, first, count, p);
 }
@@ -292,6 +303,10 @@ int dvo_process(dvo_ctx* c, int first, int count, const dvo_solver_params* p, do
     // Fork: both internal streams start after everything issued on the context stream so far.  Half 1's preprocessing
     // additionally waits for half 0's, so it runs beside half 0's solve; each internal stream is in order with its own
     // work of the previous call, which is all the dependency there is (the halves own disjoint slots).
+    // A call whose slot split differs from the one still in flight could touch slots the OTHER internal stream is working
+    // on: join first (device-side) in that case.  With the same (first, count) every stream only meets its own slots.
+    if (c->aux_pending && (c->proc_first != first || c->proc_count != count)) { const int rc = join_aux(c); if (rc) return rc; }
+    c->proc_first = first; c->proc_count = count;
     DVO_CUDA(cudaEventRecord(c->ev_fork, c->stream));
     const cudaStream_t user = c->stream;
     const int n0 = count / 2;
@@ -571,14 +586,23 @@ int dvo_get_level_buffer(dvo_ctx* c, int slot, int frame, int level, int which, 
         case DVO_BUF_EDGE: src = c->edge[frame] + o; es = 1; break;
         case DVO_BUF_D2: if (frame != DVO_FRAME_NOW) { dvo_set_error("d2 exists for the now frame only"); return DVO_ERR_ARG; } src = c->d2 + o; es = 4; break;
         case DVO_BUF_DTN: case DVO_BUF_GX: case DVO_BUF_GY:
-            if (frame != DVO_FRAME_NOW) { dvo_set_error("DT exists for the now frame only"); return DVO_ERR_ARG; } src = c->texel + o; es = 16; break;
+            if (frame != DVO_FRAME_NOW) { dvo_set_error("DT exists for the now frame only"); return DVO_ERR_ARG; } src = c->texel ? c->texel + o : nullptr; es = 16; break;
         default: dvo_set_error("dvo_get_level_buffer: unknown buffer %d", which); return DVO_ERR_ARG;
     }
     if (which >= DVO_BUF_DTN) {
         if (bytes < P * 4) { dvo_set_error("dvo_get_level_buffer: destination too small"); return DVO_ERR_ARG; }
         std::vector<float> tmp(P * 4);
-        DVO_CUDA(cudaMemcpyAsync(tmp.data(), src, P * 16, cudaMemcpyDeviceToHost, c->stream));
-        DVO_CUDA(cudaStreamSynchronize(c->stream));
+        float4* d_tmp = nullptr;
+        if (!src) {      // packed-texel contexts keep no float images: evaluate them for this slot / level on demand
+            DVO_CUDA(cudaMalloc((void**)&d_tmp, P * 16));
+            const int rc = launch_normgrad_into(c, slot, level, d_tmp);
+            if (rc) { cudaFree(d_tmp); return rc; }
+            src = d_tmp;
+        }
+        cudaError_t ce = cudaMemcpyAsync(tmp.data(), src, P * 16, cudaMemcpyDeviceToHost, c->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+        cudaFree(d_tmp);
+        DVO_CUDA(ce);
         const int comp = which - DVO_BUF_DTN;
         float* d = (float*)dst;
         for (size_t i = 0; i < P; ++i) d[i] = tmp[4 * i + comp];

@@ -17,8 +17,31 @@ struct PyrGeom {
     int w[DVO_MAX_LEVELS], h[DVO_MAX_LEVELS], P[DVO_MAX_LEVELS];
     long long off[DVO_MAX_LEVELS];
     long long total;
+    // packed distance texels (see "packed texel" below): 4x4-pixel tiles, tw[l] tiles per tile row, Pt[l] texels per image
+    // (padded to whole tiles), same level-major / slot / texel layout:  element(l, b, i) = base[ offt[l] + b * Pt[l] + i ]
+    int tw[DVO_MAX_LEVELS], Pt[DVO_MAX_LEVELS];
+    long long offt[DVO_MAX_LEVELS];
+    long long total_t;
 };
 __host__ __device__ inline long long lvl_at(const PyrGeom& g, int l, int b) { return g.off[l] + (long long)b * g.P[l]; }
+__host__ __device__ inline long long tex_at(const PyrGeom& g, int l, int b) { return g.offt[l] + (long long)b * g.Pt[l]; }
+
+// ---- packed texel -------------------------------------------------------------------------------------------------
+// Everything the solver reads of the now frame at a reprojection -- DTn, its central-difference gradient and
+// getWeightOf(DTn) -- is a function of the exact integer d2 at the pixel and at its four stencil neighbours
+// (src/SolveDVO.cpp:1774, 1063-1098, 1047-1053).  Those five integers fit 8 bytes (16-byte float texels before):
+//   word 0: bits 0..15  d2(y, x)            bits 16..25  d2(y, x-1) - d2(y, x)   (signed 10 bit)    bit 31  escape
+//   word 1: bits 0..9   d2(y, x+1) - centre bits 10..19  d2(y-1, x) - centre     bits 20..29  d2(y+1, x) - centre
+// (|sqrt d2(p) - sqrt d2(q)| <= 1 for neighbours, so |delta| <= 2 d + 1: ten bits cover every distance below 255 pixels;
+// the pack kernel range-checks every field and sets the escape bit otherwise -- the solver then reads the five values
+// from the 32-bit d2 image.)  On the first / last column (row) the REFLECT_101 taps coincide and the gradient is exactly
+// 0: both deltas are stored as 0.  Texels are stored in 4x4-pixel tiles in Morton order, so a 32-byte sector is a 2x2
+// block and a 128-byte line a 4x4 block: an edge contour crossing the block touches one line whatever its direction
+// (row-major 16-byte texels: one line per 8x1 pixels).
+#define DVO_TEX_ESCAPE 0x80000000u
+__host__ __device__ inline int tex_index(int x, int y, int tw) {
+    return (((y >> 2) * tw + (x >> 2)) << 4) | ((y & 2) << 2) | ((x & 2) << 1) | ((y & 1) << 1) | (x & 1);
+}
 
 struct Intr { float fx, fy, cx, cy; };
 
@@ -35,8 +58,10 @@ struct dvo_ctx {
     cudaStream_t aux[2];            // internal streams of dvo_process (two half batches, staggered)
     cudaEvent_t ev_fork, ev_pre[2], ev_aux_done[2];
     bool aux_pending;               // work is in flight on aux[] that the context stream has not joined yet
+    int proc_first, proc_count;     // slot range of the dvo_process call that left that work in flight
     int e2e_chunk;           // frame pairs per upload/compute pipeline stage in dvo_align_batch
     int sm_count;
+    int solve_shape;         // threads per pair in solve_kernel: 512 when max_batch <= sm_count (one pair per SM at most), else 256
     size_t smem_optin;
 
     uint8_t* gray[2];        // [frame] gray pyramid
@@ -48,7 +73,9 @@ struct dvo_ctx {
     uint8_t* edge[2];        // [frame] Canny edge maps 0/255
     uint16_t* gcol;          // now: EDT phase-1 column distances
     int32_t* d2;             // now: exact squared distance
-    float4* texel;           // now: {DTn, gx, gy, getWeightOf(DTn)}
+    float4* texel;           // now: {DTn, gx, gy, getWeightOf(DTn)} -- legacy 16-byte texels (texel_mode 0 only)
+    uint2* tex8;             // now: packed 8-byte texels (texel_mode 1, the default)
+    int texel_mode;          // 1: packed texels + in-kernel lookup tables; 0: legacy float4 texels written by normgrad_kernel
     float *ptsX, *ptsY, *ptsZ;   // ref: back-projected edge points (row-major pixel order), capacity P[l] per slot and level
     int* ptsPix;                 // ref: pixel index y*w+x of every point (restores the reference's column-major order)
     int* npts;               // [Bmax][L]
@@ -91,6 +118,9 @@ int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask);
 int launch_canny(dvo_ctx* c, int first, int count, int frames_mask);
 int launch_edt_rows(dvo_ctx* c, int first, int count);
 int launch_normgrad(dvo_ctx* c, int first, int count);
+int launch_pack(dvo_ctx* c, int first, int count);
+// inspection: {DTn, gx, gy, w} of one slot / level into a caller-provided device buffer of P[level] float4
+int launch_normgrad_into(dvo_ctx* c, int slot, int level, float4* d_out);
 int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p);
 int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k, int residual,
                 double* d_out /* 6 + 36 + 1 + 1 doubles */, float* d_eps, float* d_w, float* d_u, float* d_v, float* d_J);

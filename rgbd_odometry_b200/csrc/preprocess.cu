@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     const int wd = (w + 31) >> 5, pitch = wd + 2;
     const int nwords = a.bm_words;
     // bitmaps: shared memory (LDS/STS/ATOMS) or, for images too large for it, a global scratch
-    uint32_t* C = GLOBAL_BITMAPS ? a.gscratch + (long long)blockIdx.x * a.gscratch_stride : smem_u32;
+    // (the global scratch is indexed by SLOT, not by block: launches on different streams own disjoint slot ranges)
+    uint32_t* C = GLOBAL_BITMAPS ? a.gscratch + (long long)b * a.gscratch_stride : smem_u32;
     uint32_t* E = C + nwords;
     const uint8_t* __restrict__ g = a.gray + (long long)b * a.P;
 
@@ -686,7 +687,7 @@ int launch_edt_rows(dvo_ctx* c, int first, int count) {
 //   solver does a single 128-bit gather per reprojected point; w = getWeightOf(DTn) (src/SolveDVO.cpp:1047-1053)
 //   is a function of the pixel alone, so it is evaluated once here instead of once per point and iteration.
 // =====================================================================================================
-struct NormArgs { const int32_t* d2; float4* texel; const unsigned* maxd2; const unsigned* nedge; int w, h, P, L, first; };
+struct NormArgs { const int32_t* d2; float4* texel; const unsigned* maxd2; const unsigned* nedge; int w, h, P, L, first; long long out_stride; };
 
 // One CTA = one 32x32 pixel tile: DTn is computed once per pixel (plus a one-pixel halo) into shared memory, the
 // central differences are taken from the tile, and each warp stores 32 consecutive 16-byte texels (512 B) per row.
@@ -721,7 +722,7 @@ __global__ void __launch_bounds__(256) normgrad_kernel(NormArgs a) {
     const int tx = threadIdx.x & 31;
     const int x = x0 + tx;
     if (x >= w) return;
-    float4* __restrict__ out = a.texel + (long long)b * a.P;
+    float4* __restrict__ out = a.texel + (long long)b * a.out_stride;
     for (int ty = threadIdx.x >> 5; ty < 32; ty += 8) {
         const int y = y0 + ty;
         if (y >= h) break;
@@ -740,12 +741,78 @@ int launch_normgrad(dvo_ctx* c, int first, int count) {
     for (int l = 0; l < g.L; ++l) {
         NormArgs a; a.d2 = c->d2 + g.off[l]; a.texel = c->texel + g.off[l]; a.maxd2 = c->maxd2 + l;
         a.nedge = c->nedge + (size_t)DVO_FRAME_NOW * g.Bmax * g.L + l;
-        a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L; a.first = first;
+        a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L; a.first = first; a.out_stride = g.P[l];
         for (int z0 = 0; z0 < count; z0 += 32768) {          // gridDim.z limit is 65535
             NormArgs az = a; az.first = first + z0;
             const int nz = (count - z0 < 32768) ? count - z0 : 32768;
             dim3 grid((g.w[l] + 31) / 32, (g.h[l] + 31) / 32, nz);
             normgrad_kernel<<<grid, 256, 0, c->stream>>>(az);
+            c->launches++;
+        }
+    }
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}
+
+// inspection (dvo_get_level_buffer DTN / GX / GY): the float images of one slot / level into a temporary buffer
+int launch_normgrad_into(dvo_ctx* c, int slot, int level, float4* d_out) {
+    const PyrGeom& g = c->geom;
+    const int l = level;
+    NormArgs a; a.d2 = c->d2 + g.off[l]; a.texel = d_out; a.maxd2 = c->maxd2 + l;
+    a.nedge = c->nedge + (size_t)DVO_FRAME_NOW * g.Bmax * g.L + l;
+    a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L; a.first = slot; a.out_stride = 0;
+    dim3 grid((g.w[l] + 31) / 32, (g.h[l] + 31) / 32, 1);
+    normgrad_kernel<<<grid, 256, 0, c->stream>>>(a);
+    c->launches++;
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}
+
+// =====================================================================================================
+// packed texels (common.cuh "packed texel"): the exact d2 of every pixel and of its four stencil neighbours in 8 bytes,
+// stored in 4x4 Morton tiles.  Replaces normgrad_kernel on the hot path: 4 B read + 8 B written per pixel instead of
+// 4 + 16, and the solver's working set per reprojected point shrinks from a 16-byte texel in an 8x1-pixel line to an
+// 8-byte texel in a 4x4-pixel line.  DTn / gradient / weight are evaluated in the solver from per-level lookup tables
+// with the same IEEE operations normgrad_kernel uses, so every value stays bit-identical.
+// Thread <-> texel of the blocked layout (stores are contiguous); the five d2 loads hit L1 / L2.
+// =====================================================================================================
+struct PackArgs { const int32_t* d2; uint2* tex8; int w, h, P, Pt, tw, first; };
+
+__global__ void __launch_bounds__(256) pack_texel_kernel(PackArgs a) {
+    const int b = a.first + blockIdx.y;
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= a.Pt) return;
+    const int tile = i >> 4, k = i & 15;
+    const int ty = tile / a.tw, tx = tile - ty * a.tw;
+    const int y = (ty << 2) | ((k >> 2) & 2) | ((k >> 1) & 1);
+    const int x = (tx << 2) | ((k >> 1) & 2) | (k & 1);
+    const int w = a.w, h = a.h;
+    uint2 out = make_uint2(DVO_TEX_ESCAPE, 0u);
+    if (x < w && y < h) {
+        const int32_t* __restrict__ d = a.d2 + (long long)b * a.P + (long long)y * w + x;
+        const int c = __ldg(d);
+        const bool bx = (x == 0 || x == w - 1), by = (y == 0 || y == h - 1);
+        const int dl = bx ? 0 : __ldg(d - 1) - c, dr = bx ? 0 : __ldg(d + 1) - c;
+        const int du = by ? 0 : __ldg(d - w) - c, dd = by ? 0 : __ldg(d + w) - c;
+        const int lo = min(min(dl, dr), min(du, dd)), hi = max(max(dl, dr), max(du, dd));
+        if (c < 65536 && lo >= -512 && hi <= 511) {
+            out.x = (unsigned)c | (((unsigned)dl & 0x3FFu) << 16);
+            out.y = ((unsigned)dr & 0x3FFu) | (((unsigned)du & 0x3FFu) << 10) | (((unsigned)dd & 0x3FFu) << 20);
+        }
+    }
+    a.tex8[(long long)b * a.Pt + i] = out;
+}
+
+int launch_pack(dvo_ctx* c, int first, int count) {
+    const PyrGeom& g = c->geom;
+    for (int l = 0; l < g.L; ++l) {
+        PackArgs a; a.d2 = c->d2 + g.off[l]; a.tex8 = c->tex8 + g.offt[l];
+        a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.Pt = g.Pt[l]; a.tw = g.tw[l];
+        for (int z0 = 0; z0 < count; z0 += 32768) {          // gridDim.y limit is 65535
+            a.first = first + z0;
+            const int nz = (count - z0 < 32768) ? count - z0 : 32768;
+            dim3 grid((g.Pt[l] + 255) / 256, nz);
+            pack_texel_kernel<<<grid, 256, 0, c->stream>>>(a);
             c->launches++;
         }
     }

@@ -145,7 +145,73 @@ __device__ __forceinline__ bool chol6_dev(const double* H, const double* b, doub
 
 // ------------------------------------------------------------------ per-point evaluation
 struct PoseF { float R[9], T[3]; };
-struct LevelCam { float M00, M02, M11, M12; int w, h; float wf, hf, M00_lo, M11_lo; };
+struct LevelCam { float M00, M02, M11, M12; int w, h; float wf, hf, M00_lo, M11_lo; int tw; };
+
+// Where the solver reads the now frame's distance transform from.
+//   TEX = 1 (default): packed 8-byte texels (common.cuh) + per-level lookup tables in shared memory
+//                      lut[d2] = DTn = sqrtf(d2) * scale, lut[LUT_N + d2] = getWeightOf(DTn), d2 < LUT_N; larger d2 (a
+//                      point more than 63 pixels from every edge) are evaluated directly with the same operations.
+//   TEX = 0: legacy float4 texels {DTn, gx, gy, w} written by normgrad_kernel.
+constexpr int LUT_N = 4096;
+struct TexSrc {
+    const float4* tex;       // TEX 0: level / slot base
+    const uint2* tex8;       // TEX 1: level / slot base
+    const int32_t* d2;       // TEX 1: row-major d2 of the level / slot (escaped texels only)
+    const float* lut;        // TEX 1: shared-memory tables
+    float scale;             // TEX 1: (float)(255 / sqrt(max d2))
+};
+
+// normalize(0,255,MINMAX) scale of one now-frame level image (src/SolveDVO.cpp:1774), as normgrad_kernel computes it
+__device__ __forceinline__ float dtn_scale(unsigned mx2, unsigned ne) {
+    if (ne == 0u) return 0.0f;
+    const double smax = (double)__fsqrt_rn((float)mx2);          // smin = 0 whenever an edge exists
+    const double sc = 255.0 * ((smax > 2.220446049250313e-16) ? __ddiv_rn(1.0, smax) : 0.0);
+    return __double2float_rn(sc);
+}
+__device__ __forceinline__ float dtn_direct(int d2, float scale) { return __fmul_rn(__fsqrt_rn((float)d2), scale); }
+
+template <int THREADS>
+__device__ __forceinline__ void build_lut(float* lut, unsigned mx2, float scale) {
+    const int n = (int)min(mx2, (unsigned)(LUT_N - 1));
+    for (int i = threadIdx.x; i <= n; i += THREADS) {
+        const float v = dtn_direct(i, scale);
+        lut[i] = v; lut[LUT_N + i] = Ar<DVO_ARITH_EXACT>::weight_ref(v);
+    }
+}
+
+// the five d2 values of a packed texel; false when the texel is escaped
+struct Stencil { int c, l, r, u, d; };
+__device__ __forceinline__ bool unpack_texel(const uint2 t, Stencil& s) {
+    s.c = (int)(t.x & 0xFFFFu);
+    s.l = s.c + ((int)(t.x << 6) >> 22);
+    s.r = s.c + ((int)(t.y << 22) >> 22);
+    s.u = s.c + ((int)(t.y << 12) >> 22);
+    s.d = s.c + ((int)(t.y << 2) >> 22);
+    return (int)t.x >= 0;
+}
+__device__ __noinline__ void stencil_from_d2(const int32_t* __restrict__ d2, int w, int h, int x, int y, Stencil& s) {
+    const int32_t* d = d2 + y * w + x;
+    s.c = __ldg(d);
+    const bool bx = (x == 0 || x == w - 1), by = (y == 0 || y == h - 1);
+    s.l = bx ? s.c : __ldg(d - 1); s.r = bx ? s.c : __ldg(d + 1);
+    s.u = by ? s.c : __ldg(d - w); s.d = by ? s.c : __ldg(d + w);
+}
+// {DTn, gx, gy, getWeightOf(DTn)} of the pixel: the float4 normgrad_kernel would have written, bit for bit
+__device__ __forceinline__ float4 texel_values(const Stencil& s, const float* __restrict__ lut, float scale) {
+    float c, l, r, u, d, wt;
+    if (max(max(max(s.c, s.l), max(s.r, s.u)), s.d) < LUT_N) {
+        c = lut[s.c]; l = lut[s.l]; r = lut[s.r]; u = lut[s.u]; d = lut[s.d]; wt = lut[LUT_N + s.c];
+    } else {
+        c = dtn_direct(s.c, scale); l = dtn_direct(s.l, scale); r = dtn_direct(s.r, scale);
+        u = dtn_direct(s.u, scale); d = dtn_direct(s.d, scale); wt = Ar<DVO_ARITH_EXACT>::weight_ref(c);
+    }
+    float4 t;
+    t.x = c;
+    t.y = __fadd_rn(__fmul_rn(-0.5f, l), __fmul_rn(0.5f, r));
+    t.z = __fadd_rn(__fmul_rn(-0.5f, u), __fmul_rn(0.5f, d));
+    t.w = wt;
+    return t;
+}
 
 // Z = p'_z * RN(1/p'_z) (:339-341) can only round to 1 or to the float just below 1 (the reciprocal is correctly
 // rounded, so the product lies within 2^-24 of 1).  The four IEEE divisions of the reference's A1 matrix (:388-393)
@@ -161,6 +227,7 @@ __device__ __forceinline__ LevelCam make_level_cam(const Intr& K, const PyrGeom&
     cam.w = geom.w[l]; cam.h = geom.h[l]; cam.wf = (float)cam.w; cam.hf = (float)cam.h;
     cam.M00_lo = __fdiv_rn(cam.M00, __int_as_float(DVO_Z_BELOW_ONE));
     cam.M11_lo = __fdiv_rn(cam.M11, __int_as_float(DVO_Z_BELOW_ONE));
+    cam.tw = geom.tw[l];
     return cam;
 }
 
@@ -168,6 +235,7 @@ __device__ __forceinline__ LevelCam make_level_cam(const Intr& K, const PyrGeom&
 // idx < 0 when the reprojection falls outside the now image (J = eps = w = 0, :371-374).
 struct Proj { float px, py, pz, inv, X, Y, Z, u, v; int idx; };
 
+template <int TEX>
 __device__ __forceinline__ Proj project_point(float Xp, float Yp, float Zp, const PoseF& P, const LevelCam& cam) {
     typedef Ar<DVO_ARITH_EXACT> E;   // always IEEE-exact so that FAST arithmetic gathers the same texel
     const float* R = P.R;
@@ -182,7 +250,8 @@ __device__ __forceinline__ Proj project_point(float Xp, float Yp, float Zp, cons
     o.u = E::dot2(cam.M00, o.X, cam.M02, o.Z);                                   // :344
     o.v = E::dot2(cam.M11, o.Y, cam.M12, o.Z);
     const bool vis = (o.u >= 0.0f && o.u < cam.wf && o.v >= 0.0f && o.v < cam.hf);
-    o.idx = vis ? __float2int_rz(o.v) * cam.w + __float2int_rz(o.u) : -1;        // :376-377
+    if (TEX) o.idx = vis ? tex_index(__float2int_rz(o.u), __float2int_rz(o.v), cam.tw) : -1;
+    else o.idx = vis ? __float2int_rz(o.v) * cam.w + __float2int_rz(o.u) : -1;   // :376-377
     return o;
 }
 
@@ -231,16 +300,46 @@ __device__ __forceinline__ void finish_point(const Proj& q, const float4 t, cons
     else wgt = 1.0f;
 }
 
+// raw gathered texel of either flavour, and its resolution to {DTn, gx, gy, w}
+template <int TEX> struct Texel;
+template <> struct Texel<0> {
+    typedef float4 T;
+    static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    static __device__ __forceinline__ T load(const TexSrc& S, int idx) { return __ldg(S.tex + idx); }
+    static __device__ __forceinline__ float4 resolve(const TexSrc&, const LevelCam&, const Proj&, const T raw) { return raw; }
+};
+template <> struct Texel<1> {
+    typedef uint2 T;
+    static __device__ __forceinline__ T zero() { return make_uint2(0u, 0u); }
+    static __device__ __forceinline__ T load(const TexSrc& S, int idx) { return __ldg(S.tex8 + idx); }
+    static __device__ __forceinline__ float4 resolve(const TexSrc& S, const LevelCam& cam, const Proj& q, const T raw) {
+        Stencil s;
+        if (!unpack_texel(raw, s)) stencil_from_d2(S.d2, cam.w, cam.h, __float2int_rz(q.u), __float2int_rz(q.v), s);
+        return texel_values(s, S.lut, S.scale);
+    }
+};
+
+// DTn of pixel (x, y)
+template <int TEX>
+__device__ __forceinline__ float dtn_at(const TexSrc& S, const LevelCam& cam, int x, int y) {
+    if (!TEX) return __ldg(&S.tex[y * cam.w + x].x);
+    const unsigned w0 = __ldg(&S.tex8[tex_index(x, y, cam.tw)].x);
+    int d2 = (int)(w0 & 0xFFFFu);
+    if ((int)w0 < 0) d2 = __ldg(S.d2 + y * cam.w + x);
+    return d2 < LUT_N ? S.lut[d2] : dtn_direct(d2, S.scale);
+}
+
 // SolveDVO::interpolate (src/SolveDVO.cpp:1285-1308) at the reprojection (v = row, u = column): "squared-bilinear"
-// lookup of the normalised DT (texel.x), fp32, products left to right; ceil indices clamped to the image (the
-// reference would trip its own bound assert there).  Three extra 4-byte gathers next to the texel already fetched.
-__device__ __forceinline__ float interpolate_dt(const float4* __restrict__ tex, const LevelCam& cam, const Proj& q, float Fdd) {
+// lookup of the normalised DT, fp32, products left to right; ceil indices clamped to the image (the reference would
+// trip its own bound assert there).  Three extra gathers next to the texel already fetched.
+template <int TEX>
+__device__ __forceinline__ float interpolate_dt(const TexSrc& S, const LevelCam& cam, const Proj& q, float Fdd) {
     const int rx_d = __float2int_rz(q.u), ry_d = __float2int_rz(q.v);               // u, v >= 0 here: floor == trunc
     const float fx_d = (float)rx_d, fy_d = (float)ry_d;
     const float inc_x = __fsub_rn(q.u, fx_d), inc_y = __fsub_rn(q.v, fy_d);
     const int rx_u = min(rx_d + (q.u > fx_d ? 1 : 0), cam.w - 1), ry_u = min(ry_d + (q.v > fy_d ? 1 : 0), cam.h - 1);
-    const float Fdu = __ldg(&tex[ry_d * cam.w + rx_u].x);
-    const float Fud = __ldg(&tex[ry_u * cam.w + rx_d].x), Fuu = __ldg(&tex[ry_u * cam.w + rx_u].x);
+    const float Fdu = dtn_at<TEX>(S, cam, rx_u, ry_d);
+    const float Fud = dtn_at<TEX>(S, cam, rx_d, ry_u), Fuu = dtn_at<TEX>(S, cam, rx_u, ry_u);
     const float ax = __fsub_rn(1.0f, inc_x), ay = __fsub_rn(1.0f, inc_y);
     const float f1 = __fsqrt_rn(__fadd_rn(__fmul_rn(__fmul_rn(ax, Fdd), Fdd), __fmul_rn(__fmul_rn(inc_x, Fdu), Fdu)));
     const float f2 = __fsqrt_rn(__fadd_rn(__fmul_rn(__fmul_rn(ax, Fud), Fud), __fmul_rn(__fmul_rn(inc_x, Fuu), Fuu)));
@@ -252,21 +351,22 @@ template <bool NEED_H> struct AccN { static constexpr int N = NEED_H ? 29 : 8; }
 
 // Software-pipelined sweep over a thread's points: the coordinates are loaded two points ahead and the (random)
 // texel gather of the next point is in flight while the current point's Jacobian / fp64 accumulation executes.
-template <int ARITH, int JAC, bool NEED_H, int THREADS, bool OUT, int RES = DVO_RESIDUAL_DT_FLOOR>
+template <int ARITH, int JAC, bool NEED_H, int THREADS, bool OUT, int RES, int TEX>
 __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, const float* __restrict__ Y,
                                                   const float* __restrict__ Z, int N, const PoseF& P, const LevelCam& cam,
-                                                  const float4* __restrict__ tex, int weight_mode, float huber_k,
+                                                  const TexSrc& S, int weight_mode, float huber_k,
                                                   double* acc, int& nvis, float* o_eps, float* o_w, float* o_u, float* o_v,
                                                   float* o_J) {
     constexpr int stride = THREADS;
     const int start = threadIdx.x;
     typedef Ar<ARITH> A;
+    typedef Texel<TEX> TX;
     int i = start;
     if (i >= N) return;
     float cx = __ldg(X + i), cy = __ldg(Y + i), cz = __ldg(Z + i);
-    Proj q = project_point(cx, cy, cz, P, cam);
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (q.idx >= 0) t = __ldg(tex + q.idx);
+    Proj q = project_point<TEX>(cx, cy, cz, P, cam);
+    typename TX::T t = TX::zero();
+    if (q.idx >= 0) t = TX::load(S, q.idx);
     int i1 = i + stride;
     if (i1 < N) { cx = __ldg(X + i1); cy = __ldg(Y + i1); cz = __ldg(Z + i1); }
     for (;;) {
@@ -274,14 +374,15 @@ __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, c
         float nx = 0.f, ny = 0.f, nz = 1.f;
         if (i2 < N) { nx = __ldg(X + i2); ny = __ldg(Y + i2); nz = __ldg(Z + i2); }       // coordinates two ahead
         Proj qn; qn.idx = -1;
-        float4 tn = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i1 < N) { qn = project_point(cx, cy, cz, P, cam); if (qn.idx >= 0) tn = __ldg(tex + qn.idx); }   // gather one ahead
+        typename TX::T tn = TX::zero();
+        if (i1 < N) { qn = project_point<TEX>(cx, cy, cz, P, cam); if (qn.idx >= 0) tn = TX::load(S, qn.idx); }   // gather one ahead
         // ---- consume point i
         float Jr[6], e = 0.f, wgt = 0.f;
         if (q.idx >= 0) {
-            finish_point<ARITH, JAC>(q, t, P, cam, weight_mode, huber_k, Jr, e, wgt);
+            const float4 tv = TX::resolve(S, cam, q, t);
+            finish_point<ARITH, JAC>(q, tv, P, cam, weight_mode, huber_k, Jr, e, wgt);
             if (RES == DVO_RESIDUAL_DT_INTERP) {                                     // :443-444, weight from the interpolated value (:450)
-                e = interpolate_dt(tex, cam, q, t.x);
+                e = interpolate_dt<TEX>(S, cam, q, tv.x);
                 if (weight_mode == DVO_WEIGHT_REF_CAUCHY) wgt = A::weight_ref(e);
                 else if (weight_mode == DVO_WEIGHT_HUBER) { const float ae = fabsf(e); wgt = ae <= huber_k ? 1.0f : A::div(huber_k, ae); }
             }
@@ -384,6 +485,7 @@ struct SolverState {
 struct SolveArgs {
     PyrGeom geom; Intr K;
     const float *X, *Y, *Z; const int* npts; const unsigned* nedge_now; const float4* texel;
+    const uint2* tex8; const int32_t* d2; const unsigned* maxd2;
     const double* pose0; double* pose; dvo_pair_info* info; double* trace; int trace_iters; const int* order; const unsigned char* active;
     dvo_solver_params prm; int first;
 };
@@ -495,8 +597,9 @@ __global__ void __launch_bounds__(1024) solve_order_kernel(const int* __restrict
 // pair's points over 2/4/8 CTAs and combined partial sums through distributed shared memory was measured slower --
 // 4.29 ms -> 4.58 / 5.53 / 8.62 ms per 1024 pairs -- and removed; so was a cp.async shared-memory ring that kept 2..8
 // texel gathers in flight per thread: 4.56 .. 4.72 ms.  See DESIGN.md "measured and rejected".)
-template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES>
+template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX>
 __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve_kernel(SolveArgs a) {
+    extern __shared__ float s_lut[];          // TEX 1: 2 * LUT_N floats
     constexpr int NACC = AccN<NEED_H>::N;
     constexpr int SOLVE_WARPS = THREADS / 32;
     __shared__ double s_scr[SOLVE_WARPS * ReduceScratch<NACC>::PER_WARP];
@@ -531,8 +634,14 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
         if (N <= 0 || ne == 0u) { if (lead) s_info.status |= 1; continue; }                  // reference asserts (:282)
         const long long base = lvl_at(a.geom, l, b);
         const float* X = a.X + base; const float* Y = a.Y + base; const float* Z = a.Z + base;
-        const float4* tex = a.texel + base;
         const LevelCam cam = make_level_cam(a.K, a.geom, l);
+        TexSrc src;
+        src.tex = a.texel + base; src.tex8 = a.tex8 + tex_at(a.geom, l, b); src.d2 = a.d2 + base; src.lut = s_lut; src.scale = 0.f;
+        if (TEX) {
+            const unsigned mx2 = a.maxd2[(long long)b * L + l];
+            src.scale = dtn_scale(mx2, ne);
+            build_lut<THREADS>(s_lut, mx2, src.scale);       // visible after the barrier below
+        }
         if (lead) {
             S.bestE = 1.0E10f; S.bestRatio = 1.0f; S.bestItr = -1; S.bestSumEps = 0.0;        // :642-650
             for (int k = 0; k < 9; ++k) S.bestR[k] = (k % 4 == 0) ? 1.0 : 0.0;
@@ -550,7 +659,7 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
 #pragma unroll
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
             int nvis = 0;
-            accumulate_points<ARITH, JAC, NEED_H, THREADS, false, RES>(X, Y, Z, N, P, cam, tex, a.prm.weight, a.prm.huber_k, acc, nvis,
+            accumulate_points<ARITH, JAC, NEED_H, THREADS, false, RES, TEX>(X, Y, Z, N, P, cam, src, a.prm.weight, a.prm.huber_k, acc, nvis,
                                                   nullptr, nullptr, nullptr, nullptr, nullptr);
             block_reduce<NACC, THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
             if (lead) {
@@ -584,13 +693,15 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
 struct EvalArgs {
     PyrGeom geom; Intr K;
     const float *X, *Y, *Z; const int* npts; const float4* texel;
+    const uint2* tex8; const int32_t* d2; const unsigned* maxd2; const unsigned* nedge_now;
     const double* pose; int slot, level, weight; float huber_k;
     double* out;            // g[6], H[36], sumsq, nvis
     float *eps, *w, *u, *v, *J;
 };
 
-template <int ARITH, int JAC, int RES>
+template <int ARITH, int JAC, int RES, int TEX>
 __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
+    extern __shared__ float s_lut[];
     constexpr int NACC = AccN<true>::N;
     constexpr int SOLVE_WARPS = EVAL_THREADS / 32;
     __shared__ double s_scr[SOLVE_WARPS * ReduceScratch<NACC>::PER_WARP];
@@ -605,11 +716,19 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
     for (int k = 0; k < 9; ++k) P.R[k] = (float)a.pose[k];
     for (int k = 0; k < 3; ++k) P.T[k] = (float)a.pose[9 + k];
     const LevelCam cam = make_level_cam(a.K, a.geom, l);
+    TexSrc src;
+    src.tex = a.texel + base; src.tex8 = a.tex8 + tex_at(a.geom, l, b); src.d2 = a.d2 + base; src.lut = s_lut; src.scale = 0.f;
+    if (TEX) {
+        const unsigned mx2 = a.maxd2[(long long)b * L + l];
+        src.scale = dtn_scale(mx2, a.nedge_now[(long long)b * L + l]);
+        build_lut<EVAL_THREADS>(s_lut, mx2, src.scale);
+        __syncthreads();
+    }
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     int nvis = 0;
-    accumulate_points<ARITH, JAC, true, EVAL_THREADS, true, RES>(a.X + base, a.Y + base, a.Z + base, N, P, cam, a.texel + base, a.weight, a.huber_k,
+    accumulate_points<ARITH, JAC, true, EVAL_THREADS, true, RES, TEX>(a.X + base, a.Y + base, a.Z + base, N, P, cam, src, a.weight, a.huber_k,
                                         acc, nvis, a.eps, a.w, a.u, a.v, a.J);
     block_reduce<NACC, EVAL_THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
     if (threadIdx.x == 0) {
@@ -642,40 +761,69 @@ __global__ void gop_kernel(int nseq, int nframes, const int* __restrict__ kind, 
 
 }  // namespace
 
-template <int ARITH, int JAC>
+// Kernels that use the lookup tables need 32 KB of dynamic shared memory on top of their static reduction scratch:
+// opt in once per kernel and device.
+constexpr int LUT_BYTES = 2 * LUT_N * (int)sizeof(float);
+template <typename KArgs, void (*KERN)(KArgs)>
+static cudaError_t optin_lut_smem(int device) {
+    static unsigned long long done = 0ull;
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done & bit) return cudaSuccess;
+    const cudaError_t e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_BYTES);
+    if (e == cudaSuccess) done |= bit;
+    return e;
+}
+
+template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX>
+static cudaError_t launch_solve_inst(dvo_ctx* c, const SolveArgs& a, int count) {
+    if (TEX) {
+        const cudaError_t e = optin_lut_smem<SolveArgs, solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX>>(c->cfg.device);
+        if (e != cudaSuccess) return e;
+    }
+    solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX><<<count, THREADS, TEX ? LUT_BYTES : 0, c->stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <int ARITH, int JAC, int TEX>
 static cudaError_t launch_solve_t(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
     constexpr int THREADS = 256;
     constexpr int F = DVO_RESIDUAL_DT_FLOOR, I = DVO_RESIDUAL_DT_INTERP;
     if (a.prm.residual == I) {
         if (ARITH != DVO_ARITH_EXACT) return cudaErrorNotSupported;      // the interpolated variant is built for EXACT arithmetic only
-        if (need_h) solve_kernel<DVO_ARITH_EXACT, JAC, true, THREADS, I><<<count, THREADS, 0, c->stream>>>(a);
-        else solve_kernel<DVO_ARITH_EXACT, JAC, false, THREADS, I><<<count, THREADS, 0, c->stream>>>(a);
-    } else {
-        // Up to one pair per SM there is nothing to overlap a CTA with, so a pair gets 512 threads: the sweeps run twice as
-        // wide and a pair's latency drops by a third (148 pairs, GN: 0.91 -> 0.62 ms).  At full load the two shapes tie
-        // (3.76 vs 3.80 ms per 1024 pairs), so larger launches keep two 256-thread CTAs per SM.
-        const bool wide = (ARITH == DVO_ARITH_EXACT) && count <= c->sm_count;
-        if (wide && need_h) solve_kernel<DVO_ARITH_EXACT, JAC, true, 512, F><<<count, 512, 0, c->stream>>>(a);
-        else if (wide) solve_kernel<DVO_ARITH_EXACT, JAC, false, 512, F><<<count, 512, 0, c->stream>>>(a);
-        else if (need_h) solve_kernel<ARITH, JAC, true, THREADS, F><<<count, THREADS, 0, c->stream>>>(a);
-        else solve_kernel<ARITH, JAC, false, THREADS, F><<<count, THREADS, 0, c->stream>>>(a);
+        if (need_h) return launch_solve_inst<DVO_ARITH_EXACT, JAC, true, THREADS, I, TEX>(c, a, count);
+        return launch_solve_inst<DVO_ARITH_EXACT, JAC, false, THREADS, I, TEX>(c, a, count);
     }
-    return cudaGetLastError();
+    // Up to one pair per SM there is nothing to overlap a CTA with, so a pair gets 512 threads: the sweeps run twice as
+    // wide and a pair's latency drops by a third (148 pairs, GN: 0.91 -> 0.62 ms).  At full load the two shapes tie
+    // (3.76 vs 3.80 ms per 1024 pairs), so larger launches keep two 256-thread CTAs per SM.
+    // The shape is fixed per context (dvo_create: max_batch <= SM count -> 512), never per launch: the two shapes group the
+    // fp64 partial sums differently, and a pair's pose must not depend on how many pairs happen to share a launch.
+    const bool wide = (ARITH == DVO_ARITH_EXACT) && c->solve_shape == 512;
+    if (wide && need_h) return launch_solve_inst<DVO_ARITH_EXACT, JAC, true, 512, F, TEX>(c, a, count);
+    if (wide) return launch_solve_inst<DVO_ARITH_EXACT, JAC, false, 512, F, TEX>(c, a, count);
+    if (need_h) return launch_solve_inst<ARITH, JAC, true, THREADS, F, TEX>(c, a, count);
+    return launch_solve_inst<ARITH, JAC, false, THREADS, F, TEX>(c, a, count);
+}
+
+template <int TEX>
+static cudaError_t launch_solve_tex(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
+    const int ar = a.prm.arithmetic == DVO_ARITH_FAST ? DVO_ARITH_FAST : DVO_ARITH_EXACT;
+    const int jc = a.prm.jacobian == DVO_JAC_EXACT ? DVO_JAC_EXACT : DVO_JAC_REFERENCE;
+    if (ar == DVO_ARITH_EXACT && jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_REFERENCE, TEX>(c, a, count, need_h);
+    if (ar == DVO_ARITH_EXACT) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_EXACT, TEX>(c, a, count, need_h);
+    if (jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_REFERENCE, TEX>(c, a, count, need_h);
+    return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_EXACT, TEX>(c, a, count, need_h);
 }
 
 static cudaError_t launch_solve_any(dvo_ctx* c, const SolveArgs& a, int count, bool need_h) {
-    const int ar = a.prm.arithmetic == DVO_ARITH_FAST ? DVO_ARITH_FAST : DVO_ARITH_EXACT;
-    const int jc = a.prm.jacobian == DVO_JAC_EXACT ? DVO_JAC_EXACT : DVO_JAC_REFERENCE;
-    if (ar == DVO_ARITH_EXACT && jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_REFERENCE>(c, a, count, need_h);
-    if (ar == DVO_ARITH_EXACT) return launch_solve_t<DVO_ARITH_EXACT, DVO_JAC_EXACT>(c, a, count, need_h);
-    if (jc == DVO_JAC_REFERENCE) return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_REFERENCE>(c, a, count, need_h);
-    return launch_solve_t<DVO_ARITH_FAST, DVO_JAC_EXACT>(c, a, count, need_h);
+    return c->texel_mode ? launch_solve_tex<1>(c, a, count, need_h) : launch_solve_tex<0>(c, a, count, need_h);
 }
 
 int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
     SolveArgs a;
     a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts;
     a.nedge_now = c->nedge + (size_t)DVO_FRAME_NOW * c->geom.Bmax * c->geom.L; a.texel = c->texel;
+    a.tex8 = c->tex8; a.d2 = c->d2; a.maxd2 = c->maxd2;
     a.pose0 = c->pose0; a.pose = c->pose; a.info = c->info; a.trace = c->trace; a.trace_iters = c->cfg.trace_iters;
     a.prm = *p; a.first = first;
     // H is needed by GN / LM, and by SUBGRAD_REF only when a trace is kept (parity tests on J^T W J)
@@ -691,25 +839,41 @@ int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
     return DVO_OK;
 }
 
+template <int ARITH, int JAC, int RES, int TEX>
+static cudaError_t launch_eval_inst(dvo_ctx* c, const EvalArgs& a) {
+    if (TEX) {
+        const cudaError_t e = optin_lut_smem<EvalArgs, eval_kernel<ARITH, JAC, RES, TEX>>(c->cfg.device);
+        if (e != cudaSuccess) return e;
+    }
+    eval_kernel<ARITH, JAC, RES, TEX><<<1, EVAL_THREADS, TEX ? LUT_BYTES : 0, c->stream>>>(a);
+    return cudaGetLastError();
+}
+
+template <int TEX>
+static int launch_eval_tex(dvo_ctx* c, const EvalArgs& a, int jac, int arith, int residual) {
+    const bool ex = arith != DVO_ARITH_FAST, rj = jac != DVO_JAC_EXACT;
+    constexpr int F = DVO_RESIDUAL_DT_FLOOR, I = DVO_RESIDUAL_DT_INTERP;
+    cudaError_t e;
+    if (residual == I) {
+        if (!ex) { dvo_set_error("the interpolated-DT residual is built for EXACT arithmetic only"); return DVO_ERR_ARG; }
+        e = rj ? launch_eval_inst<DVO_ARITH_EXACT, DVO_JAC_REFERENCE, I, TEX>(c, a) : launch_eval_inst<DVO_ARITH_EXACT, DVO_JAC_EXACT, I, TEX>(c, a);
+    } else if (ex && rj) e = launch_eval_inst<DVO_ARITH_EXACT, DVO_JAC_REFERENCE, F, TEX>(c, a);
+    else if (ex) e = launch_eval_inst<DVO_ARITH_EXACT, DVO_JAC_EXACT, F, TEX>(c, a);
+    else if (rj) e = launch_eval_inst<DVO_ARITH_FAST, DVO_JAC_REFERENCE, F, TEX>(c, a);
+    else e = launch_eval_inst<DVO_ARITH_FAST, DVO_JAC_EXACT, F, TEX>(c, a);
+    c->launches++;
+    DVO_CUDA(e);
+    return DVO_OK;
+}
+
 int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k, int residual,
                 double* d_out, float* d_eps, float* d_w, float* d_u, float* d_v, float* d_J) {
     EvalArgs a;
     a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts; a.texel = c->texel;
+    a.tex8 = c->tex8; a.d2 = c->d2; a.maxd2 = c->maxd2; a.nedge_now = c->nedge + (size_t)DVO_FRAME_NOW * c->geom.Bmax * c->geom.L;
     a.pose = d_pose12; a.slot = slot; a.level = level; a.weight = weight; a.huber_k = huber_k; a.out = d_out;
     a.eps = d_eps; a.w = d_w; a.u = d_u; a.v = d_v; a.J = d_J;
-    const bool ex = arith != DVO_ARITH_FAST, rj = jac != DVO_JAC_EXACT;
-    constexpr int F = DVO_RESIDUAL_DT_FLOOR, I = DVO_RESIDUAL_DT_INTERP;
-    if (residual == I) {
-        if (!ex) { dvo_set_error("the interpolated-DT residual is built for EXACT arithmetic only"); return DVO_ERR_ARG; }
-        if (rj) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_REFERENCE, I><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-        else eval_kernel<DVO_ARITH_EXACT, DVO_JAC_EXACT, I><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-    } else if (ex && rj) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_REFERENCE, F><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-    else if (ex) eval_kernel<DVO_ARITH_EXACT, DVO_JAC_EXACT, F><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-    else if (rj) eval_kernel<DVO_ARITH_FAST, DVO_JAC_REFERENCE, F><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-    else eval_kernel<DVO_ARITH_FAST, DVO_JAC_EXACT, F><<<1, EVAL_THREADS, 0, c->stream>>>(a);
-    c->launches++;
-    DVO_CUDA(cudaGetLastError());
-    return DVO_OK;
+    return c->texel_mode ? launch_eval_tex<1>(c, a, jac, arith, residual) : launch_eval_tex<0>(c, a, jac, arith, residual);
 }
 
 int launch_gop(dvo_ctx* c, int nseq, int nframes, const int* d_kind, const double* d_rel, double* d_out) {
