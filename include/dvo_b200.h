@@ -117,6 +117,12 @@ int dvo_set_intrinsics(dvo_ctx* ctx, float fx, float fy, float cx, float cy);
  * (src/SolveDVO.cpp:490-614).  Full-resolution images; the pyramid is built by dvo_build_pyramids.
  * depth may be NULL for the now frame (the edge solver never reads it). */
 int dvo_set_frames(dvo_ctx* ctx, int frame, int first, int count, const uint8_t* gray, const uint16_t* depth, int mem);
+/* The same ingest from the RAW sensor frames the pyramid publisher receives (src/camTopic2PublisherPyD.cpp:65-80, :338-348):
+ * bgr = u8 HWC (cv_bridge "bgr8"), depth_m = f32 metres (32FC1).  One fused kernel applies depth16 = saturate_u16(cvRound(
+ * 1000.0f * depth)), 0 -> 1 (:75-78) and framemono = cvtColor(BGR2GRAY) (:347; OpenCV 4 fixed point, (B*3735 + G*19235 +
+ * R*9798 + 2^14) >> 15) straight into the level-0 regions; the publisher's per-level gray equals the NEAREST level of this
+ * full-resolution gray because BGR2GRAY is per pixel.  depth_m may be NULL where dvo_set_frames allows depth == NULL. */
+int dvo_set_frames_raw(dvo_ctx* ctx, int frame, int first, int count, const uint8_t* bgr, const float* depth_m, int mem);
 /* SolveDVO::setPrevFrameAsRefFrame (src/SolveDVO.cpp:561-584): the PREVIOUS now frame of every slot (p_now_*, kept on the
  * device by dvo_set_frames(NOW) when keep_now_depth = 1) becomes its reference frame's level 0; follow with
  * dvo_build_pyramids(.., 1) and dvo_prepare(.., 1) as the reference does. */
@@ -187,6 +193,13 @@ int dvo_run_sequences_gated(dvo_ctx* ctx, int nseq, int nframes, const uint8_t* 
                             const dvo_solver_params* params, const dvo_keyframe_policy* policy, double* rel_poses, int* kind,
                             int* reason, double* global_poses);
 
+/* Both loops above with the INPUT sequences in host (DVO_MEM_HOST; pinned memory makes the uploads asynchronous) or device
+ * memory (DVO_MEM_DEVICE).  Host inputs are pipelined: frame t+1 of every sequence is uploaded on a copy stream (one strided
+ * 2-D copy per image plane) while frame t is solved.  Outputs are host buffers as above; reason / global_poses may be NULL. */
+int dvo_run_sequences_mem(dvo_ctx* ctx, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, int mem,
+                          const dvo_solver_params* params, const dvo_keyframe_policy* policy, double* rel_poses, int* kind,
+                          int* reason, double* global_poses);
+
 /* ---- inspection (parity tests; not on the hot path) ---- */
 int dvo_level_dims(dvo_ctx* ctx, int level, int* w, int* h);
 int dvo_get_level_buffer(dvo_ctx* ctx, int slot, int frame, int level, int which, void* host_dst, size_t bytes);
@@ -204,6 +217,11 @@ int dvo_eval_normal_equations_ex(dvo_ctx* ctx, int slot, int level, const double
 /* per-iteration trace of the last dvo_run (needs cfg.trace_iters > 0): for level `level`, `trace_iters` records of
  * 56 doubles: g[6], H[36], energy, nvis, R[9], T[3] (zero where not executed) */
 int dvo_get_trace(dvo_ctx* ctx, int slot, int level, double* trace);
+
+/* energyAtEachIteration of runIterations (src/SolveDVO.cpp:634, :690): ||eps|| of the first min(capacity, 128) iterations the last
+ * dvo_run executed at `level` for `slot`; entries beyond info.iterations_run[level] are stale.  Always recorded (one float per
+ * iteration), independent of cfg.trace_iters. */
+int dvo_get_energies(dvo_ctx* ctx, int slot, int level, float* energies, int capacity);
 
 /* per-stage device time of the most recent calls, CUDA events on the context stream (ms); enable first */
 enum { DVO_STAGE_H2D = 0, DVO_STAGE_PYRAMID, DVO_STAGE_CANNY, DVO_STAGE_EDT_ROWS, DVO_STAGE_NORMGRAD, DVO_STAGE_SOLVE,
@@ -277,10 +295,24 @@ int dvo_photo_get_poses(dvo_photo_ctx* ctx, int first, int count, double* R9T3, 
 /* PyramidalStorageStruct::getLevel (src/PyramidalStorage.cpp:71-102): any stored member of one slot / level, host copy */
 int dvo_photo_get_level(dvo_photo_ctx* ctx, int slot, int frame, int level, int which, void* host_dst, size_t bytes, int compat);
 int dvo_photo_get_A(dvo_photo_ctx* ctx, int slot, int level, double* A36);
+/* PyramidalStorageStruct::addLevel with the caller's own images (src/PyramidalStorage.cpp:38-65): overwrite one stored level image
+ * (which = DVO_PHOTO_GRAY / DVO_PHOTO_DEPTH at any level, DVO_PHOTO_BGR at level 0; host source, exact size).  X / Y / Z / J / *Vals
+ * are functions of these and are re-evaluated by the kernels; call dvo_photo_prepare_ref afterwards to refresh A = J^T J. */
+int dvo_photo_put_level(dvo_photo_ctx* ctx, int slot, int frame, int level, int which, const void* host_src, size_t bytes);
 /* one evaluation of estimate()'s loop body at a given pose (inspection): warped canvas (f64 [rows][cols], may be NULL),
  * b = J^T (W) eps, A, sum eps^2, nReprojected, residual count */
 int dvo_photo_eval(dvo_photo_ctx* ctx, int slot, int level, const double* R9T3, int compat, double huber_k, double* b6, double* A36,
                    double* sumsq, int* nreproj, int* nused, double* canvas);
+
+/* ---- device-resident storage blobs: what PyramidalStorageStruct (src/PyramidalStorage.cpp:38-102) keeps per level when a
+ * caller pushes its own eleven arrays -- a device allocation with host upload / download instead of a host deep copy ---- */
+typedef struct dvo_blob dvo_blob;
+int dvo_blob_create(size_t bytes, int device, dvo_blob** out);
+int dvo_blob_upload(dvo_blob* blob, const void* host_src, size_t bytes);
+int dvo_blob_download(dvo_blob* blob, void* host_dst, size_t bytes);
+void* dvo_blob_device_ptr(dvo_blob* blob);
+size_t dvo_blob_bytes(dvo_blob* blob);
+int dvo_blob_destroy(dvo_blob* blob);
 
 /* ---- undistortion front-end of the publisher (src/camTopic2PublisherPyD.cpp:86-117: cv::undistort of the BGR frame and of
  * the 16-bit depth frame before the pyramid is built).  `count` images of `type`, tightly packed; K4 = fx, fy, cx, cy;

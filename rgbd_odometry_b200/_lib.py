@@ -59,13 +59,14 @@ class RgbdInfo(C.Structure):
 # every symbol include/dvo_b200.h declares
 SYMBOLS = [
     "dvo_last_error", "dvo_device_count", "dvo_create", "dvo_destroy", "dvo_set_stream", "dvo_synchronize",
-    "dvo_set_intrinsics", "dvo_set_frames", "dvo_promote_now_to_ref", "dvo_build_pyramids", "dvo_prepare",
+    "dvo_set_intrinsics", "dvo_set_frames", "dvo_set_frames_raw", "dvo_promote_now_to_ref", "dvo_build_pyramids", "dvo_prepare",
     "dvo_set_initial_pose", "dvo_run", "dvo_process", "dvo_join", "dvo_join_stream", "dvo_get_poses", "dvo_align_batch", "dvo_level_dims", "dvo_get_level_buffer",
-    "dvo_get_points", "dvo_eval_normal_equations", "dvo_eval_normal_equations_ex", "dvo_get_trace", "dvo_enable_timing", "dvo_get_stage_ms",
-    "dvo_launch_count", "dvo_gop_compose", "dvo_run_sequences", "dvo_run_sequences_gated",
+    "dvo_get_points", "dvo_eval_normal_equations", "dvo_eval_normal_equations_ex", "dvo_get_trace", "dvo_get_energies", "dvo_enable_timing", "dvo_get_stage_ms",
+    "dvo_launch_count", "dvo_gop_compose", "dvo_run_sequences", "dvo_run_sequences_gated", "dvo_run_sequences_mem",
     "dvo_photo_create", "dvo_photo_destroy", "dvo_photo_set_stream", "dvo_photo_synchronize", "dvo_photo_launch_count",
     "dvo_photo_set_intrinsics", "dvo_photo_set_frames", "dvo_photo_prepare_ref", "dvo_photo_set_pose", "dvo_photo_estimate",
-    "dvo_photo_get_poses", "dvo_photo_get_level", "dvo_photo_get_A", "dvo_photo_eval",
+    "dvo_photo_get_poses", "dvo_photo_get_level", "dvo_photo_get_A", "dvo_photo_eval", "dvo_photo_put_level",
+    "dvo_blob_create", "dvo_blob_upload", "dvo_blob_download", "dvo_blob_device_ptr", "dvo_blob_bytes", "dvo_blob_destroy",
     "dvo_undistort",
     "dvo_rgbd_create", "dvo_rgbd_destroy", "dvo_rgbd_set_stream", "dvo_rgbd_synchronize", "dvo_rgbd_launch_count",
     "dvo_rgbd_set_intrinsics", "dvo_rgbd_set_frames", "dvo_rgbd_compute_jacobians", "dvo_rgbd_set_pose", "dvo_rgbd_gauss_newton",
@@ -95,6 +96,7 @@ def load(build_if_missing=True):
     lib.dvo_synchronize.argtypes = [C.c_void_p]
     lib.dvo_set_intrinsics.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_float]
     lib.dvo_set_frames.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.dvo_set_frames_raw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     lib.dvo_promote_now_to_ref.argtypes = [C.c_void_p, C.c_int, C.c_int]
     lib.dvo_build_pyramids.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
     lib.dvo_prepare.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
@@ -116,6 +118,7 @@ def load(build_if_missing=True):
                                                  C.c_void_p, C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int),
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dvo_get_trace.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dvo_get_energies.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
     lib.dvo_enable_timing.argtypes = [C.c_void_p, C.c_int]
     lib.dvo_get_stage_ms.argtypes = [C.c_void_p, C.c_void_p]
     lib.dvo_gop_compose.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -123,6 +126,8 @@ def load(build_if_missing=True):
                                       C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dvo_run_sequences_gated.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(SolverParams),
                                             C.POINTER(KeyframePolicy), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.dvo_run_sequences_mem.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(SolverParams),
+                                          C.POINTER(KeyframePolicy), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dvo_photo_create.argtypes = [C.POINTER(PhotoConfig), C.POINTER(C.c_void_p)]
     lib.dvo_photo_destroy.argtypes = [C.c_void_p]
     lib.dvo_photo_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -137,6 +142,15 @@ def load(build_if_missing=True):
     lib.dvo_photo_get_poses.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     lib.dvo_photo_get_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
     lib.dvo_photo_get_A.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.dvo_photo_put_level.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
+    lib.dvo_blob_create.argtypes = [C.c_size_t, C.c_int, C.POINTER(C.c_void_p)]
+    lib.dvo_blob_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.dvo_blob_download.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    lib.dvo_blob_device_ptr.argtypes = [C.c_void_p]
+    lib.dvo_blob_device_ptr.restype = C.c_void_p
+    lib.dvo_blob_bytes.argtypes = [C.c_void_p]
+    lib.dvo_blob_bytes.restype = C.c_size_t
+    lib.dvo_blob_destroy.argtypes = [C.c_void_p]
     lib.dvo_photo_eval.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_void_p,
                                    C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p]
     lib.dvo_undistort.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]

@@ -95,6 +95,16 @@ class BatchAligner:
         check(self.lib.dvo_set_frames(self.h, frame, first, count, _ptr(gray), _ptr(depth), MEM_DEVICE if device else MEM_HOST),
               "dvo_set_frames")
 
+    def set_frames_raw(self, frame, bgr, depth_m=None, first=0, count=None, device=False):
+        """Raw sensor frames: bgr (n, H, W, 3) u8 and depth_m (n, H, W) f32 metres (dvo_set_frames_raw)."""
+        if not device:
+            bgr = np.ascontiguousarray(bgr, np.uint8)
+            count = bgr.shape[0] if count is None else count
+            if depth_m is not None:
+                depth_m = np.ascontiguousarray(depth_m, np.float32)
+        check(self.lib.dvo_set_frames_raw(self.h, frame, first, count, _ptr(bgr), _ptr(depth_m), MEM_DEVICE if device else MEM_HOST),
+              "dvo_set_frames_raw")
+
     def build_pyramids(self, count, first=0, frames_mask=3):
         check(self.lib.dvo_build_pyramids(self.h, first, count, frames_mask), "dvo_build_pyramids")
 
@@ -169,6 +179,18 @@ class BatchAligner:
                                                _ptr(kind), _ptr(reason), _ptr(glob)), "dvo_run_sequences_gated")
         return rel, kind, reason, glob
 
+    def run_sequences_mem(self, gray, depth, nseq, nframes, params, policy, device=False, want_global=True):
+        """dvo_run_sequences_mem: gray / depth are numpy arrays (host; pinned arrays upload asynchronously) or, with device=True,
+        raw device pointers to [nseq][nframes][H][W] buffers."""
+        rel = np.empty((nseq, nframes, 12), np.float64)
+        kind = np.empty((nseq, nframes), np.int32)
+        reason = np.empty((nseq, nframes), np.int32)
+        glob = np.empty((nseq, nframes, 19), np.float64) if want_global else None
+        check(self.lib.dvo_run_sequences_mem(self.h, nseq, nframes, _ptr(gray), _ptr(depth), MEM_DEVICE if device else MEM_HOST,
+                                             C.byref(params), C.byref(policy), _ptr(rel), _ptr(kind), _ptr(reason), _ptr(glob)),
+              "dvo_run_sequences_mem")
+        return rel, kind, reason, glob
+
     def level_dims(self, level):
         w, h = C.c_int(), C.c_int()
         check(self.lib.dvo_level_dims(self.h, level, C.byref(w), C.byref(h)), "dvo_level_dims")
@@ -213,6 +235,11 @@ class BatchAligner:
         check(self.lib.dvo_get_trace(self.h, slot, level, _ptr(tr)), "dvo_get_trace")
         return {"g": tr[:, 0:6], "H": tr[:, 6:42].reshape(n, 6, 6), "energy": tr[:, 42], "nvis": tr[:, 43],
                 "R": tr[:, 44:53].reshape(n, 3, 3), "T": tr[:, 53:56]}
+
+    def get_energies(self, slot, level, n=128):
+        out = np.zeros(n, np.float32)
+        check(self.lib.dvo_get_energies(self.h, slot, level, _ptr(out), n), "dvo_get_energies")
+        return out
 
     def enable_timing(self, on=True):
         check(self.lib.dvo_enable_timing(self.h, int(on)), "dvo_enable_timing")

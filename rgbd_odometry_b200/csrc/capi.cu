@@ -56,9 +56,21 @@ int dvo_device_count(void) {
     return n;
 }
 
+// inside dvo_create: any CUDA failure after the context object exists releases everything acquired so far
+#define CREATE_CUDA(call)                                                                       \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            dvo_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            dvo_destroy(c);                                                                     \
+            return DVO_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
 int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     if (!cfg || !out) { dvo_set_error("dvo_create: null argument"); return DVO_ERR_ARG; }
-    if (cfg->width < 8 || cfg->height < 8 || cfg->levels < 1 || cfg->levels > DVO_MAX_LEVELS || cfg->max_batch < 1 ||
+    // max_batch <= 65535: several kernels carry the slot index in gridDim.y / gridDim.z
+    if (cfg->width < 8 || cfg->height < 8 || cfg->levels < 1 || cfg->levels > DVO_MAX_LEVELS || cfg->max_batch < 1 || cfg->max_batch > 65535 ||
         cfg->width >= DVO_EDT_INF_1D || cfg->height >= DVO_EDT_INF_1D) {
         dvo_set_error("dvo_create: bad config %dx%d levels=%d max_batch=%d", cfg->width, cfg->height, cfg->levels, cfg->max_batch);
         return DVO_ERR_ARG;
@@ -82,7 +94,7 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     long long acc = 0; int maxP = 0;
     for (int l = 0; l < g.L; ++l) {
         g.w[l] = level_dim(cfg->width, l); g.h[l] = level_dim(cfg->height, l);
-        if (g.w[l] < 2 || g.h[l] < 2) { dvo_set_error("dvo_create: level %d is %dx%d (too small)", l, g.w[l], g.h[l]); delete c; return DVO_ERR_ARG; }
+        if (g.w[l] < 2 || g.h[l] < 2) { dvo_set_error("dvo_create: level %d is %dx%d (too small)", l, g.w[l], g.h[l]); dvo_destroy(c); return DVO_ERR_ARG; }
         g.P[l] = g.w[l] * g.h[l]; g.off[l] = acc * g.Bmax; acc += g.P[l];
         if (g.P[l] > maxP) maxP = g.P[l];
     }
@@ -94,28 +106,28 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     }
     g.total_t = acct * g.Bmax;
     cudaDeviceProp prop;
-    DVO_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    CREATE_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
     c->sm_count = prop.multiProcessorCount;
     c->smem_optin = prop.sharedMemPerBlockOptin;
     c->solve_shape = (cfg->max_batch <= c->sm_count) ? 512 : 256;
     if (const char* e = getenv("DVO_SOLVE_SHAPE")) { const int v = atoi(e); if (v == 256 || v == 512) c->solve_shape = v; }   // experiment knob
     c->texel_mode = 1;
     if (const char* e = getenv("DVO_TEXEL_MODE")) c->texel_mode = atoi(e) ? 1 : 0;                                           // experiment knob (A/B)
-    DVO_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
-    DVO_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 16; ++i) DVO_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
-    DVO_CUDA(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 16; ++i) CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_entry, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) {
-        DVO_CUDA(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
-        DVO_CUDA(cudaEventCreateWithFlags(&c->ev_pre[k], cudaEventDisableTiming));
-        DVO_CUDA(cudaEventCreateWithFlags(&c->ev_aux_done[k], cudaEventDisableTiming));
+        CREATE_CUDA(cudaStreamCreateWithFlags(&c->aux[k], cudaStreamNonBlocking));
+        CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_pre[k], cudaEventDisableTiming));
+        CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_aux_done[k], cudaEventDisableTiming));
     }
-    DVO_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     c->e2e_chunk = 256;
     if (const char* e = getenv("DVO_E2E_CHUNK")) { const int v = atoi(e); if (v > 0) c->e2e_chunk = v; }
-    DVO_CUDA(cudaEventCreate(&c->ev_a));
-    DVO_CUDA(cudaEventCreate(&c->ev_b));
+    CREATE_CUDA(cudaEventCreate(&c->ev_a));
+    CREATE_CUDA(cudaEventCreate(&c->ev_b));
 
     const size_t T = (size_t)g.total, B = (size_t)g.Bmax;
     int rc = DVO_OK;
@@ -130,6 +142,7 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     A(dalloc(&c->npts, B * g.L)); A(dalloc(&c->solve_order, B)); A(dalloc(&c->seq_mask, B)); A(dalloc(&c->seq_state, B)); A(dalloc(&c->nedge, 2 * B * g.L)); A(dalloc(&c->maxd2, B * g.L));
     A(dalloc(&c->pose0, B * 12)); A(dalloc(&c->pose, B * 12)); A(dalloc(&c->info, B));
     if (cfg->trace_iters > 0) A(dalloc(&c->trace, B * g.L * cfg->trace_iters * DVO_TRACE_DOUBLES));
+    A(dalloc(&c->energy, B * g.L * DVO_ENERGY_ITERS));
     // hysteresis bitmaps that do not fit in shared memory live in a global scratch (one pair of bitmaps per CTA)
     {
         const int wd = (g.w[0] + 31) >> 5;
@@ -138,14 +151,14 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
         if (words * 4 + 8192 > c->smem_optin) { c->bitmap_scratch_words = words; A(dalloc(&c->bitmap_scratch, words * B)); }
     }
     if (rc != DVO_OK) { dvo_destroy(c); return rc; }
-    DVO_CUDA(cudaMemsetAsync(c->npts, 0, sizeof(int) * B * g.L, c->stream));
-    DVO_CUDA(cudaMemsetAsync(c->nedge, 0, sizeof(unsigned) * 2 * B * g.L, c->stream));
-    DVO_CUDA(cudaMemsetAsync(c->maxd2, 0, sizeof(unsigned) * B * g.L, c->stream));
-    DVO_CUDA(cudaMemsetAsync(c->info, 0, sizeof(dvo_pair_info) * B, c->stream));
-    DVO_CUDA(cudaMallocHost((void**)&c->h_pose, sizeof(double) * 12 * B));
-    DVO_CUDA(cudaMallocHost((void**)&c->h_info, sizeof(dvo_pair_info) * B));
+    CREATE_CUDA(cudaMemsetAsync(c->npts, 0, sizeof(int) * B * g.L, c->stream));
+    CREATE_CUDA(cudaMemsetAsync(c->nedge, 0, sizeof(unsigned) * 2 * B * g.L, c->stream));
+    CREATE_CUDA(cudaMemsetAsync(c->maxd2, 0, sizeof(unsigned) * B * g.L, c->stream));
+    CREATE_CUDA(cudaMemsetAsync(c->info, 0, sizeof(dvo_pair_info) * B, c->stream));
+    CREATE_CUDA(cudaMallocHost((void**)&c->h_pose, sizeof(double) * 12 * B));
+    CREATE_CUDA(cudaMallocHost((void**)&c->h_info, sizeof(dvo_pair_info) * B));
     dvo_set_initial_pose(c, 0, g.Bmax, nullptr, DVO_MEM_HOST);
-    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    CREATE_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
     return DVO_OK;
 }
@@ -157,7 +170,7 @@ int dvo_destroy(dvo_ctx* c) {
     for (int f = 0; f < 2; ++f) { cudaFree(c->gray[f]); cudaFree(c->depth[f]); cudaFree(c->edge[f]); }
     cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->tex8); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ); cudaFree(c->ptsPix);
     cudaFree(c->npts); cudaFree(c->solve_order); cudaFree(c->seq_mask); cudaFree(c->seq_state); cudaFree(c->nedge); cudaFree(c->maxd2); cudaFree(c->pose0); cudaFree(c->pose); cudaFree(c->info);
-    cudaFree(c->trace); cudaFree(c->bitmap_scratch); cudaFree(c->prev_gray); cudaFree(c->prev_depth);
+    cudaFree(c->trace); cudaFree(c->energy); cudaFree(c->bitmap_scratch); cudaFree(c->prev_gray); cudaFree(c->prev_depth); cudaFree(c->raw_bgr); cudaFree(c->raw_depth);
     free(c->now_valid); free(c->prev_valid);
     if (c->h_pose) cudaFreeHost(c->h_pose);
     if (c->h_info) cudaFreeHost(c->h_info);
@@ -197,30 +210,66 @@ int dvo_set_intrinsics(dvo_ctx* c, float fx, float fy, float cx, float cy) {
     return DVO_OK;
 }
 
+}  // extern "C"
+
+// Validation and p_now_* bookkeeping shared by dvo_set_frames / dvo_set_frames_raw.  Every argument is checked before any
+// copy is enqueued or any flag changes, so an error return leaves the context as it was.
+static int begin_set_frames(dvo_ctx* c, const char* who, int frame, int first, int count, bool have_gray, bool have_depth) {
+    if (!range_ok(c, first, count) || (frame != DVO_FRAME_REF && frame != DVO_FRAME_NOW) || !have_gray) { dvo_set_error("%s: bad argument", who); return DVO_ERR_ARG; }
+    if (frame == DVO_FRAME_REF && !have_depth) { dvo_set_error("%s: the reference frame needs depth", who); return DVO_ERR_ARG; }
+    bool rotate = false;
+    if (frame == DVO_FRAME_NOW && c->prev_gray) {
+        if (!have_depth) { dvo_set_error("%s: a context with keep_now_depth needs the now frame's depth", who); return DVO_ERR_ARG; }
+        bool any = false, all = true;
+        for (int i = first; i < first + count; ++i) { any |= c->now_valid[i] != 0; all &= c->now_valid[i] != 0; }
+        if (any && !all) { dvo_set_error("%s: slots [%d,%d) mix first and subsequent now frames", who, first, first + count); return DVO_ERR_STATE; }
+        rotate = all && count > 0;
+    }
+    const size_t P0 = c->geom.P[0];
+    if (rotate) {
+        // setRcvdFrameAsNowFrame keeps the outgoing now frame as p_now_* (src/SolveDVO.cpp:594-600)
+        DVO_CUDA(cudaMemcpyAsync(c->prev_gray + P0 * first, c->gray[1] + lvl_at(c->geom, 0, first), P0 * count, cudaMemcpyDeviceToDevice, c->stream));
+        DVO_CUDA(cudaMemcpyAsync(c->prev_depth + P0 * first, c->depth[1] + lvl_at(c->geom, 0, first), P0 * count * 2, cudaMemcpyDeviceToDevice, c->stream));
+        for (int i = first; i < first + count; ++i) c->prev_valid[i] = 1;
+    }
+    if (frame == DVO_FRAME_NOW) for (int i = first; i < first + count; ++i) c->now_valid[i] = 1;
+    return DVO_OK;
+}
+
+extern "C" {
+
 int dvo_set_frames(dvo_ctx* c, int frame, int first, int count, const uint8_t* gray, const uint16_t* depth, int mem) {
     if (c) { const int jr = join_aux(c); if (jr) return jr; }
-    if (!range_ok(c, first, count) || (frame != DVO_FRAME_REF && frame != DVO_FRAME_NOW) || !gray) { dvo_set_error("dvo_set_frames: bad argument"); return DVO_ERR_ARG; }
-    if (frame == DVO_FRAME_REF && !depth) { dvo_set_error("dvo_set_frames: the reference frame needs depth"); return DVO_ERR_ARG; }
+    { const int rc = begin_set_frames(c, "dvo_set_frames", frame, first, count, gray != nullptr, depth != nullptr); if (rc) return rc; }
     StageTimer t(c, DVO_STAGE_H2D);
     const size_t P0 = c->geom.P[0];
     const cudaMemcpyKind k = mem == DVO_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    if (frame == DVO_FRAME_NOW && c->prev_gray) {
-        // setRcvdFrameAsNowFrame keeps the outgoing now frame as p_now_* (src/SolveDVO.cpp:594-600)
-        bool any = false, all = true;
-        for (int i = first; i < first + count; ++i) { any |= c->now_valid[i] != 0; all &= c->now_valid[i] != 0; }
-        if (any && !all) { dvo_set_error("dvo_set_frames: slots [%d,%d) mix first and subsequent now frames", first, first + count); return DVO_ERR_STATE; }
-        if (all && count > 0) {
-            DVO_CUDA(cudaMemcpyAsync(c->prev_gray + P0 * first, c->gray[1] + lvl_at(c->geom, 0, first), P0 * count, cudaMemcpyDeviceToDevice, c->stream));
-            DVO_CUDA(cudaMemcpyAsync(c->prev_depth + P0 * first, c->depth[1] + lvl_at(c->geom, 0, first), P0 * count * 2, cudaMemcpyDeviceToDevice, c->stream));
-            for (int i = first; i < first + count; ++i) c->prev_valid[i] = 1;
-        }
-        if (!depth) { dvo_set_error("dvo_set_frames: a context with keep_now_depth needs the now frame's depth"); return DVO_ERR_ARG; }
-    }
-    if (frame == DVO_FRAME_NOW) for (int i = first; i < first + count; ++i) c->now_valid[i] = 1;
     DVO_CUDA(cudaMemcpyAsync(c->gray[frame] + lvl_at(c->geom, 0, first), gray, P0 * count, k, c->stream));
     if (depth && c->depth[frame])
         DVO_CUDA(cudaMemcpyAsync(c->depth[frame] + lvl_at(c->geom, 0, first), depth, P0 * count * sizeof(uint16_t), k, c->stream));
     return DVO_OK;
+}
+
+int dvo_set_frames_raw(dvo_ctx* c, int frame, int first, int count, const uint8_t* bgr, const float* depth_m, int mem) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
+    { const int rc = begin_set_frames(c, "dvo_set_frames_raw", frame, first, count, bgr != nullptr, depth_m != nullptr); if (rc) return rc; }
+    if (count == 0) return DVO_OK;
+    StageTimer t(c, DVO_STAGE_H2D);
+    const size_t P0 = c->geom.P[0];
+    const uint8_t* d_bgr = bgr; const float* d_dm = depth_m;
+    if (mem != DVO_MEM_DEVICE) {
+        if (c->raw_capacity < (size_t)count) {           // staging sized for the largest range seen so far
+            DVO_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->raw_bgr); cudaFree(c->raw_depth); c->raw_bgr = nullptr; c->raw_depth = nullptr; c->raw_capacity = 0;
+            int rc = dalloc(&c->raw_bgr, (size_t)count * P0 * 3); if (rc) return rc;
+            rc = dalloc(&c->raw_depth, (size_t)count * P0); if (rc) return rc;
+            c->raw_capacity = (size_t)count;
+        }
+        DVO_CUDA(cudaMemcpyAsync(c->raw_bgr, bgr, P0 * count * 3, cudaMemcpyHostToDevice, c->stream));
+        if (depth_m) DVO_CUDA(cudaMemcpyAsync(c->raw_depth, depth_m, P0 * count * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+        d_bgr = c->raw_bgr; d_dm = depth_m ? c->raw_depth : nullptr;
+    }
+    return launch_ingest_raw(c, frame, first, count, d_bgr, d_dm);
 }
 
 int dvo_promote_now_to_ref(dvo_ctx* c, int first, int count) {
@@ -396,59 +445,7 @@ int dvo_align_batch(dvo_ctx* c, int count, const uint8_t* ref_gray, const uint16
     return rc;
 }
 
-// SolveDVO::loop (src/SolveDVO.cpp:1896-2373) for `nseq` independent sequences processed in lock step (slot = sequence):
-// frame 0 is the first reference / key frame (:2013-2017); every later frame is aligned against the current reference with
-// the previous frame's pose as the initial guess (:1931-1932, :2097-2104); when (n - lastRefFrame) == keyframe_every the
-// previous frame becomes the reference, the pose is reset and the frame is solved again (:2155-2233).  The solve the
-// reference performs against the outgoing key frame right before a switch is discarded there (:2210-2227) and is skipped.
-int dvo_run_sequences(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* p,
-                      int keyframe_every, double* rel_poses, int* kind, double* global_poses) {
-    if (c) { const int jr = join_aux(c); if (jr) return jr; }
-    if (!c || nseq < 1 || nseq > c->cfg.max_batch || nframes < 1 || !gray || !depth || !p || !rel_poses || !kind) { dvo_set_error("dvo_run_sequences: bad argument"); return DVO_ERR_ARG; }
-    if (!c->prev_gray) { dvo_set_error("dvo_run_sequences: create the context with keep_now_depth = 1"); return DVO_ERR_STATE; }
-    if (!c->haveK) { dvo_set_error("dvo_run_sequences: intrinsics not set"); return DVO_ERR_STATE; }
-    const size_t P0 = c->geom.P[0];
-    int rc;
-    auto upload = [&](int frame, int t) -> int {          // frame t of every sequence -> slots [0, nseq)
-        for (int s = 0; s < nseq; ++s) {
-            const size_t src = ((size_t)s * nframes + t) * P0;
-            int r = dvo_set_frames(c, frame, s, 1, gray + src, depth + src, DVO_MEM_HOST);
-            if (r) return r;
-        }
-        return DVO_OK;
-    };
-    for (int s = 0; s < nseq; ++s) { c->now_valid[s] = 0; c->prev_valid[s] = 0; }
-    if ((rc = upload(DVO_FRAME_REF, 0))) return rc;
-    if ((rc = dvo_build_pyramids(c, 0, nseq, 1))) return rc;
-    if ((rc = dvo_prepare(c, 0, nseq, 1))) return rc;
-    std::vector<double> ident((size_t)12 * nseq, 0.0);
-    for (int s = 0; s < nseq; ++s) { ident[12 * (size_t)s] = ident[12 * (size_t)s + 4] = ident[12 * (size_t)s + 8] = 1.0; }
-    std::vector<double> cur(ident);
-    for (int s = 0; s < nseq; ++s) { memcpy(rel_poses + ((size_t)s * nframes) * 12, ident.data(), 96); kind[(size_t)s * nframes] = 1; }   // pushAsKeyFrame(0, 1, I, 0)
-    int lastRef = 0;
-    for (int t = 1; t < nframes; ++t) {
-        if ((rc = upload(DVO_FRAME_NOW, t))) return rc;                                   // setRcvdFrameAsNowFrame
-        if ((rc = dvo_build_pyramids(c, 0, nseq, 2))) return rc;
-        if ((rc = dvo_prepare(c, 0, nseq, 2))) return rc;
-        const bool switch_ref = (t - lastRef) == keyframe_every && lastRef != t - 1;
-        if (switch_ref) {
-            lastRef = t - 1;
-            if ((rc = dvo_promote_now_to_ref(c, 0, nseq))) return rc;                     // setPrevFrameAsRefFrame
-            if ((rc = dvo_build_pyramids(c, 0, nseq, 1))) return rc;
-            if ((rc = dvo_prepare(c, 0, nseq, 1))) return rc;                             // computeDistTransfrmOfRef + preProcessRefFrame
-            for (int s = 0; s < nseq; ++s) kind[(size_t)s * nframes + t - 1] = 2;         // gop.updateMostRecentToKeyFrame
-            cur = ident;                                                                  // cR_64 = I, cT_64 = 0
-        }
-        if ((rc = dvo_set_initial_pose(c, 0, nseq, cur.data(), DVO_MEM_HOST))) return rc;
-        if ((rc = dvo_run(c, 0, nseq, p))) return rc;
-        if ((rc = dvo_get_poses(c, 0, nseq, cur.data(), nullptr, DVO_MEM_HOST))) return rc;
-        for (int s = 0; s < nseq; ++s) { memcpy(rel_poses + ((size_t)s * nframes + t) * 12, cur.data() + 12 * (size_t)s, 96); kind[(size_t)s * nframes + t] = 0; }   // pushAsOrdinaryFrame
-    }
-    if (global_poses) return dvo_gop_compose(c, nseq, nframes, kind, rel_poses, global_poses, DVO_MEM_HOST);
-    return DVO_OK;
-}
-
-// ---- gated sequence loop: the key-frame decision of SolveDVO::loop (:2117-2233) taken per slot on the device ----
+// ---- sequence mode: SolveDVO::loop (src/SolveDVO.cpp:1896-2373) for `nseq` independent sequences in lock step ----
 }  // extern "C"
 
 namespace {
@@ -492,53 +489,115 @@ __global__ void seq_init_kernel(int nseq, int nframes, double* __restrict__ pose
     for (int k = 0; k < 12; ++k) { const double v = (k == 0 || k == 4 || k == 8) ? 1.0 : 0.0; pose0[12 * (long long)s + k] = v; rel[12 * (long long)s * nframes + k] = v; }
     kind[(long long)s * nframes] = 1; reason[(long long)s * nframes] = 1;                    // gop.pushAsKeyFrame(nFrame, 1, I, 0) (:2016)
 }
-}  // namespace
 
-extern "C" {
-
-int dvo_run_sequences_gated(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* p,
-                            const dvo_keyframe_policy* pol, double* rel_poses, int* kind, int* reason, double* global_poses) {
+// One loop for both entry points.  Frame 0 is the first reference / key frame (:2013-2017); every later frame is aligned against
+// the current reference with the previous frame's pose as the initial guess (:1931-1932, :2097-2104); a key-frame signal makes the
+// PREVIOUS frame the reference, resets the pose and solves the frame again (:2155-2233).  Everything between frames stays on the
+// device: poses, statistics, the per-slot decision (seq_gate_kernel) and the record of relative poses / kinds / reasons.
+//
+// Uploads are pipelined: frame t+1 of every sequence travels on the copy stream into one of two staging buffers (one strided
+// 2-D copy per image plane instead of nseq small ones) while frame t is being solved; the compute stream then moves it into
+// the level-0 regions with a device-to-device copy (after saving the outgoing now frame as p_now_*, :594-600).
+//
+// With the periodic rule alone (the shipped policy) the host knows the switch frames, so (a) the masked switch pass is only
+// launched at those frames and (b) the solve against the outgoing key frame, whose result the reference discards
+// (:2210-2227), is skipped.  With the quality gates the decision depends on that solve, so it runs and every frame from t = 2
+// on is followed by the masked pass (its kernels return at once for unflagged slots).
+int run_sequences_core(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, int mem, const dvo_solver_params* p,
+                       const dvo_keyframe_policy* pol, double* rel_poses, int* kind, int* reason, double* global_poses) {
+    const char* who = "dvo_run_sequences";
     if (c) { const int jr = join_aux(c); if (jr) return jr; }
-    if (!c || nseq < 1 || nseq > c->cfg.max_batch || nframes < 1 || !gray || !depth || !p || !pol || !rel_poses || !kind) { dvo_set_error("dvo_run_sequences_gated: bad argument"); return DVO_ERR_ARG; }
-    if (!c->prev_gray) { dvo_set_error("dvo_run_sequences_gated: create the context with keep_now_depth = 1"); return DVO_ERR_STATE; }
-    if (!c->haveK) { dvo_set_error("dvo_run_sequences_gated: intrinsics not set"); return DVO_ERR_STATE; }
+    if (!c || nseq < 1 || nseq > c->cfg.max_batch || nframes < 1 || !gray || !depth || !p || !pol || !rel_poses || !kind) { dvo_set_error("%s: bad argument", who); return DVO_ERR_ARG; }
+    if (!c->prev_gray) { dvo_set_error("%s: create the context with keep_now_depth = 1", who); return DVO_ERR_STATE; }
+    if (!c->haveK) { dvo_set_error("%s: intrinsics not set", who); return DVO_ERR_STATE; }
     int finest = -1;
     for (int l = 0; l < c->geom.L; ++l) if (p->iters[l] > 0) { finest = l; break; }
-    if (finest < 0) { dvo_set_error("dvo_run_sequences_gated: no level has iterations"); return DVO_ERR_ARG; }
+    if (finest < 0) { dvo_set_error("%s: no level has iterations", who); return DVO_ERR_ARG; }
     const size_t P0 = c->geom.P[0], n = (size_t)nseq * nframes;
-    double* d_rel = nullptr; int* d_kind = nullptr; int* d_reason = nullptr; double* d_glob = nullptr;
+    const bool host_in = (mem != DVO_MEM_DEVICE);
     int rc = DVO_OK;
-    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DVO_OK) { dvo_set_error("dvo_run_sequences_gated: %s", cudaGetErrorString(e)); rc = DVO_ERR_CUDA; } return rc != DVO_OK; };
-    if (fail(cudaMalloc((void**)&d_rel, sizeof(double) * 12 * n)) || fail(cudaMalloc((void**)&d_kind, sizeof(int) * n)) || fail(cudaMalloc((void**)&d_reason, sizeof(int) * n))) {
-        cudaFree(d_rel); cudaFree(d_kind); cudaFree(d_reason); return rc;
-    }
+    auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DVO_OK) { dvo_set_error("%s: %s", who, cudaGetErrorString(e)); rc = DVO_ERR_CUDA; } return rc != DVO_OK; };
+
+    // ---- buffers: record of the run (device), staging for the uploads
+    double* d_rel = nullptr; int* d_kind = nullptr; int* d_reason = nullptr; double* d_glob = nullptr;
+    uint8_t* stage_g[2] = {nullptr, nullptr}; uint16_t* stage_d[2] = {nullptr, nullptr};
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+    auto cleanup = [&]() {
+        cudaFree(d_rel); cudaFree(d_kind); cudaFree(d_reason); cudaFree(d_glob);
+        for (int k = 0; k < 2; ++k) { cudaFree(stage_g[k]); cudaFree(stage_d[k]); if (ev_ready[k]) cudaEventDestroy(ev_ready[k]); if (ev_free[k]) cudaEventDestroy(ev_free[k]); }
+    };
+    fail(cudaMalloc((void**)&d_rel, sizeof(double) * 12 * n)); fail(cudaMalloc((void**)&d_kind, sizeof(int) * n)); fail(cudaMalloc((void**)&d_reason, sizeof(int) * n));
+    if (host_in)
+        for (int k = 0; k < 2 && rc == DVO_OK; ++k) {
+            fail(cudaMalloc((void**)&stage_g[k], P0 * nseq)); fail(cudaMalloc((void**)&stage_d[k], P0 * nseq * sizeof(uint16_t)));
+            fail(cudaEventCreateWithFlags(&ev_ready[k], cudaEventDisableTiming)); fail(cudaEventCreateWithFlags(&ev_free[k], cudaEventDisableTiming));
+        }
+    if (rc != DVO_OK) { cleanup(); return rc; }
     fail(cudaMemsetAsync(d_rel, 0, sizeof(double) * 12 * n, c->stream));
     fail(cudaMemsetAsync(d_kind, 0, sizeof(int) * n, c->stream));
     fail(cudaMemsetAsync(d_reason, 0, sizeof(int) * n, c->stream));
-    auto upload = [&](int frame, int t) -> int {          // frame t of every sequence -> slots [0, nseq)
-        for (int s = 0; s < nseq; ++s) {
-            const size_t src = ((size_t)s * nframes + t) * P0;
-            int r = dvo_set_frames(c, frame, s, 1, gray + src, depth + src, DVO_MEM_HOST);
-            if (r) return r;
-        }
-        return DVO_OK;
+    if (host_in) { fail(cudaEventRecord(c->ev_entry, c->stream)); fail(cudaStreamWaitEvent(c->copy_stream, c->ev_entry, 0)); }
+
+    // frame t of every sequence: host -> staging buffer t & 1 on the copy stream
+    bool staged_before[2] = {false, false};
+    auto upload = [&](int t) {
+        if (!host_in || t >= nframes || rc != DVO_OK) return;
+        const int k = t & 1;
+        if (staged_before[k]) fail(cudaStreamWaitEvent(c->copy_stream, ev_free[k], 0));
+        fail(cudaMemcpy2DAsync(stage_g[k], P0, gray + (size_t)t * P0, (size_t)nframes * P0, P0, nseq, cudaMemcpyHostToDevice, c->copy_stream));
+        fail(cudaMemcpy2DAsync(stage_d[k], P0 * 2, depth + (size_t)t * P0, (size_t)nframes * P0 * 2, P0 * 2, nseq, cudaMemcpyHostToDevice, c->copy_stream));
+        fail(cudaEventRecord(ev_ready[k], c->copy_stream));
+        staged_before[k] = true;
     };
+    // staged (or device-resident) frame t -> level-0 regions of `frame` on the compute stream
+    auto ingest = [&](int frame, int t) {
+        if (rc != DVO_OK) return;
+        uint8_t* dg = c->gray[frame] + lvl_at(c->geom, 0, 0); uint16_t* dd = c->depth[frame] + lvl_at(c->geom, 0, 0);
+        if (frame == DVO_FRAME_NOW && c->now_valid[0]) {                                     // setRcvdFrameAsNowFrame keeps the outgoing now frame (:594-600)
+            fail(cudaMemcpyAsync(c->prev_gray, dg, P0 * nseq, cudaMemcpyDeviceToDevice, c->stream));
+            fail(cudaMemcpyAsync(c->prev_depth, dd, P0 * nseq * 2, cudaMemcpyDeviceToDevice, c->stream));
+            for (int s2 = 0; s2 < nseq; ++s2) c->prev_valid[s2] = 1;
+        }
+        if (frame == DVO_FRAME_NOW) for (int s2 = 0; s2 < nseq; ++s2) c->now_valid[s2] = 1;
+        if (host_in) {
+            const int k = t & 1;
+            fail(cudaStreamWaitEvent(c->stream, ev_ready[k], 0));
+            fail(cudaMemcpyAsync(dg, stage_g[k], P0 * nseq, cudaMemcpyDeviceToDevice, c->stream));
+            fail(cudaMemcpyAsync(dd, stage_d[k], P0 * nseq * 2, cudaMemcpyDeviceToDevice, c->stream));
+            fail(cudaEventRecord(ev_free[k], c->stream));
+        } else {
+            fail(cudaMemcpy2DAsync(dg, P0, gray + (size_t)t * P0, (size_t)nframes * P0, P0, nseq, cudaMemcpyDeviceToDevice, c->stream));
+            fail(cudaMemcpy2DAsync(dd, P0 * 2, depth + (size_t)t * P0, (size_t)nframes * P0 * 2, P0 * 2, nseq, cudaMemcpyDeviceToDevice, c->stream));
+        }
+    };
+
     const int blk = (nseq + 127) / 128;
-    for (int s = 0; s < nseq; ++s) { c->now_valid[s] = 0; c->prev_valid[s] = 0; }
-    if (rc == DVO_OK) rc = upload(DVO_FRAME_REF, 0);
+    const bool timing = c->timing;
+    c->timing = false;                                                                       // per-stage timers synchronise; keep the pipeline asynchronous
+    for (int s2 = 0; s2 < nseq; ++s2) { c->now_valid[s2] = 0; c->prev_valid[s2] = 0; }
+    upload(0); upload(1);
+    ingest(DVO_FRAME_REF, 0);
     if (rc == DVO_OK) rc = dvo_build_pyramids(c, 0, nseq, 1);
     if (rc == DVO_OK) rc = dvo_prepare(c, 0, nseq, 1);
     if (rc == DVO_OK) { seq_init_kernel<<<blk, 128, 0, c->stream>>>(nseq, nframes, c->pose0, c->seq_state, d_rel, d_kind, d_reason); c->launches++; fail(cudaGetLastError()); }
+    int host_last_ref = 0;                                                                   // mirrors lastRef of every slot under the periodic rule alone
     for (int t = 1; t < nframes && rc == DVO_OK; ++t) {
-        if ((rc = upload(DVO_FRAME_NOW, t))) break;                                          // setRcvdFrameAsNowFrame
+        ingest(DVO_FRAME_NOW, t);                                                            // setRcvdFrameAsNowFrame
+        upload(t + 1);                                                                       // next frame travels while this one is solved
+        if (rc != DVO_OK) break;
         if ((rc = dvo_build_pyramids(c, 0, nseq, 2))) break;
         if ((rc = dvo_prepare(c, 0, nseq, 2))) break;
-        if ((rc = dvo_run(c, 0, nseq, p))) break;                                            // warm start: pose0 holds the previous frame's pose (:1931-1932)
+        bool switch_pass = t >= 2, first_solve = true;                                       // a previous now frame exists from t = 2 on
+        if (!pol->use_quality_gates) {
+            switch_pass = t >= 2 && pol->keyframe_every > 0 && (t - host_last_ref) == pol->keyframe_every && host_last_ref != t - 1;
+            if (switch_pass) { host_last_ref = t - 1; first_solve = false; }
+        }
+        if (first_solve && (rc = dvo_run(c, 0, nseq, p))) break;                             // warm start: pose0 holds the previous frame's pose (:1931-1932)
         seq_gate_kernel<<<blk, 128, 0, c->stream>>>(nseq, nframes, t, *pol, finest, c->info, c->pose, c->pose0, c->seq_state, c->seq_mask, d_rel, d_kind, d_reason);
         c->launches++;
         if (fail(cudaGetLastError())) break;
-        if (t >= 2) {                                                                        // a previous now frame exists from t = 2 on (lastRef != t-1 excludes t = 1)
-            c->active = c->seq_mask;                                                         // switch pass: only the flagged slots do any work
+        if (switch_pass) {
+            c->active = c->seq_mask;                                                         // only the flagged slots do any work
             rc = dvo_promote_now_to_ref(c, 0, nseq);                                         // setPrevFrameAsRefFrame (:2196)
             if (rc == DVO_OK) rc = dvo_build_pyramids(c, 0, nseq, 1);
             if (rc == DVO_OK) rc = dvo_prepare(c, 0, nseq, 1);                               // computeDistTransfrmOfRef + preProcessRefFrame (:2197)
@@ -551,6 +610,7 @@ int dvo_run_sequences_gated(dvo_ctx* c, int nseq, int nframes, const uint8_t* gr
         }
     }
     c->active = nullptr;
+    c->timing = timing;
     if (rc == DVO_OK && global_poses) {
         if (!fail(cudaMalloc((void**)&d_glob, sizeof(double) * 19 * n))) {
             rc = launch_gop(c, nseq, nframes, d_kind, d_rel, d_glob);
@@ -561,10 +621,31 @@ int dvo_run_sequences_gated(dvo_ctx* c, int nseq, int nframes, const uint8_t* gr
         fail(cudaMemcpyAsync(rel_poses, d_rel, sizeof(double) * 12 * n, cudaMemcpyDeviceToHost, c->stream));
         fail(cudaMemcpyAsync(kind, d_kind, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
         if (reason) fail(cudaMemcpyAsync(reason, d_reason, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
-        fail(cudaStreamSynchronize(c->stream));
-    } else cudaStreamSynchronize(c->stream);
-    cudaFree(d_rel); cudaFree(d_kind); cudaFree(d_reason); cudaFree(d_glob);
+    }
+    cudaStreamSynchronize(c->copy_stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == DVO_OK) { dvo_set_error("%s: %s", who, cudaGetErrorString(cudaGetLastError())); rc = DVO_ERR_CUDA; }
+    cleanup();
     return rc;
+}
+}  // namespace
+
+extern "C" {
+
+int dvo_run_sequences(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* p,
+                      int keyframe_every, double* rel_poses, int* kind, double* global_poses) {
+    dvo_keyframe_policy pol; memset(&pol, 0, sizeof(pol));
+    pol.keyframe_every = keyframe_every; pol.use_quality_gates = 0; pol.laplacian_thresh = 3.0f; pol.visible_ratio_thresh = 0.8f; pol.min_reprojections = 50;
+    return run_sequences_core(c, nseq, nframes, gray, depth, DVO_MEM_HOST, p, &pol, rel_poses, kind, nullptr, global_poses);
+}
+
+int dvo_run_sequences_gated(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, const dvo_solver_params* p,
+                            const dvo_keyframe_policy* pol, double* rel_poses, int* kind, int* reason, double* global_poses) {
+    return run_sequences_core(c, nseq, nframes, gray, depth, DVO_MEM_HOST, p, pol, rel_poses, kind, reason, global_poses);
+}
+
+int dvo_run_sequences_mem(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, const uint16_t* depth, int mem, const dvo_solver_params* p,
+                          const dvo_keyframe_policy* pol, double* rel_poses, int* kind, int* reason, double* global_poses) {
+    return run_sequences_core(c, nseq, nframes, gray, depth, mem, p, pol, rel_poses, kind, reason, global_poses);
 }
 
 int dvo_level_dims(dvo_ctx* c, int level, int* w, int* h) {
@@ -595,7 +676,7 @@ int dvo_get_level_buffer(dvo_ctx* c, int slot, int frame, int level, int which, 
         float4* d_tmp = nullptr;
         if (!src) {      // packed-texel contexts keep no float images: evaluate them for this slot / level on demand
             DVO_CUDA(cudaMalloc((void**)&d_tmp, P * 16));
-            const int rc = launch_normgrad_into(c, slot, level, d_tmp);
+            const int rc = c->texel_mode ? launch_resolve_texels(c, slot, level, d_tmp) : launch_normgrad_into(c, slot, level, d_tmp);
             if (rc) { cudaFree(d_tmp); return rc; }
             src = d_tmp;
         }
@@ -677,12 +758,19 @@ int dvo_eval_normal_equations_ex(dvo_ctx* c, int slot, int level, const double* 
     DVO_CUDA(cudaMemcpyAsync(&N, c->npts + (size_t)slot * c->geom.L + level, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     DVO_CUDA(cudaStreamSynchronize(c->stream));
     double* d_pose = nullptr; double* d_out = nullptr; float* d_pp = nullptr;
-    DVO_CUDA(cudaMalloc((void**)&d_pose, sizeof(double) * 12));
-    DVO_CUDA(cudaMalloc((void**)&d_out, sizeof(double) * 44));
     const bool pp = eps || w || u || v || J;
     const size_t n1 = (size_t)(N > 0 ? N : 1);
-    if (pp) DVO_CUDA(cudaMalloc((void**)&d_pp, sizeof(float) * n1 * 10));
-    DVO_CUDA(cudaMemcpyAsync(d_pose, R9T3, sizeof(double) * 12, cudaMemcpyHostToDevice, c->stream));
+    {   // temporaries: released on every path
+        cudaError_t e = cudaMalloc((void**)&d_pose, sizeof(double) * 12);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, sizeof(double) * 44);
+        if (e == cudaSuccess && pp) e = cudaMalloc((void**)&d_pp, sizeof(float) * n1 * 10);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_pose, R9T3, sizeof(double) * 12, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            dvo_set_error("dvo_eval_normal_equations: %s", cudaGetErrorString(e));
+            cudaFree(d_pose); cudaFree(d_out); cudaFree(d_pp);
+            return DVO_ERR_CUDA;
+        }
+    }
     float *de = nullptr, *dw = nullptr, *du = nullptr, *dv = nullptr, *dJ = nullptr;
     if (pp) { de = d_pp; dw = d_pp + n1; du = d_pp + 2 * n1; dv = d_pp + 3 * n1; dJ = d_pp + 4 * n1; }
     int rc = launch_eval(c, slot, level, d_pose, prm->jacobian, prm->weight, prm->arithmetic, prm->huber_k, prm->residual, d_out, de, dw, du, dv, dJ);
@@ -727,6 +815,16 @@ int dvo_get_trace(dvo_ctx* c, int slot, int level, double* trace) {
     return DVO_OK;
 }
 
+int dvo_get_energies(dvo_ctx* c, int slot, int level, float* energies, int capacity) {
+    if (c) { const int jr = join_aux(c); if (jr) return jr; }
+    if (!range_ok(c, slot, 1) || level < 0 || level >= c->geom.L || !energies || capacity < 0) return DVO_ERR_ARG;
+    const int n = capacity < DVO_ENERGY_ITERS ? capacity : DVO_ENERGY_ITERS;
+    if (n == 0) return DVO_OK;
+    DVO_CUDA(cudaMemcpyAsync(energies, c->energy + ((size_t)slot * c->geom.L + level) * DVO_ENERGY_ITERS, sizeof(float) * n, cudaMemcpyDeviceToHost, c->stream));
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    return DVO_OK;
+}
+
 int dvo_enable_timing(dvo_ctx* c, int on) {
     if (!c) return DVO_ERR_ARG;
     c->timing = on != 0;
@@ -748,11 +846,18 @@ int dvo_gop_compose(dvo_ctx* c, int nseq, int nframes, const int* kind, const do
     const size_t n = (size_t)nseq * nframes;
     if (mem == DVO_MEM_DEVICE) return launch_gop(c, nseq, nframes, kind, rel, out);
     int* d_kind = nullptr; double* d_rel = nullptr; double* d_out = nullptr;
-    DVO_CUDA(cudaMalloc((void**)&d_kind, sizeof(int) * n));
-    DVO_CUDA(cudaMalloc((void**)&d_rel, sizeof(double) * 12 * n));
-    DVO_CUDA(cudaMalloc((void**)&d_out, sizeof(double) * 19 * n));
-    DVO_CUDA(cudaMemcpyAsync(d_kind, kind, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
-    DVO_CUDA(cudaMemcpyAsync(d_rel, rel, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, c->stream));
+    {
+        cudaError_t e = cudaMalloc((void**)&d_kind, sizeof(int) * n);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_rel, sizeof(double) * 12 * n);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&d_out, sizeof(double) * 19 * n);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_kind, kind, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_rel, rel, sizeof(double) * 12 * n, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            dvo_set_error("dvo_gop_compose: %s", cudaGetErrorString(e));
+            cudaFree(d_kind); cudaFree(d_rel); cudaFree(d_out);
+            return DVO_ERR_CUDA;
+        }
+    }
     int rc = launch_gop(c, nseq, nframes, d_kind, d_rel, d_out);
     if (rc == DVO_OK) {
         cudaError_t e = cudaMemcpyAsync(out, d_out, sizeof(double) * 19 * n, cudaMemcpyDeviceToHost, c->stream);
@@ -761,6 +866,44 @@ int dvo_gop_compose(dvo_ctx* c, int nseq, int nframes, const int* kind, const do
     }
     cudaFree(d_kind); cudaFree(d_rel); cudaFree(d_out);
     return rc;
+}
+
+// ---- device-resident storage blobs (PyramidalStorageStruct keeps caller-provided level arrays on the device) ----
+struct dvo_blob { void* d; size_t bytes; int device; };
+
+int dvo_blob_create(size_t bytes, int device, dvo_blob** out) {
+    if (!out || bytes == 0) { dvo_set_error("dvo_blob_create: bad argument"); return DVO_ERR_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); dvo_set_error("dvo_blob_create: no usable CUDA device (there is no CPU fallback)"); return DVO_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { dvo_set_error("dvo_blob_create: device %d out of range", device); return DVO_ERR_ARG; }
+    DVO_CUDA(cudaSetDevice(device));
+    dvo_blob* b = new (std::nothrow) dvo_blob();
+    if (!b) return DVO_ERR_NOMEM;
+    b->bytes = bytes; b->device = device; b->d = nullptr;
+    if (cudaMalloc(&b->d, bytes) != cudaSuccess) { cudaGetLastError(); delete b; dvo_set_error("dvo_blob_create: cudaMalloc(%zu) failed", bytes); return DVO_ERR_NOMEM; }
+    *out = b;
+    return DVO_OK;
+}
+int dvo_blob_upload(dvo_blob* b, const void* host_src, size_t bytes) {
+    if (!b || !host_src || bytes > b->bytes) { dvo_set_error("dvo_blob_upload: bad argument"); return DVO_ERR_ARG; }
+    DVO_CUDA(cudaSetDevice(b->device));
+    DVO_CUDA(cudaMemcpy(b->d, host_src, bytes, cudaMemcpyHostToDevice));
+    return DVO_OK;
+}
+int dvo_blob_download(dvo_blob* b, void* host_dst, size_t bytes) {
+    if (!b || !host_dst || bytes > b->bytes) { dvo_set_error("dvo_blob_download: bad argument"); return DVO_ERR_ARG; }
+    DVO_CUDA(cudaSetDevice(b->device));
+    DVO_CUDA(cudaMemcpy(host_dst, b->d, bytes, cudaMemcpyDeviceToHost));
+    return DVO_OK;
+}
+void* dvo_blob_device_ptr(dvo_blob* b) { return b ? b->d : nullptr; }
+size_t dvo_blob_bytes(dvo_blob* b) { return b ? b->bytes : 0; }
+int dvo_blob_destroy(dvo_blob* b) {
+    if (!b) return DVO_OK;
+    cudaSetDevice(b->device);
+    cudaFree(b->d);
+    delete b;
+    return DVO_OK;
 }
 
 }  // extern "C"

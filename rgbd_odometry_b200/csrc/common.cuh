@@ -47,6 +47,8 @@ struct Intr { float fx, fy, cx, cy; };
 
 // One trace record per executed iteration: g[6], H[36], energy, nvis, R[9], T[3].
 #define DVO_TRACE_DOUBLES 56
+// energyAtEachIteration (src/SolveDVO.cpp:634): the first DVO_ENERGY_ITERS energies of every level of the last solve are always kept
+#define DVO_ENERGY_ITERS 128
 
 struct dvo_ctx {
     dvo_config cfg;
@@ -89,8 +91,12 @@ struct dvo_ctx {
     double* pose;            // [Bmax][12]
     dvo_pair_info* info;     // [Bmax]
     double* trace;           // [Bmax][L][trace_iters][56] or null
+    float* energy;           // [Bmax][L][DVO_ENERGY_ITERS] ||eps|| of every executed iteration of the last solve
     uint32_t* bitmap_scratch;    // hysteresis bitmaps for images too large for shared memory, or null
     size_t bitmap_scratch_words; // per CTA
+
+    // device staging of dvo_set_frames_raw with host buffers (allocated on first use)
+    uint8_t* raw_bgr; float* raw_depth; size_t raw_capacity;   // in images
 
     // host staging for dvo_align_batch / dvo_get_poses
     double* h_pose;          // pinned [Bmax][12]
@@ -121,11 +127,14 @@ int launch_normgrad(dvo_ctx* c, int first, int count);
 int launch_pack(dvo_ctx* c, int first, int count);
 // inspection: {DTn, gx, gy, w} of one slot / level into a caller-provided device buffer of P[level] float4
 int launch_normgrad_into(dvo_ctx* c, int slot, int level, float4* d_out);
+// same images, resolved from the packed texels through the solver's own lookup path (texel_mode 1)
+int launch_resolve_texels(dvo_ctx* c, int slot, int level, float4* d_out);
 int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p);
 int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac, int weight, int arith, float huber_k, int residual,
                 double* d_out /* 6 + 36 + 1 + 1 doubles */, float* d_eps, float* d_w, float* d_u, float* d_v, float* d_J);
 int launch_gop(dvo_ctx* c, int nseq, int nframes, const int* d_kind, const double* d_rel, double* d_out);
 int launch_promote(dvo_ctx* c, int first, int count);
+int launch_ingest_raw(dvo_ctx* c, int frame, int first, int count, const uint8_t* d_bgr, const float* d_depth_m);
 
 // ---- arithmetic policies for the per-point fp32 math ----
 // EXACT: one IEEE rounding per written operation, never contracted -> bit-identical to the oracle compiled with

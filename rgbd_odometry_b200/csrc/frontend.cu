@@ -80,3 +80,65 @@ extern "C" int dvo_undistort(const void* src, void* dst, int width, int height, 
     if (e != cudaSuccess) { dvo_set_error("dvo_undistort: %s", cudaGetErrorString(e)); return DVO_ERR_CUDA; }
     return DVO_OK;
 }
+
+// =====================================================================================================
+// Raw-frame ingest (src/camTopic2PublisherPyD.cpp:65-80, :338-348): the publisher receives a bgr8 frame and a 32FC1 depth
+// frame in metres.  depth16 = convertTo(CV_16UC1) of 1000.0 * depth (fp32 product, cvRound = round half to even,
+// saturate), then setTo(1, depth16 == 0); framemono = cvtColor(BGR2GRAY) of the NEAREST-resized BGR -- BGR2GRAY is
+// per pixel, so gray(level i) = NEAREST level i of the full-resolution gray, which the pyramid kernels already build.
+// One fused pass writes the context's level-0 gray / depth regions: 7 B read, 3 B written per pixel.
+// =====================================================================================================
+__device__ __forceinline__ unsigned gray_of(unsigned b, unsigned g, unsigned r) { return (b * 3735u + g * 19235u + r * 9798u + (1u << 14)) >> 15; }
+__device__ __forceinline__ unsigned mm_of(float m) {
+    const float v = m * 1000.0f;                                     // -fmad=false: one rounding
+    if (!(fabsf(v) <= 3.0e38f)) return 1u;                           // NaN / inf -> cvRound gives INT_MIN -> saturates to 0 -> 1
+    const int r = __float2int_rn(fminf(fmaxf(v, -1.0e9f), 1.0e9f));
+    const int s = min(max(r, 0), 65535);
+    return s == 0 ? 1u : (unsigned)s;
+}
+
+__global__ void __launch_bounds__(256) ingest_raw_kernel(const uint8_t* __restrict__ bgr, const float* __restrict__ depth_m, uint8_t* __restrict__ gray,
+                                                         uint16_t* __restrict__ depth, long long P0, long long slot_stride_px, int vec) {
+    // grid.y = image; source images are tightly packed (P0 pixels each), destinations are the level-0 regions of consecutive slots
+    const long long q = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q >= P0) return;
+    const uint8_t* sb = bgr + ((long long)blockIdx.y * P0 + q) * 3;
+    const float* sd = depth_m ? depth_m + (long long)blockIdx.y * P0 + q : nullptr;
+    uint8_t* dg = gray + (long long)blockIdx.y * slot_stride_px + q;
+    uint16_t* dd = depth ? depth + (long long)blockIdx.y * slot_stride_px + q : nullptr;
+    if (vec && q + 4 <= P0) {
+        const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sb);
+        const uint32_t w0 = s32[0], w1 = s32[1], w2 = s32[2];        // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+        const unsigned g0 = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+        const unsigned g1 = gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+        const unsigned g2 = gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+        const unsigned g3 = gray_of((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+        *reinterpret_cast<uint32_t*>(dg) = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+        if (sd && dd) {
+            const float4 m = *reinterpret_cast<const float4*>(sd);
+            *reinterpret_cast<uint2*>(dd) = make_uint2(mm_of(m.x) | (mm_of(m.y) << 16), mm_of(m.z) | (mm_of(m.w) << 16));
+        }
+    } else {
+        for (int k = 0; k < 4 && q + k < P0; ++k) {
+            dg[k] = (uint8_t)gray_of(sb[3 * k], sb[3 * k + 1], sb[3 * k + 2]);
+            if (sd && dd) dd[k] = (uint16_t)mm_of(sd[k]);
+        }
+    }
+}
+
+int launch_ingest_raw(dvo_ctx* c, int frame, int first, int count, const uint8_t* d_bgr, const float* d_depth_m) {
+    const long long P0 = c->geom.P[0];
+    // 4-pixel vector path: every image's pixel count and the source pointers must keep 4-byte / 16-byte alignment
+    const int vec = (P0 % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_bgr) & 3) == 0) && (!d_depth_m || (reinterpret_cast<uintptr_t>(d_depth_m) & 15) == 0);
+    uint8_t* gray = c->gray[frame] + lvl_at(c->geom, 0, first);
+    uint16_t* depth = (d_depth_m && c->depth[frame]) ? c->depth[frame] + lvl_at(c->geom, 0, first) : nullptr;
+    for (int z0 = 0; z0 < count; z0 += 32768) {
+        const int nz = (count - z0 < 32768) ? count - z0 : 32768;
+        dim3 grid((unsigned)((P0 / 4 + 1 + 255) / 256), (unsigned)nz);
+        ingest_raw_kernel<<<grid, 256, 0, c->stream>>>(d_bgr + (long long)z0 * P0 * 3, d_depth_m ? d_depth_m + (long long)z0 * P0 : nullptr,
+                                                       gray + (long long)z0 * P0, depth ? depth + (long long)z0 * P0 : nullptr, P0, P0, vec);
+        c->launches++;
+    }
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}

@@ -461,9 +461,19 @@ template <typename T> int ph_alloc(T** p, size_t n) {
 
 extern "C" {
 
+#define PH_CREATE_CUDA(call)                                                                    \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess) {                                                               \
+            dvo_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            dvo_photo_destroy(c);                                                               \
+            return DVO_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
 int dvo_photo_create(const dvo_photo_config* cfg, dvo_photo_ctx** out) {
     if (!cfg || !out) { dvo_set_error("dvo_photo_create: null argument"); return DVO_ERR_ARG; }
-    if (cfg->levels < 1 || cfg->levels > PH_MAX_LEVELS || cfg->max_batch < 1 || cfg->width < 8 || cfg->height < 8 ||
+    if (cfg->levels < 1 || cfg->levels > PH_MAX_LEVELS || cfg->max_batch < 1 || cfg->max_batch > 65535 || cfg->width < 8 || cfg->height < 8 ||
         (cfg->width % (1 << (cfg->levels - 1))) || (cfg->height % (1 << (cfg->levels - 1)))) {
         dvo_set_error("dvo_photo_create: bad config %dx%d levels=%d (dimensions must be divisible by 2^(levels-1))", cfg->width, cfg->height, cfg->levels);
         return DVO_ERR_ARG;
@@ -485,7 +495,7 @@ int dvo_photo_create(const dvo_photo_config* cfg, dvo_photo_ctx** out) {
     long long acc = 0;
     for (int l = 0; l < g.L; ++l) { g.w[l] = cfg->width >> l; g.h[l] = cfg->height >> l; g.P[l] = g.w[l] * g.h[l]; g.off[l] = acc * g.Bmax; acc += g.P[l]; }
     g.total = acc * g.Bmax;
-    DVO_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    PH_CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
     c->maxblk = (g.P[0] + PH_THREADS * 8 - 1) / (PH_THREADS * 8);
     const size_t B = g.Bmax, P0 = g.P[0];
@@ -494,10 +504,10 @@ int dvo_photo_create(const dvo_photo_config* cfg, dvo_photo_ctx** out) {
     for (int f = 0; f < 2; ++f) { A(ph_alloc(&c->bgr[f], B * P0 * 3)); A(ph_alloc(&c->gray[f], (size_t)g.total)); A(ph_alloc(&c->depth[f], (size_t)g.total)); }
     A(ph_alloc(&c->winner, B * P0)); A(ph_alloc(&c->partial, B * c->maxblk * PH_NACC)); A(ph_alloc(&c->A, B * g.L * 36)); A(ph_alloc(&c->st, B));
     if (rc != DVO_OK) { dvo_photo_destroy(c); return rc; }
-    DVO_CUDA(cudaMemsetAsync(c->st, 0, sizeof(PhState) * B, c->stream));
-    DVO_CUDA(cudaMemsetAsync(c->A, 0, sizeof(double) * B * g.L * 36, c->stream));
+    PH_CREATE_CUDA(cudaMemsetAsync(c->st, 0, sizeof(PhState) * B, c->stream));
+    PH_CREATE_CUDA(cudaMemsetAsync(c->A, 0, sizeof(double) * B * g.L * 36, c->stream));
     dvo_photo_set_pose(c, 0, g.Bmax, nullptr);
-    DVO_CUDA(cudaStreamSynchronize(c->stream));
+    PH_CREATE_CUDA(cudaStreamSynchronize(c->stream));
     *out = c;
     return DVO_OK;
 }
@@ -566,16 +576,21 @@ int dvo_photo_prepare_ref(dvo_photo_ctx* c, int first, int count, int compat) {
 
 int dvo_photo_set_pose(dvo_photo_ctx* c, int first, int count, const double* R9T3) {
     if (!ph_range_ok(c, first, count)) return DVO_ERR_ARG;
+    if (count == 0) return DVO_OK;
     std::vector<double> id((size_t)12 * count, 0.0);
     if (R9T3) memcpy(id.data(), R9T3, sizeof(double) * 12 * count);
     else for (int i = 0; i < count; ++i) { id[12 * (size_t)i] = 1.0; id[12 * (size_t)i + 4] = 1.0; id[12 * (size_t)i + 8] = 1.0; }
     double* d = nullptr;
     DVO_CUDA(cudaMalloc((void**)&d, sizeof(double) * 12 * count));
-    DVO_CUDA(cudaMemcpyAsync(d, id.data(), sizeof(double) * 12 * count, cudaMemcpyHostToDevice, c->stream));
-    ph_init_state_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(c->st, first, count, d, 0.0);
-    c->launches++;
-    DVO_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d);
+    cudaError_t e = cudaMemcpyAsync(d, id.data(), sizeof(double) * 12 * count, cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        ph_init_state_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(c->st, first, count, d, 0.0);
+        c->launches++;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);                                   // released on every path
+    DVO_CUDA(e);
     return DVO_OK;
 }
 
@@ -659,6 +674,24 @@ int dvo_photo_get_level(dvo_photo_ctx* c, int slot, int frame, int level, int wh
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
     cudaFree(d_out); cudaFree(d_bgr);
     if (e != cudaSuccess) { dvo_set_error("dvo_photo_get_level: %s", cudaGetErrorString(e)); return DVO_ERR_CUDA; }
+    return DVO_OK;
+}
+
+// PyramidalStorageStruct::addLevel with caller-provided images (src/PyramidalStorage.cpp:38-65): replaces one stored level image.
+// The derived members (X, Y, Z, J, *Vals) are functions of (im_r, dim_r, K, level) and are re-evaluated by the kernels;
+// follow with dvo_photo_prepare_ref to refresh A = J^T J.
+int dvo_photo_put_level(dvo_photo_ctx* c, int slot, int frame, int level, int which, const void* src, size_t bytes) {
+    if (!ph_range_ok(c, slot, 1) || level < 0 || level >= c->g.L || (frame != 0 && frame != 1) || !src) { dvo_set_error("dvo_photo_put_level: bad argument"); return DVO_ERR_ARG; }
+    const PhGeom& g = c->g;
+    const size_t P = g.P[level];
+    void* dst = nullptr; size_t need = 0;
+    if (which == DVO_PHOTO_GRAY) { dst = c->gray[frame] + ph_at(g, level, slot); need = P; }
+    else if (which == DVO_PHOTO_DEPTH) { dst = c->depth[frame] + ph_at(g, level, slot); need = P * 2; }
+    else if (which == DVO_PHOTO_BGR && level == 0) { dst = c->bgr[frame] + (size_t)slot * g.P[0] * 3; need = P * 3; }
+    else { dvo_set_error("dvo_photo_put_level: only GRAY / DEPTH (any level) and BGR (level 0) are stored on the device"); return DVO_ERR_ARG; }
+    if (bytes != need) { dvo_set_error("dvo_photo_put_level: expected %zu bytes, got %zu", need, bytes); return DVO_ERR_ARG; }
+    DVO_CUDA(cudaMemcpyAsync(dst, src, need, cudaMemcpyHostToDevice, c->stream));
+    DVO_CUDA(cudaStreamSynchronize(c->stream));
     return DVO_OK;
 }
 

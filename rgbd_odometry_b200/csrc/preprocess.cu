@@ -776,42 +776,56 @@ int launch_normgrad_into(dvo_ctx* c, int slot, int level, float4* d_out) {
 // with the same IEEE operations normgrad_kernel uses, so every value stays bit-identical.
 // Thread <-> texel of the blocked layout (stores are contiguous); the five d2 loads hit L1 / L2.
 // =====================================================================================================
-struct PackArgs { const int32_t* d2; uint2* tex8; int w, h, P, Pt, tw, first; };
+struct PackArgs { const int32_t* d2; uint2* tex8; int w, h, P, Pt, tw, th, first; };
 
+// One CTA = a 64x8-pixel region = 16x2 tiles: the d2 values (plus a one-pixel halo) are staged through shared memory with
+// row-contiguous loads, every thread assembles two texels, and each warp stores 256 contiguous bytes (two whole tiles).
+constexpr int PACK_RW = 64, PACK_RH = 8;
 __global__ void __launch_bounds__(256) pack_texel_kernel(PackArgs a) {
-    const int b = a.first + blockIdx.y;
-    const int i = blockIdx.x * 256 + threadIdx.x;
-    if (i >= a.Pt) return;
-    const int tile = i >> 4, k = i & 15;
-    const int ty = tile / a.tw, tx = tile - ty * a.tw;
-    const int y = (ty << 2) | ((k >> 2) & 2) | ((k >> 1) & 1);
-    const int x = (tx << 2) | ((k >> 1) & 2) | (k & 1);
+    __shared__ int tile[PACK_RH + 2][PACK_RW + 2 + 1];
+    const int b = a.first + blockIdx.z;
     const int w = a.w, h = a.h;
-    uint2 out = make_uint2(DVO_TEX_ESCAPE, 0u);
-    if (x < w && y < h) {
-        const int32_t* __restrict__ d = a.d2 + (long long)b * a.P + (long long)y * w + x;
-        const int c = __ldg(d);
-        const bool bx = (x == 0 || x == w - 1), by = (y == 0 || y == h - 1);
-        const int dl = bx ? 0 : __ldg(d - 1) - c, dr = bx ? 0 : __ldg(d + 1) - c;
-        const int du = by ? 0 : __ldg(d - w) - c, dd = by ? 0 : __ldg(d + w) - c;
-        const int lo = min(min(dl, dr), min(du, dd)), hi = max(max(dl, dr), max(du, dd));
-        if (c < 65536 && lo >= -512 && hi <= 511) {
-            out.x = (unsigned)c | (((unsigned)dl & 0x3FFu) << 16);
-            out.y = ((unsigned)dr & 0x3FFu) | (((unsigned)du & 0x3FFu) << 10) | (((unsigned)dd & 0x3FFu) << 20);
-        }
+    const int x0 = blockIdx.x * PACK_RW, y0 = blockIdx.y * PACK_RH;
+    const int32_t* __restrict__ d = a.d2 + (long long)b * a.P;
+    for (int i = threadIdx.x; i < (PACK_RH + 2) * (PACK_RW + 2); i += 256) {
+        const int ry = i / (PACK_RW + 2), rx = i - ry * (PACK_RW + 2);
+        const int y = y0 + ry - 1, x = x0 + rx - 1;
+        tile[ry][rx] = (x >= 0 && x < w && y >= 0 && y < h) ? __ldg(d + (long long)y * w + x) : 0;
     }
-    a.tex8[(long long)b * a.Pt + i] = out;
+    __syncthreads();
+    uint2* __restrict__ out = a.tex8 + (long long)b * a.Pt;
+#pragma unroll
+    for (int r = 0; r < PACK_RH / 4; ++r) {
+        const int ty = blockIdx.y * (PACK_RH / 4) + r, tx = blockIdx.x * (PACK_RW / 4) + (threadIdx.x >> 4);
+        if (ty >= a.th || tx >= a.tw) continue;
+        const int k = threadIdx.x & 15;
+        const int ly = (r << 2) | ((k >> 2) & 2) | ((k >> 1) & 1), lx = ((threadIdx.x >> 4) << 2) | ((k >> 1) & 2) | (k & 1);
+        const int y = y0 + ly, x = x0 + lx;
+        uint2 t = make_uint2(DVO_TEX_ESCAPE, 0u);
+        if (x < w && y < h) {
+            const int c = tile[ly + 1][lx + 1];
+            const bool bx = (x == 0 || x == w - 1), by = (y == 0 || y == h - 1);
+            const int dl = bx ? 0 : tile[ly + 1][lx] - c, dr = bx ? 0 : tile[ly + 1][lx + 2] - c;
+            const int du = by ? 0 : tile[ly][lx + 1] - c, dd = by ? 0 : tile[ly + 2][lx + 1] - c;
+            const int lo = min(min(dl, dr), min(du, dd)), hi = max(max(dl, dr), max(du, dd));
+            if (c < 65536 && lo >= -512 && hi <= 511) {
+                t.x = (unsigned)c | (((unsigned)dl & 0x3FFu) << 16);
+                t.y = ((unsigned)dr & 0x3FFu) | (((unsigned)du & 0x3FFu) << 10) | (((unsigned)dd & 0x3FFu) << 20);
+            }
+        }
+        out[(((long long)ty * a.tw + tx) << 4) + k] = t;
+    }
 }
 
 int launch_pack(dvo_ctx* c, int first, int count) {
     const PyrGeom& g = c->geom;
     for (int l = 0; l < g.L; ++l) {
         PackArgs a; a.d2 = c->d2 + g.off[l]; a.tex8 = c->tex8 + g.offt[l];
-        a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.Pt = g.Pt[l]; a.tw = g.tw[l];
-        for (int z0 = 0; z0 < count; z0 += 32768) {          // gridDim.y limit is 65535
+        a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.Pt = g.Pt[l]; a.tw = g.tw[l]; a.th = (g.h[l] + 3) >> 2;
+        for (int z0 = 0; z0 < count; z0 += 32768) {          // gridDim.z limit is 65535
             a.first = first + z0;
             const int nz = (count - z0 < 32768) ? count - z0 : 32768;
-            dim3 grid((g.Pt[l] + 255) / 256, nz);
+            dim3 grid((a.tw + PACK_RW / 4 - 1) / (PACK_RW / 4), (a.th + PACK_RH / 4 - 1) / (PACK_RH / 4), nz);
             pack_texel_kernel<<<grid, 256, 0, c->stream>>>(a);
             c->launches++;
         }

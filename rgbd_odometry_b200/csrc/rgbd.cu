@@ -344,7 +344,7 @@ int rg_level_dim(int dim, int level) { return (int)nearbyint((double)dim * ldexp
 extern "C" {
 
 int dvo_rgbd_create(const dvo_rgbd_config* cfg, dvo_rgbd_ctx** out) {
-    if (!cfg || !out || cfg->width < 8 || cfg->height < 8 || cfg->levels < 2 || cfg->levels > RG_MAX_LEVELS || cfg->max_batch < 1) {
+    if (!cfg || !out || cfg->width < 8 || cfg->height < 8 || cfg->levels < 2 || cfg->levels > RG_MAX_LEVELS || cfg->max_batch < 1 || cfg->max_batch > 65535) {
         dvo_set_error("dvo_rgbd_create: bad configuration"); return DVO_ERR_ARG;
     }
     int ndev = 0;

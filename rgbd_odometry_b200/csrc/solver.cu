@@ -487,15 +487,17 @@ struct SolveArgs {
     const float *X, *Y, *Z; const int* npts; const unsigned* nedge_now; const float4* texel;
     const uint2* tex8; const int32_t* d2; const unsigned* maxd2;
     const double* pose0; double* pose; dvo_pair_info* info; double* trace; int trace_iters; const int* order; const unsigned char* active;
+    float* energy;
     dvo_solver_params prm; int first;
 };
 
 // One iteration's serial tail (thread 0): best tracking, step computation, pose update.  Returns 1 to stop the level.
 __device__ __forceinline__ int solver_step(SolverState& S, const double* tot, int nvis, int N, int itr, const dvo_solver_params& prm,
-                                        bool need_h, dvo_pair_info* info, int level, double* trace_rec) {
+                                        bool need_h, dvo_pair_info* info, int level, double* trace_rec, float* energy_rec) {
     const float ratio = (float)nvis / (float)N;                                   // :457
     const float energy = (float)sqrt(tot[6]);                                      // :1310-1312
     info->iterations_run[level] = itr + 1;
+    if (itr < DVO_ENERGY_ITERS) energy_rec[itr] = energy;                          // energyAtEachIteration (:634, :690)
     double Hf[36];
     if (need_h) {
         int idx = 8;
@@ -666,7 +668,7 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
                 double* tr = nullptr;
                 if (a.trace && itr < a.trace_iters)
                     tr = a.trace + (((long long)b * L + l) * a.trace_iters + itr) * DVO_TRACE_DOUBLES;
-                s_stop = solver_step(S, s_tot, s_nvtot, N, itr, a.prm, NEED_H, &s_info, l, tr);
+                s_stop = solver_step(S, s_tot, s_nvtot, N, itr, a.prm, NEED_H, &s_info, l, tr, a.energy + ((long long)b * L + l) * DVO_ENERGY_ITERS);
                 for (int k = 0; k < 9; ++k) s_pose.R[k] = (float)S.cR[k];                      // pose of the next iteration (:673-674)
                 for (int k = 0; k < 3; ++k) s_pose.T[k] = (float)S.cT[k];
             }
@@ -736,6 +738,29 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
         int idx = 8;
         for (int r = 0; r < 6; ++r) for (int c = r; c < 6; ++c) { a.out[6 + 6 * r + c] = s_tot[idx]; a.out[6 + 6 * c + r] = s_tot[idx]; ++idx; }
         a.out[42] = s_tot[6]; a.out[43] = (double)s_nvtot;
+    }
+}
+
+// ------------------------------------------------------------------ packed texels -> float images (parity inspection)
+// {DTn, gx, gy, w} of every pixel of one slot / level through exactly the code path the solver uses (packed texel or
+// escaped d2 stencil, lookup table or direct evaluation), so that dvo_get_level_buffer checks that path pixel by pixel.
+struct ResolveArgs { PyrGeom geom; const uint2* tex8; const int32_t* d2; const unsigned* maxd2; const unsigned* nedge_now; int slot, level; float4* out; };
+
+__global__ void __launch_bounds__(256) resolve_texels_kernel(ResolveArgs a) {
+    extern __shared__ float s_lut[];
+    const int b = a.slot, l = a.level, L = a.geom.L;
+    const int w = a.geom.w[l], h = a.geom.h[l], tw = a.geom.tw[l];
+    const unsigned mx2 = a.maxd2[(long long)b * L + l];
+    const float scale = dtn_scale(mx2, a.nedge_now[(long long)b * L + l]);
+    build_lut<256>(s_lut, mx2, scale);
+    __syncthreads();
+    const uint2* __restrict__ tex = a.tex8 + tex_at(a.geom, l, b);
+    const int32_t* __restrict__ d2 = a.d2 + lvl_at(a.geom, l, b);
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < w * h; i += gridDim.x * 256) {
+        const int y = i / w, x = i - y * w;
+        Stencil s;
+        if (!unpack_texel(__ldg(tex + tex_index(x, y, tw)), s)) stencil_from_d2(d2, w, h, x, y, s);
+        a.out[i] = texel_values(s, s_lut, scale);
     }
 }
 
@@ -824,7 +849,7 @@ int launch_solve(dvo_ctx* c, int first, int count, const dvo_solver_params* p) {
     a.geom = c->geom; a.K = c->K; a.X = c->ptsX; a.Y = c->ptsY; a.Z = c->ptsZ; a.npts = c->npts;
     a.nedge_now = c->nedge + (size_t)DVO_FRAME_NOW * c->geom.Bmax * c->geom.L; a.texel = c->texel;
     a.tex8 = c->tex8; a.d2 = c->d2; a.maxd2 = c->maxd2;
-    a.pose0 = c->pose0; a.pose = c->pose; a.info = c->info; a.trace = c->trace; a.trace_iters = c->cfg.trace_iters;
+    a.pose0 = c->pose0; a.pose = c->pose; a.info = c->info; a.trace = c->trace; a.trace_iters = c->cfg.trace_iters; a.energy = c->energy;
     a.prm = *p; a.first = first;
     // H is needed by GN / LM, and by SUBGRAD_REF only when a trace is kept (parity tests on J^T W J)
     const bool need_h = (p->solver != DVO_SOLVER_SUBGRAD_REF) || (c->trace != nullptr);
@@ -874,6 +899,18 @@ int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac
     a.pose = d_pose12; a.slot = slot; a.level = level; a.weight = weight; a.huber_k = huber_k; a.out = d_out;
     a.eps = d_eps; a.w = d_w; a.u = d_u; a.v = d_v; a.J = d_J;
     return c->texel_mode ? launch_eval_tex<1>(c, a, jac, arith, residual) : launch_eval_tex<0>(c, a, jac, arith, residual);
+}
+
+int launch_resolve_texels(dvo_ctx* c, int slot, int level, float4* d_out) {
+    ResolveArgs a;
+    a.geom = c->geom; a.tex8 = c->tex8; a.d2 = c->d2; a.maxd2 = c->maxd2;
+    a.nedge_now = c->nedge + (size_t)DVO_FRAME_NOW * c->geom.Bmax * c->geom.L; a.slot = slot; a.level = level; a.out = d_out;
+    DVO_CUDA((optin_lut_smem<ResolveArgs, resolve_texels_kernel>(c->cfg.device)));
+    const int blocks = (c->geom.P[level] + 255) / 256;
+    resolve_texels_kernel<<<blocks < 64 ? blocks : 64, 256, LUT_BYTES, c->stream>>>(a);
+    c->launches++;
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
 }
 
 int launch_gop(dvo_ctx* c, int nseq, int nframes, const int* d_kind, const double* d_rel, double* d_out) {

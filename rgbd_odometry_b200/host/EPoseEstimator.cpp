@@ -58,7 +58,7 @@ void EPoseEstimator::setRefFrame(dvo::ImageView& rgb, dvo::ImageView& depth) {
     dvo_photo_config cfg; cfg.levels = 5; while (cfg.levels > 1 && ((rgb.cols % (1 << (cfg.levels - 1))) || (rgb.rows % (1 << (cfg.levels - 1))))) --cfg.levels;
     rc = dvo_photo_prepare_ref(ctx_, 0, 1, compat_ ? 1 : 0);   // evaluateJacobian for every level (:88-102)
     assert(rc == 0);
-    for (int lvl = 0; lvl < cfg.levels; ++lvl) { setRefPyramidalImages(lvl); pydStore.addLevel(lvl, lvl); }
+    for (int lvl = 0; lvl < cfg.levels; ++lvl) { setRefPyramidalImages(lvl); pydStore.addLevelFromDevice(lvl, lvl); }   // :88-102, no host copies
     isJEvaluated = true; is3dCordsReady = true;
     (void)rc;
 }

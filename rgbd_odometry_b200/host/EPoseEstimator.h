@@ -21,6 +21,19 @@ public:
     void setRefPyramidalImages(int level);                          // :266-290
     float estimate(dvo::Matrix3d& initR, dvo::Vector3d& initT);     // :135-209
     void xdebug();
+#ifdef DVO_HAVE_OPENCV
+    // the reference's signatures (include/EPoseEstimator.h:38-39)
+    void setRefFrame(cv::Mat& rgb, cv::Mat& depth) { dvo::ImageView r(rgb), d(depth); setRefFrame(r, d); }
+    void setNowFrame(cv::Mat& rgb, cv::Mat& depth) { dvo::ImageView r(rgb), d(depth); setNowFrame(r, d); }
+#endif
+#ifdef DVO_HAVE_EIGEN
+    float estimate(Eigen::Matrix3d& initR, Eigen::Vector3d& initT) {       // include/EPoseEstimator.h:45
+        dvo::Matrix3d R(initR); dvo::Vector3d T(initT);
+        const float v = estimate(R, T);
+        initR = static_cast<Eigen::Matrix3d>(R); initT = static_cast<Eigen::Vector3d>(T);
+        return v;
+    }
+#endif
 
     // public members, as in the reference ("//private:" is commented out, include/EPoseEstimator.h:54)
     bool cameraIntrinsicsReady;

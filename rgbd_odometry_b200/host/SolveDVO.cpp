@@ -19,7 +19,11 @@ SolveDVO::SolveDVO(int width, int height, int levels)
     solver.arithmetic = DVO_ARITH_EXACT; solver.huber_k = 1.345f; solver.lm_lambda0 = 1e-3;
     solver.residual = DVO_RESIDUAL_DT_FLOOR;               // set to DVO_RESIDUAL_DT_INTERP for the __INTERPOLATE_DISTANCE_TRANSFORM build (:443)
     std::memset(&lastInfo, 0, sizeof(lastInfo));
-    dvo_config cfg = {width, height, levels, 1, 0, /*keep_now_depth*/ 1, /*trace_iters*/ 128};
+    casualFolder = "TUM_RGBD/fr1_rpy"; casualRefIndex = 80; casualNowIndex = 85; casualIterations = 100;   // :2397, :2414, :2428
+    fileLoopFolder = "TUM_RGBD/fr2_desk"; fileLoopStart = 300; fileLoopEnd = 3000; fileLoopIterations = 500;   // :2460-2463, :2513
+    dryFrames = 0;
+    // no per-iteration trace: energyAtEachIteration comes from dvo_get_energies, so the class API runs the production kernels
+    dvo_config cfg = {width, height, levels, 1, 0, /*keep_now_depth*/ 1, /*trace_iters*/ 0};
     const int rc = dvo_create(&cfg, &ctx_);
     if (rc != DVO_OK) { std::fprintf(stderr, "SolveDVO: %s\n", dvo_last_error()); std::abort(); }   // no CPU fallback
 }
@@ -117,7 +121,7 @@ void SolveDVO::preProcessRefFrame() {
 void SolveDVO::runIterations(int level, int maxIterations, dvo::Matrix3d& cR, dvo::Vector3d& cT, dvo::VectorXf& energyAtEachIteration,
                              dvo::VectorXf& finalEpsilons, dvo::MatrixXf& finalReprojections, int& bestEnergyIndex, float& finalVisibleRatio) {
     assert(level >= 0 && level < levels_);                      // :625 (the reference asserts level <= 3)
-    assert(maxIterations > 0 && maxIterations <= 128);
+    assert(maxIterations > 0);                                 // energies beyond the first 128 iterations are not recorded (left 0)
     assert(isRefFrameAvailable && isNowFrameAvailable && isCameraIntrinsicsAvailable);
     dvo_solver_params p = solver;
     for (int l = 0; l < DVO_MAX_LEVELS; ++l) p.iters[l] = 0;
@@ -130,10 +134,10 @@ void SolveDVO::runIterations(int level, int maxIterations, dvo::Matrix3d& cR, dv
     check(dvo_get_poses(ctx_, 0, 1, pose, &lastInfo, DVO_MEM_HOST), "runIterations");
     for (int i = 0; i < 9; ++i) cR.m[i] = pose[i];
     for (int i = 0; i < 3; ++i) cT.v[i] = pose[9 + i];
-    std::vector<double> tr((size_t)128 * 56);
-    check(dvo_get_trace(ctx_, 0, level, tr.data()), "runIterations");
+    float en[128];
+    check(dvo_get_energies(ctx_, 0, level, en, 128), "runIterations");
     energyAtEachIteration.assign(maxIterations, 0.f);           // :634
-    for (int k = 0; k < maxIterations && k < lastInfo.iterations_run[level]; ++k) energyAtEachIteration[k] = (float)tr[(size_t)k * 56 + 42];
+    for (int k = 0; k < maxIterations && k < 128 && k < lastInfo.iterations_run[level]; ++k) energyAtEachIteration[k] = en[k];
     const int n = lastInfo.npts[level];
     finalEpsilons.assign(n, 0.f); finalReprojections.rows = 3; finalReprojections.cols = n; finalReprojections.data.assign((size_t)3 * n, 1.f);
     if (n > 0) {
@@ -185,5 +189,89 @@ void SolveDVO::loopFromFrames(const uint8_t* gray, const uint16_t* depth, int nf
         dvo::ImageView g(gray + P * t, height_, width_, dvo::U8C1), d(depth + P * t, height_, width_, dvo::U16C1);
         setRcvdFrame(g, d);
         processFrame();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------- the reference's loops
+void SolveDVO::setXmlFrameSource(const char* folder, int start, int end) {
+    const std::string dir(folder);
+    int next = start;
+    frameSource_ = [dir, next, end](SolveDVO& self) mutable -> bool {
+        if (next > end) { std::fprintf(stderr, "Done with all files...Quitting...\n"); return false; }          // :1955-1959
+        char name[1000];
+        std::snprintf(name, sizeof(name), "%s/framemono_%04d.xml", dir.c_str(), next);                            // :1961
+        if (!self.loadFromFile(name)) { std::fprintf(stderr, "No More files, Quitting..\n"); return false; }     // :1963-1966
+        ++next;
+        return true;
+    };
+}
+
+// loop() (:1896-2373): the first available frame becomes the reference / first key frame (:1950-2030), every later frame goes
+// through setRcvdFrameAsNowFrame, the coarse-to-fine runIterations and the key-frame rule -- processFrame() is one turn.
+void SolveDVO::loop() {
+    assert(frameSource_ && "setFrameSource / setXmlFrameSource first (replaces the ROS subscription)");
+    while (frameSource_(*this)) {
+        if (!isFrameAvailable) continue;                                                                          // :1971, :2055
+        processFrame();
+    }
+}
+
+// loopDry() (:1803-1893): frames are consumed and set as the now frame (pyramid, edges, distance transform), nothing is solved.
+void SolveDVO::loopDry() {
+    assert(frameSource_ && "setFrameSource / setXmlFrameSource first");
+    dryFrames = 0;
+    while (frameSource_(*this)) {
+        if (!isFrameAvailable) continue;                                                                          // :1843
+        setRcvdFrameAsNowFrame();                                                                                 // :1848
+        isFrameAvailable = false;                                                                                 // :1886
+        ++dryFrames;                                                                                              // nFrame++ (:1888)
+    }
+}
+
+// casualTestFunction() (:2377-2442): reference frame from one dump, now frame from another, runIterations(0, 100, ...) from
+// identity; the energies it prints to stdout are kept in casualEnergies as well.
+void SolveDVO::casualTestFunction() {
+    char frameFileName[1000];
+    cR_64 = dvo::Matrix3d::Identity(); cT_64 = dvo::Vector3d::Zero();                                             // :2383-2384
+    dvo::VectorXf epsilonVec; dvo::MatrixXf reprojections; int bestEnergyIndex = -1; float visibleRatio = 0.0f;
+    std::snprintf(frameFileName, sizeof(frameFileName), "%s/framemono_%04d.xml", casualFolder.c_str(), casualRefIndex);
+    if (!loadFromFile(frameFileName)) { std::fprintf(stderr, "Cannot open file1\n"); return; }                   // :2399-2401 (the reference carries on and asserts)
+    setRcvdFrameAsRefFrame(); preProcessRefFrame();                                                               // :2405-2406
+    std::snprintf(frameFileName, sizeof(frameFileName), "%s/framemono_%04d.xml", casualFolder.c_str(), casualNowIndex);
+    if (!loadFromFile(frameFileName)) { std::fprintf(stderr, "Cannot open file1\n"); return; }                   // :2416-2418
+    setRcvdFrameAsNowFrame();                                                                                     // :2422
+    runIterations(0, casualIterations, cR_64, cT_64, casualEnergies, epsilonVec, reprojections, bestEnergyIndex, visibleRatio);   // :2428
+    for (size_t i = 0; i < casualEnergies.size(); ++i) std::printf("%g\n", casualEnergies[i]);                    // :2438-2441
+}
+
+// loopFromFile() (:2448-2600): dumps START..END-1.  A file whose index is a multiple of 5 becomes the reference -- after its pose
+// against the outgoing reference has been estimated when it is not the first (:2507-2531) -- and then EVERY file, the new
+// reference included (the `else` is commented out, :2533-2544), is set as the now frame and aligned with one
+// runIterations(0, 500) at level 0.  nT = keyT + keyR cT, nR = keyR cR (:2547-2548) is kept per file in fileLoopR / fileLoopT
+// (the reference hands it to its RViz publisher).
+void SolveDVO::loopFromFile() {
+    char frameFileName[1000];
+    dvo::VectorXf energy, eps; dvo::MatrixXf reproj; int bestIdx = -1; float vis = 0.f;
+    dvo::Matrix3d cR = dvo::Matrix3d::Identity(), keyR = dvo::Matrix3d::Identity(), nR = dvo::Matrix3d::Identity();
+    dvo::Vector3d cT = dvo::Vector3d::Zero(), keyT = dvo::Vector3d::Zero(), nT = dvo::Vector3d::Zero();
+    fileLoopR.clear(); fileLoopT.clear();
+    for (int iFrameNum = fileLoopStart; iFrameNum < fileLoopEnd; ++iFrameNum) {
+        std::snprintf(frameFileName, sizeof(frameFileName), "%s/framemono_%04d.xml", fileLoopFolder.c_str(), iFrameNum);
+        if (!loadFromFile(frameFileName)) { std::fprintf(stderr, "No More files, Quitting..\n"); break; }         // :2500-2503
+        if (iFrameNum % 5 == 0) {                                                                                 // :2507
+            if (iFrameNum > fileLoopStart) {
+                setRcvdFrameAsNowFrame();                                                                         // :2513
+                runIterations(0, fileLoopIterations, cR, cT, energy, eps, reproj, bestIdx, vis);                  // :2517
+            }
+            keyR = nR; keyT = nT;                                                                                 // :2519-2520
+            lastRefFrame = iFrameNum;
+            setRcvdFrameAsRefFrame(); preProcessRefFrame();                                                       // :2523-2525
+            cR = dvo::Matrix3d::Identity(); cT = dvo::Vector3d::Zero();                                           // :2527-2528
+        }
+        setRcvdFrameAsNowFrame();                                                                                 // :2535
+        runIterations(0, fileLoopIterations, cR, cT, energy, eps, reproj, bestIdx, vis);                          // :2538
+        nT = keyT + keyR * cT; nR = keyR * cR;                                                                    // :2547-2548
+        fileLoopR.push_back(nR); fileLoopT.push_back(nT);
+        isFrameAvailable = false;
     }
 }

@@ -80,6 +80,60 @@ int hostapi_eposeestimator(const uint8_t* ref_bgr, const uint16_t* ref_depth, co
     return e.pydStore.size();
 }
 
+// PyramidalStorageStruct::addLevel with the reference's eleven-argument signature (include/PyramidalStorage.h:42-48).
+// (1) an UNBOUND storage is pure storage: what is pushed comes back from getLevel, entry by push order, `level` ignored;
+// (2) a storage bound to an estimator that was given reference frame A receives the eleven arrays of reference frame B (taken from
+//     a second estimator): estimate() must then behave exactly like an estimator whose reference frame is B.
+// Returns 0 when every storage round trip is exact; R9 / T3 / A36 = pose and normal matrix of (2).
+int hostapi_pydstore_add_level(const uint8_t* bgrA, const uint16_t* depthA, const uint8_t* bgrB, const uint16_t* depthB, const uint8_t* now_bgr,
+                               const uint16_t* now_depth, int W, int H, double fx, double fy, double cx, double cy, int level, int iters,
+                               double huber_k, double lambda0, double* R9, double* T3, double* A36, int* sizes) {
+    dvo::ImageView a_rgb(bgrA, H, W, dvo::U8C3), a_d(depthA, H, W, dvo::U16C1), b_rgb(bgrB, H, W, dvo::U8C3), b_d(depthB, H, W, dvo::U16C1);
+    dvo::ImageView n_rgb(now_bgr, H, W, dvo::U8C3), n_d(now_depth, H, W, dvo::U16C1);
+    EPoseEstimator eA(false), eB(false);
+    eA.setCameraMatrix(fx, fy, cx, cy); eB.setCameraMatrix(fx, fy, cx, cy);
+    eA.iterations = iters; eA.huber_k = huber_k; eA.lm_lambda0 = lambda0;
+    eA.setRefFrame(a_rgb, a_d); eA.setNowFrame(n_rgb, n_d);
+    eB.setRefFrame(b_rgb, b_d);
+    const int nlev = eB.pydStore.size();
+    struct Lvl { std::vector<uint8_t> c, g; std::vector<uint16_t> d; dvo::ArrayXXd X, Y, Z, gv, rv, gr, bv; dvo::MatrixXd J; int rows, cols; };
+    std::vector<Lvl> lv(nlev);
+    for (int l = 0; l < nlev; ++l) { Lvl& q = lv[l]; eB.pydStore.getLevel(l, q.c, q.g, q.d, q.X, q.Y, q.Z, q.J, q.gv, q.rv, q.gr, q.bv); q.rows = H >> l; q.cols = W >> l; }
+    int bad = 0;
+    auto same = [&](PyramidalStorageStruct& st, int idx, const Lvl& q) {
+        Lvl r; st.getLevel(idx, r.c, r.g, r.d, r.X, r.Y, r.Z, r.J, r.gv, r.rv, r.gr, r.bv);
+        return r.c == q.c && r.g == q.g && r.d == q.d && r.X.data == q.X.data && r.Y.data == q.Y.data && r.Z.data == q.Z.data && r.J.data == q.J.data &&
+               r.gv.data == q.gv.data && r.rv.data == q.rv.data && r.gr.data == q.gr.data && r.bv.data == q.bv.data && r.J.rows == q.J.rows && r.X.rows == q.X.rows;
+    };
+    {   // (1) unbound: push levels 2 and 1 in that order, with "level" arguments that do not match the push order
+        PyramidalStorageStruct st;
+        for (int k = 0; k < 2; ++k) {
+            Lvl& q = lv[2 - k];
+            st.addLevel(k == 0 ? 4 : 0, dvo::ImageView(q.c.data(), q.rows, q.cols, dvo::U8C3), dvo::ImageView(q.g.data(), q.rows, q.cols, dvo::U8C1),
+                        dvo::ImageView(q.d.data(), q.rows, q.cols, dvo::U16C1), q.X, q.Y, q.Z, q.J, q.gv, q.rv, q.gr, q.bv);
+        }
+        sizes[0] = st.size();
+        if (!same(st, 0, lv[2]) || !same(st, 1, lv[1])) bad |= 1;
+        st.clearPyramid();
+        sizes[1] = st.size();
+    }
+    // (2) bound: replace A's pyramid by B's arrays
+    eA.pydStore.clearPyramid();
+    for (int l = 0; l < nlev; ++l) {
+        Lvl& q = lv[l];
+        eA.pydStore.addLevel(l, dvo::ImageView(q.c.data(), q.rows, q.cols, dvo::U8C3), dvo::ImageView(q.g.data(), q.rows, q.cols, dvo::U8C1),
+                             dvo::ImageView(q.d.data(), q.rows, q.cols, dvo::U16C1), q.X, q.Y, q.Z, q.J, q.gv, q.rv, q.gr, q.bv);
+    }
+    sizes[2] = eA.pydStore.size();
+    for (int l = 0; l < nlev; ++l) if (!same(eA.pydStore, l, lv[l])) bad |= 2;
+    eA.setPyramidalImages(level);
+    std::memcpy(A36, eA.A, 288);
+    dvo::Matrix3d R; dvo::Vector3d T;
+    eA.estimate(R, T);
+    std::memcpy(R9, R.m, 72); std::memcpy(T3, T.v, 24);
+    return bad;
+}
+
 // GOP<float> and GOP<double> replay (explicit instantiations, src/GOP.cpp:244-245)
 int hostapi_gop_replay(int n, const int* kind, const int* reason, const double* rel, double* out19, int* is_key, int* reason_out, int use_float) {
     if (use_float) {
@@ -215,6 +269,71 @@ int hostapi_solvedvo_from_files(const char* ref_xml, const char* now_xml, int W,
     for (int i = 0; i < 9; ++i) R9[i] = cR.m[i];
     for (int i = 0; i < 3; ++i) T3[i] = cT.v[i];
     return 0;
+}
+
+// SolveDVO::loop() / loopDry() over the XML dumps "<folder>/framemono_%04d.xml", start..end (the reference's
+// __DATA_FROM_XML_FILES__ build); out as hostapi_solvedvo_sequence.  Returns the number of frames processed.
+int hostapi_solvedvo_loop_xml(const char* folder, int start, int end, int dry, int W, int H, int levels, float fx, float fy, float cx, float cy,
+                              const int* iters, double* out19, int* is_key, int* reason, int capacity) {
+    SolveDVO s(W, H, levels);
+    s.setIntrinsics(fx, fy, cx, cy);
+    for (int l = 0; l < levels; ++l) s.iterationsConfig[l] = iters[l];
+    s.setXmlFrameSource(folder, start, end);
+    if (dry) { s.loopDry(); return (int)s.dryFrames + (s.gop.size() == 0 && s.isNowFrameAvailable ? 0 : 100000); }
+    s.loop();
+    const int n = s.gop.size() < capacity ? s.gop.size() : capacity;
+    for (int i = 0; i < n; ++i) {
+        const dvo::Pose& p = s.gop.getGlobalPoseAt(i);
+        double* o = out19 + 19 * (size_t)i;
+        std::memcpy(o, s.gop.getGlobalRAt(i).m, 72); std::memcpy(o + 9, s.gop.getGlobalTAt(i).v, 24);
+        o[12] = p.position.x; o[13] = p.position.y; o[14] = p.position.z;
+        o[15] = p.orientation.x; o[16] = p.orientation.y; o[17] = p.orientation.z; o[18] = p.orientation.w;
+        is_key[i] = s.gop.isKeyFrameAt(i); reason[i] = s.gop.getReasonAt(i);
+    }
+    return s.gop.size();
+}
+// SolveDVO::loop() fed by a callback that hands over in-memory frames, skipping every `skip_every`-th turn without a frame
+// (a ros::spinOnce() that delivered nothing): the loop must `continue` on those turns
+int hostapi_solvedvo_loop_callback(const uint8_t* gray, const uint16_t* depth, int nframes, int skip_every, int W, int H, int levels, float fx, float fy,
+                                   float cx, float cy, const int* iters, double* out19) {
+    SolveDVO s(W, H, levels);
+    s.setIntrinsics(fx, fy, cx, cy);
+    for (int l = 0; l < levels; ++l) s.iterationsConfig[l] = iters[l];
+    const size_t P = (size_t)W * H;
+    int t = 0, turn = 0;
+    s.setFrameSource([&](SolveDVO& self) -> bool {
+        if (t >= nframes) return false;
+        if (skip_every > 0 && (++turn % skip_every) == 0) return true;            // nothing arrived this turn
+        self.setRcvdFrame(dvo::ImageView(gray + P * t, H, W, dvo::U8C1), dvo::ImageView(depth + P * t, H, W, dvo::U16C1));
+        ++t;
+        return true;
+    });
+    s.loop();
+    for (int i = 0; i < s.gop.size() && i < nframes; ++i) { double* o = out19 + 19 * (size_t)i; std::memcpy(o, s.gop.getGlobalRAt(i).m, 72); std::memcpy(o + 9, s.gop.getGlobalTAt(i).v, 24); }
+    return s.gop.size();
+}
+// SolveDVO::casualTestFunction(): folder/framemono_<ref>.xml vs folder/framemono_<now>.xml, runIterations(0, iters)
+int hostapi_solvedvo_casual(const char* folder, int ref_index, int now_index, int iterations, int W, int H, int levels, float fx, float fy, float cx,
+                            float cy, double* R9, double* T3, float* energies, int capacity) {
+    SolveDVO s(W, H, levels);
+    s.setIntrinsics(fx, fy, cx, cy);
+    s.casualFolder = folder; s.casualRefIndex = ref_index; s.casualNowIndex = now_index; s.casualIterations = iterations;
+    s.casualTestFunction();
+    std::memcpy(R9, s.cR_64.m, 72); std::memcpy(T3, s.cT_64.v, 24);
+    const int n = (int)s.casualEnergies.size() < capacity ? (int)s.casualEnergies.size() : capacity;
+    for (int i = 0; i < n; ++i) energies[i] = s.casualEnergies[i];
+    return (int)s.casualEnergies.size();
+}
+// SolveDVO::loopFromFile(): out = 12 doubles (nR, nT) per processed file
+int hostapi_solvedvo_loop_from_file(const char* folder, int start, int end, int iterations, int W, int H, int levels, float fx, float fy, float cx,
+                                    float cy, double* out12, int capacity) {
+    SolveDVO s(W, H, levels);
+    s.setIntrinsics(fx, fy, cx, cy);
+    s.fileLoopFolder = folder; s.fileLoopStart = start; s.fileLoopEnd = end; s.fileLoopIterations = iterations;
+    s.loopFromFile();
+    const int n = (int)s.fileLoopR.size() < capacity ? (int)s.fileLoopR.size() : capacity;
+    for (int i = 0; i < n; ++i) { std::memcpy(out12 + 12 * (size_t)i, s.fileLoopR[i].m, 72); std::memcpy(out12 + 12 * (size_t)i + 9, s.fileLoopT[i].v, 24); }
+    return (int)s.fileLoopR.size();
 }
 
 // RGBDOdometry::eventLoop body over an in-memory sequence of BGR / depth frames: out = nframes * 16 doubles (base * T)

@@ -15,6 +15,54 @@ def lib():
     return _h
 
 
+_hcv = None
+
+
+def build_cv_shim(force=False):
+    """tests/cpp/host_capi_cv.cpp compiled against the stand-in OpenCV / Eigen headers (tests/standin_include): exercises the
+    `#ifdef DVO_HAVE_OPENCV / DVO_HAVE_EIGEN` overloads of the host classes.  Returns the path of the built library."""
+    import os, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = os.path.join(root, "tests", "cpp", "host_capi_cv.cpp")
+    out = os.path.join(root, "tests", "cpp", "libdvo_host_cv.so")
+    host = _build.build_host()
+    deps = [src, host] + [os.path.join(root, "rgbd_odometry_b200", "host", f) for f in os.listdir(os.path.join(root, "rgbd_odometry_b200", "host")) if f.endswith(".h")]
+    if force or not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-I", os.path.join(root, "include"), "-I", os.path.join(root, "rgbd_odometry_b200", "host"),
+                               "-I", os.path.join(root, "tests", "standin_include"), "-o", out, src, "-L", os.path.join(root, "rgbd_odometry_b200"),
+                               "-ldvo_host", "-ldvo_b200", "-Wl,-rpath,$ORIGIN/../../rgbd_odometry_b200"])
+    return out
+
+
+def cvlib():
+    global _hcv
+    if _hcv is None:
+        _hcv = C.CDLL(build_cv_shim())
+    return _hcv
+
+
+def cv_eposeestimator(ref_bgr, ref_depth, now_bgr, now_depth, K, level, iters=6, huber_k=10.0, lambda0=1e-3):
+    H, W = ref_depth.shape
+    h, w = H >> level, W >> level
+    R = np.zeros(9); T = np.zeros(3); J = np.zeros((6, h * w)); ok = C.c_int()
+    c = lambda a: np.ascontiguousarray(a).copy()
+    n = cvlib().cvapi_eposeestimator(_p(c(ref_bgr)), _p(c(ref_depth)), _p(c(now_bgr)), _p(c(now_depth)), W, H, C.c_double(K[0]), C.c_double(K[1]),
+                                     C.c_double(K[2]), C.c_double(K[3]), level, iters, C.c_double(huber_k), C.c_double(lambda0), _p(R), _p(T), _p(J),
+                                     C.byref(ok))
+    return {"levels": n, "R": R.reshape(3, 3), "T": T, "J": J.T.copy(), "roundtrip_ok": bool(ok.value)}       # J arrives column-major (Eigen)
+
+
+def cv_solvedvo_run_iterations(ref_gray, ref_depth, now_gray, now_depth, levels, level, max_iter, K):
+    H, W = ref_gray.shape
+    R = np.zeros(9); T = np.zeros(3); en = np.zeros(max_iter, np.float32); cap = W * H
+    eps = np.zeros(cap, np.float32); ru = np.zeros(cap, np.float32); bi = C.c_int(); vr = C.c_float(); gop = np.zeros(12)
+    c = lambda a: np.ascontiguousarray(a).copy()
+    n = cvlib().cvapi_solvedvo_run_iterations(_p(c(ref_gray)), _p(c(ref_depth)), _p(c(now_gray)), _p(c(now_depth)), W, H, levels, C.c_float(K[0]),
+                                              C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3]), level, max_iter, _p(R), _p(T), _p(en), _p(eps), _p(ru),
+                                              C.byref(bi), C.byref(vr), _p(gop))
+    return {"R": R.reshape(3, 3), "T": T, "energies": en, "eps": eps[:n], "u": ru[:n], "best_index": bi.value, "visible_ratio": vr.value, "gop": gop}
+
+
 def _p(a, t=None):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
@@ -73,6 +121,16 @@ def eposeestimator(ref_bgr, ref_depth, now_bgr, now_depth, K, compat, level, ite
     return {"R": R.reshape(3, 3), "T": T, "A": A, "visible": vis.value, "status": st.value, "J": J, "X": X, "gray": g, "levels": nlev}
 
 
+def pydstore_add_level(bgrA, depthA, bgrB, depthB, now_bgr, now_depth, K, level, iters=6, huber_k=10.0, lambda0=1e-3):
+    H, W = depthA.shape
+    R = np.zeros(9); T = np.zeros(3); A = np.zeros((6, 6)); sizes = np.zeros(3, np.int32)
+    c = np.ascontiguousarray
+    bad = lib().hostapi_pydstore_add_level(_p(c(bgrA)), _p(c(depthA)), _p(c(bgrB)), _p(c(depthB)), _p(c(now_bgr)), _p(c(now_depth)), W, H,
+                                           C.c_double(K[0]), C.c_double(K[1]), C.c_double(K[2]), C.c_double(K[3]), level, iters,
+                                           C.c_double(huber_k), C.c_double(lambda0), _p(R), _p(T), _p(A), _p(sizes))
+    return bad, R.reshape(3, 3), T, A, sizes
+
+
 # ---- FrameIO ----
 def store_frame_xml(path, mono_levels, depth_levels):
     H, W = mono_levels[0].shape
@@ -128,6 +186,37 @@ def solvedvo_from_files(ref_xml, now_xml, W, H, levels, iters, K):
                                            C.c_float(K[2]), C.c_float(K[3]), _p(it), _p(R), _p(T))
     assert rc == 0, rc
     return R.reshape(3, 3), T
+
+
+def solvedvo_loop_xml(folder, start, end, W, H, levels, iters, K, dry=False, capacity=256):
+    it = np.array(iters, np.int32)
+    out = np.zeros((capacity, 19)); is_key = np.zeros(capacity, np.int32); reason = np.zeros(capacity, np.int32)
+    n = lib().hostapi_solvedvo_loop_xml(str(folder).encode(), start, end, int(dry), W, H, levels, C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]),
+                                        C.c_float(K[3]), _p(it), _p(out), _p(is_key), _p(reason), capacity)
+    return n, out[:max(0, min(n, capacity))], is_key[:max(0, min(n, capacity))], reason[:max(0, min(n, capacity))]
+
+
+def solvedvo_loop_callback(gray, depth, levels, iters, K, skip_every=0):
+    n, H, W = gray.shape
+    it = np.array(iters, np.int32)
+    out = np.zeros((n, 19))
+    m = lib().hostapi_solvedvo_loop_callback(_p(np.ascontiguousarray(gray, np.uint8)), _p(np.ascontiguousarray(depth, np.uint16)), n, skip_every, W, H,
+                                             levels, C.c_float(K[0]), C.c_float(K[1]), C.c_float(K[2]), C.c_float(K[3]), _p(it), _p(out))
+    return m, out
+
+
+def solvedvo_casual(folder, ref_index, now_index, iterations, W, H, levels, K):
+    R = np.zeros(9); T = np.zeros(3); en = np.zeros(max(iterations, 1), np.float32)
+    n = lib().hostapi_solvedvo_casual(str(folder).encode(), ref_index, now_index, iterations, W, H, levels, C.c_float(K[0]), C.c_float(K[1]),
+                                      C.c_float(K[2]), C.c_float(K[3]), _p(R), _p(T), _p(en), len(en))
+    return n, R.reshape(3, 3), T, en
+
+
+def solvedvo_loop_from_file(folder, start, end, iterations, W, H, levels, K, capacity=64):
+    out = np.zeros((capacity, 12))
+    n = lib().hostapi_solvedvo_loop_from_file(str(folder).encode(), start, end, iterations, W, H, levels, C.c_float(K[0]), C.c_float(K[1]),
+                                              C.c_float(K[2]), C.c_float(K[3]), _p(out), capacity)
+    return n, out[:max(0, min(n, capacity))]
 
 
 # ---- RGBDOdometry host class ----

@@ -51,3 +51,11 @@ def test_product_does_not_import_oracle():
                 txt = open(os.path.join(dp, f), errors="replace").read()
                 m = bad.search(txt)
                 assert m is None, f"{os.path.join(dp, f)} uses the oracle: {m.group(0)!r}"
+
+
+def test_cv_eigen_overloads_compile_against_standin_headers():
+    """The cv::Mat / Eigen overloads of the host classes (reference signatures) compile and link; run-time parity is a GPU test."""
+    import ctypes as C
+    import host_lib as Hh
+    lib = C.CDLL(Hh.build_cv_shim())
+    assert hasattr(lib, "cvapi_eposeestimator") and hasattr(lib, "cvapi_solvedvo_run_iterations")

@@ -438,3 +438,57 @@ def test_undistort_front_end_bit_exact():
     # identity lens: an exact copy
     img = rng.integers(0, 256, (1, 48, 64), dtype=np.uint8)
     assert np.array_equal(dvo.undistort(img, (60.0, 60.0, 31.5, 23.5), (0, 0, 0, 0, 0)), img)
+
+
+def test_raw_frame_ingest_bit_exact():
+    """dvo_set_frames_raw (src/camTopic2PublisherPyD.cpp:65-80, :338-348): fused BGR2GRAY + metres -> u16 millimetres
+    (cvRound half-even, saturate, 0 -> 1) into the level-0 regions, against the oracle (itself pinned to cv2), then the whole
+    path on top of it equals the path fed with the converted images.  Odd size = scalar tail path."""
+    rng = np.random.default_rng(21)
+    for (W, H, L) in ((640, 480, 4), (101, 77, 2)):
+        K = (525.0 * W / 640, 525.0 * W / 640, (W - 1) / 2.0, (H - 1) / 2.0)
+        d = O.synth_batch(60, 2, W, H, K, bgr=True, now_depth=True)
+        dm_ref = d["ref_depth"].astype(np.float32) / np.float32(1000.0) + rng.uniform(-4e-4, 4e-4, d["ref_depth"].shape).astype(np.float32)
+        dm_now = d["now_depth"].astype(np.float32) / np.float32(1000.0)
+        # values the conversion must saturate / repair: zero, negative, > 65.535 m, half-way cases, NaN, +-inf
+        dm_ref[0, 0, :9] = [0.0, -1.0, 70.0, 0.0005, 0.0015, 0.0025, np.nan, np.inf, -np.inf]
+        al = dvo.BatchAligner(W, H, L, max_batch=3, keep_now_depth=True, intrinsics=K)
+        al.set_frames_raw(dvo.FRAME_REF, d["ref_bgr"], dm_ref, first=1)
+        al.set_frames_raw(dvo.FRAME_NOW, d["now_bgr"], dm_now, first=1)
+        al.build_pyramids(2, first=1)
+        want_ref = np.stack([O.depth_m_to_mm(dm_ref[i]) for i in range(2)])
+        assert list(want_ref[0, 0, :9]) == [1, 1, 65535, 1, 2, 2, 1, 1, 1], want_ref[0, 0, :9]
+        for i in range(2):
+            assert np.array_equal(al.get_level_buffer(i + 1, 0, 0, "gray"), O.bgr2gray(d["ref_bgr"][i]))
+            assert np.array_equal(al.get_level_buffer(i + 1, 1, 0, "gray"), O.bgr2gray(d["now_bgr"][i]))
+            assert np.array_equal(al.get_level_buffer(i + 1, 0, 0, "depth"), want_ref[i])
+            assert np.array_equal(al.get_level_buffer(i + 1, 1, 0, "depth"), O.depth_m_to_mm(dm_now[i]))
+            for l in range(1, L):                 # gray(level) == BGR2GRAY(NEAREST(bgr)) as the publisher computes it
+                assert np.array_equal(al.get_level_buffer(i + 1, 0, l, "gray"), O.bgr2gray(O.pyr_nearest(d["ref_bgr"][i], l)))
+        iters = tuple([6] * L)
+        prm = dvo.solver_params(solver=dvo.GN, iters=iters)
+        al.prepare(2, first=1); al.run(2, prm, first=1)
+        got, _ = al.get_poses(2, first=1)
+        al2 = dvo.BatchAligner(W, H, L, max_batch=3, intrinsics=K)
+        g_ref = np.stack([O.bgr2gray(x) for x in d["ref_bgr"]]); g_now = np.stack([O.bgr2gray(x) for x in d["now_bgr"]])
+        want, _ = al2.align_batch(g_ref, want_ref, g_now, prm)
+        assert np.array_equal(got, want)
+        with pytest.raises(dvo.DvoError):          # the reference frame needs depth; nothing may have been modified by the failed call
+            al.set_frames_raw(dvo.FRAME_REF, d["ref_bgr"], None, first=1)
+        assert np.array_equal(al.get_level_buffer(1, 0, 0, "depth"), want_ref[0])
+        al.close(); al2.close()
+
+
+def test_set_frames_error_leaves_state_untouched():
+    """A NOW upload without depth on a keep_now_depth context is rejected BEFORE the previous-frame rotation happens."""
+    W, H, K = 160, 120, (131.25, 131.25, 79.5, 59.5)
+    d = O.synth_batch(5, 1, W, H, K, now_depth=True)
+    al = dvo.BatchAligner(W, H, 2, max_batch=1, keep_now_depth=True, intrinsics=K)
+    al.set_frames(dvo.FRAME_REF, d["ref_gray"], d["ref_depth"])
+    al.set_frames(dvo.FRAME_NOW, d["now_gray"], d["now_depth"])
+    with pytest.raises(dvo.DvoError, match="needs the now frame's depth"):
+        al.set_frames(dvo.FRAME_NOW, d["ref_gray"], None)
+    with pytest.raises(dvo.DvoError, match="previous now frame"):          # the failed call must not have produced a "previous" frame
+        al.promote_now_to_ref(1)
+    assert np.array_equal(al.get_level_buffer(0, 1, 0, "gray"), d["now_gray"][0])
+    al.close()

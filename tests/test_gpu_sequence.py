@@ -123,3 +123,29 @@ def test_gated_keyframe_policy_on_device():
         switches.append(tuple(np.nonzero(okind == 2)[0]))
     assert any(len(sw) for sw in switches) and len(set(switches)) > 1, switches      # the sequences really diverged
     al.close()
+
+
+def test_sequences_from_device_memory_and_pinned_host_match():
+    """dvo_run_sequences_mem: the same sequences given as pageable host arrays, pinned host arrays (asynchronous, pipelined uploads)
+    and device-resident buffers give bit-identical records."""
+    import torch
+    W, H, L, K = 320, 240, 3, (262.5, 262.5, 159.5, 119.5)
+    nseq, nframes = 4, 8
+    seqs = [O.synth_sequence(90 + s, nframes, W, H, K, max_angle_deg=0.4, max_trans_m=0.008) for s in range(nseq)]
+    gray = np.stack([s[0] for s in seqs]); depth = np.stack([s[1] for s in seqs])
+    prm = dvo.solver_params(iters=(8, 8, 8))
+    al = dvo.BatchAligner(W, H, L, max_batch=nseq, keep_now_depth=True, intrinsics=K)
+    for pol in (dvo.keyframe_policy(keyframe_every=3), dvo.keyframe_policy(keyframe_every=0, use_quality_gates=True, laplacian_thresh=9.5, visible_ratio_thresh=0.95)):
+        want = al.run_sequences_mem(gray, depth, nseq, nframes, prm, pol)
+        pg, pd = torch.from_numpy(gray).pin_memory(), torch.from_numpy(depth.view(np.int16)).pin_memory()
+        got_pin = al.run_sequences_mem(pg.data_ptr(), pd.data_ptr(), nseq, nframes, prm, pol)
+        dg, dd = pg.cuda(), pd.cuda()
+        torch.cuda.synchronize()
+        got_dev = al.run_sequences_mem(dg.data_ptr(), dd.data_ptr(), nseq, nframes, prm, pol, device=True)
+        for a, b, c in zip(want, got_pin, got_dev):
+            assert np.array_equal(a, b) and np.array_equal(a, c)
+    rel, kind, glob = al.run_sequences(gray, depth, prm, keyframe_every=3)
+    w = al.run_sequences_mem(gray, depth, nseq, nframes, prm, dvo.keyframe_policy(keyframe_every=3))
+    assert np.array_equal(rel, w[0]) and np.array_equal(kind, w[1]) and np.array_equal(glob, w[3])
+    assert list(np.nonzero(kind[0] == 2)[0]) == [2, 4, 6]
+    al.close()
