@@ -112,6 +112,8 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     c->solve_shape = (cfg->max_batch <= c->sm_count) ? 512 : 256;
     if (const char* e = getenv("DVO_SOLVE_SHAPE")) { const int v = atoi(e); if (v == 256 || v == 512) c->solve_shape = v; }   // experiment knob
     c->texel_mode = 1;
+    c->edt_band = 0;
+    if (const char* e = getenv("DVO_EDT_BAND")) c->edt_band = atoi(e);                                                       // experiment knob
     if (const char* e = getenv("DVO_TEXEL_MODE")) c->texel_mode = atoi(e) ? 1 : 0;                                           // experiment knob (A/B)
     CREATE_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     c->stream = c->own_stream;
@@ -148,7 +150,7 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
         const int wd = (g.w[0] + 31) >> 5;
         size_t wa = (size_t)(wd + 2) * (g.h[0] + 2), wt = (size_t)(wd << 5) * (((g.h[0] + 31) >> 5) | 1);
         const size_t words = 2 * (wa > wt ? wa : wt);
-        if (words * 4 + 8192 > c->smem_optin) { c->bitmap_scratch_words = words; A(dalloc(&c->bitmap_scratch, words * B)); }
+        if (words * 4 + 8192 > c->smem_optin) { c->bitmap_scratch_words = words; A(dalloc(&c->bitmap_scratch, words * B * 2)); }
     }
     if (rc != DVO_OK) { dvo_destroy(c); return rc; }
     CREATE_CUDA(cudaMemsetAsync(c->npts, 0, sizeof(int) * B * g.L, c->stream));
@@ -294,8 +296,12 @@ int dvo_prepare(dvo_ctx* c, int first, int count, int frames_mask) {
     int rc;
     { StageTimer t(c, DVO_STAGE_CANNY); rc = launch_canny(c, first, count, frames_mask); if (rc) return rc; }
     if (frames_mask & 2) {
-        { StageTimer t(c, DVO_STAGE_EDT_ROWS); rc = launch_edt_rows(c, first, count); if (rc) return rc; }
-        { StageTimer t(c, DVO_STAGE_NORMGRAD); rc = c->texel_mode ? launch_pack(c, first, count) : launch_normgrad(c, first, count); if (rc) return rc; }
+        if (c->texel_mode && c->edt_band >= 0) {       // fused: the stage slot of the row pass times both
+            StageTimer t(c, DVO_STAGE_EDT_ROWS); rc = launch_edt_pack(c, first, count); if (rc) return rc;
+        } else {
+            { StageTimer t(c, DVO_STAGE_EDT_ROWS); rc = launch_edt_rows(c, first, count); if (rc) return rc; }
+            { StageTimer t(c, DVO_STAGE_NORMGRAD); rc = c->texel_mode ? launch_pack(c, first, count) : launch_normgrad(c, first, count); if (rc) return rc; }
+        }
     }
     return DVO_OK;
 }
@@ -330,8 +336,11 @@ static int process_range(dvo_ctx* c, int first, int count, const dvo_solver_para
     int rc;
     if ((rc = launch_pyramid(c, first, count, 3))) return rc;
     if ((rc = launch_canny(c, first, count, 3))) return rc;
-    if ((rc = launch_edt_rows(c, first, count))) return rc;
-    if ((rc = c->texel_mode ? launch_pack(c, first, count) : launch_normgrad(c, first, count))) return rc;
+    if (c->texel_mode && c->edt_band >= 0) { if ((rc = launch_edt_pack(c, first, count))) return rc; }
+    else {
+        if ((rc = launch_edt_rows(c, first, count))) return rc;
+        if ((rc = c->texel_mode ? launch_pack(c, first, count) : launch_normgrad(c, first, count))) return rc;
+    }
     if (pre_done) DVO_CUDA(cudaEventRecord(pre_done, c->stream));
     return launch_solve(c, first, count, p);
 }
@@ -669,6 +678,18 @@ int dvo_get_level_buffer(dvo_ctx* c, int slot, int frame, int level, int which, 
         case DVO_BUF_DTN: case DVO_BUF_GX: case DVO_BUF_GY:
             if (frame != DVO_FRAME_NOW) { dvo_set_error("DT exists for the now frame only"); return DVO_ERR_ARG; } src = c->texel ? c->texel + o : nullptr; es = 16; break;
         default: dvo_set_error("dvo_get_level_buffer: unknown buffer %d", which); return DVO_ERR_ARG;
+    }
+    if (which == DVO_BUF_D2 && c->texel_mode && c->edt_band >= 0) {      // fused EDT + texel kernel: the 32-bit image is sparse, rebuild the dense one
+        if (bytes < P * 4) { dvo_set_error("dvo_get_level_buffer: destination too small"); return DVO_ERR_ARG; }
+        int32_t* d_tmp = nullptr;
+        DVO_CUDA(cudaMalloc((void**)&d_tmp, P * 4));
+        const int rc = launch_d2_from_texels(c, slot, level, d_tmp);
+        cudaError_t ce = rc ? cudaSuccess : cudaMemcpyAsync(dst, d_tmp, P * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+        cudaFree(d_tmp);
+        if (rc) return rc;
+        DVO_CUDA(ce);
+        return DVO_OK;
     }
     if (which >= DVO_BUF_DTN) {
         if (bytes < P * 4) { dvo_set_error("dvo_get_level_buffer: destination too small"); return DVO_ERR_ARG; }

@@ -77,6 +77,7 @@ struct dvo_ctx {
     int32_t* d2;             // now: exact squared distance
     float4* texel;           // now: {DTn, gx, gy, getWeightOf(DTn)} -- legacy 16-byte texels (texel_mode 0 only)
     uint2* tex8;             // now: packed 8-byte texels (texel_mode 1, the default)
+    int edt_band;            // experiment knob: band height of the fused EDT + texel kernel (0 = automatic); -1 = unfused kernels
     int texel_mode;          // 1: packed texels + in-kernel lookup tables; 0: legacy float4 texels written by normgrad_kernel
     float *ptsX, *ptsY, *ptsZ;   // ref: back-projected edge points (row-major pixel order), capacity P[l] per slot and level
     int* ptsPix;                 // ref: pixel index y*w+x of every point (restores the reference's column-major order)
@@ -93,7 +94,8 @@ struct dvo_ctx {
     double* trace;           // [Bmax][L][trace_iters][56] or null
     float* energy;           // [Bmax][L][DVO_ENERGY_ITERS] ||eps|| of every executed iteration of the last solve
     uint32_t* bitmap_scratch;    // hysteresis bitmaps for images too large for shared memory, or null
-    size_t bitmap_scratch_words; // per CTA
+    size_t bitmap_scratch_words; // per slot and frame (the scratch holds 2 x Bmax of them: reference and now CTAs run in one launch)
+    size_t canny_smem_optin;     // largest dynamic shared-memory opt-in made for canny_kernel so far
 
     // device staging of dvo_set_frames_raw with host buffers (allocated on first use)
     uint8_t* raw_bgr; float* raw_depth; size_t raw_capacity;   // in images
@@ -125,6 +127,8 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask);
 int launch_edt_rows(dvo_ctx* c, int first, int count);
 int launch_normgrad(dvo_ctx* c, int first, int count);
 int launch_pack(dvo_ctx* c, int first, int count);
+int launch_edt_pack(dvo_ctx* c, int first, int count);
+int launch_d2_from_texels(dvo_ctx* c, int slot, int level, int32_t* d_out);      // EDT rows + packed texels fused (texel_mode 1)
 // inspection: {DTn, gx, gy, w} of one slot / level into a caller-provided device buffer of P[level] float4
 int launch_normgrad_into(dvo_ctx* c, int slot, int level, float4* d_out);
 // same images, resolved from the packed texels through the solver's own lookup path (texel_mode 1)

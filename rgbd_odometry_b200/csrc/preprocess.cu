@@ -105,16 +105,18 @@ int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
 //           selectedPts/enlistRefEdgePts (src/SolveDVO.cpp:1230-1264, 224-264), emitted row-major (see phase 4).
 // =====================================================================================================
 struct CannyArgs {
-    const uint8_t* gray;   // level region of this frame (slot 0)
-    uint8_t* edge;
+    const uint8_t* gray[2];   // level region of the reference / now frame (slot 0)
+    uint8_t* edge[2];
     const uint16_t* depth; // ref
     uint16_t* gcol;        // now
     float *X, *Y, *Z;      // ref, level region
     int* pix;              // ref, level region: pixel index y*w+x of every emitted point
     int* npts;             // + level, stride L
-    unsigned* nedge;       // + level, stride L (this frame)
+    unsigned* nedge[2];    // + level, stride L (per frame)
     int w, h, P, L;
-    int do_points, do_cols;
+    int frame0;            // frame of blocks [0, count): 0 = reference, 1 = now
+    int count;             // blocks [count, 2 count) process the now frame of the same slots (one launch for both frames)
+    long long gscratch_frame_stride;   // global bitmaps: offset of the now frame's scratch
     float tmpfx, tmpfy, tmpcx, tmpcy;
     uint32_t* gscratch;    // null -> shared memory bitmaps
     long long gscratch_stride;
@@ -152,6 +154,13 @@ __device__ __forceinline__ void row_sums(const uint8_t* __restrict__ grow, int w
 
 constexpr int CANNY_MAX_WARPS = 24;
 
+// The hysteresis sweep is a chaotic relaxation on purpose: within a round a thread reads neighbouring words their owners may be
+// updating (bits only ever get set, every word has one writer, the loop ends after a round without changes).  In shared memory
+// those reads go through a volatile pointer, so the compiler neither caches nor merges them and the behaviour is defined; the
+// global-scratch variant keeps plain (L1-cached) accesses, ordered by the block barrier between rounds.
+template <bool GLOBAL_BITMAPS> struct HystPtr { typedef volatile uint32_t* type; };
+template <> struct HystPtr<true> { typedef uint32_t* type; };
+
 template <bool GLOBAL_BITMAPS>
 __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     extern __shared__ uint32_t smem_u32[];
@@ -161,16 +170,21 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     __shared__ unsigned char s_chg[2][768];
     const int T = blockDim.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = a.first + blockIdx.x;
+    // one launch covers the reference AND the now frame of every slot: 2 x count CTAs leave a much fuller last wave than two
+    // launches of count CTAs each (1024 CTAs at 296 resident = 3.46 waves)
+    const int second = (blockIdx.x >= (unsigned)a.count) ? 1 : 0;
+    const int frame = second ? DVO_FRAME_NOW : a.frame0;
+    const int b = a.first + (int)blockIdx.x - second * a.count;
+    const bool do_points = (frame == DVO_FRAME_REF), do_cols = (frame == DVO_FRAME_NOW);
     if (a.active && !a.active[b]) return;
     const int w = a.w, h = a.h;
     const int wd = (w + 31) >> 5, pitch = wd + 2;
     const int nwords = a.bm_words;
     // bitmaps: shared memory (LDS/STS/ATOMS) or, for images too large for it, a global scratch
     // (the global scratch is indexed by SLOT, not by block: launches on different streams own disjoint slot ranges)
-    uint32_t* C = GLOBAL_BITMAPS ? a.gscratch + (long long)b * a.gscratch_stride : smem_u32;
+    uint32_t* C = GLOBAL_BITMAPS ? a.gscratch + (long long)b * a.gscratch_stride + (long long)frame * a.gscratch_frame_stride : smem_u32;
     uint32_t* E = C + nwords;
-    const uint8_t* __restrict__ g = a.gray + (long long)b * a.P;
+    const uint8_t* __restrict__ g = a.gray[frame] + (long long)b * a.P;
 
     for (int i = tid; i < 2 * nwords; i += T) C[i] = 0u;
     if (tid == 0) { s_cnt = 0u; s_base = 0; }
@@ -296,25 +310,48 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
                     }
             }
             if (active) {
-                auto visit = [&](int y) {
-                    const int idx = (y + 1) * pitch + wx + 1;
-                    const uint32_t c = C[idx];
-                    if (c == 0u) return;
-                    const uint32_t e = E[idx];
-                    if (e == c) return;
-                    uint32_t n = 0u;
-#pragma unroll
-                    for (int dy = -1; dy <= 1; ++dy) {
-                        const int j = idx + dy * pitch;
-                        const uint32_t ec = E[j], el = E[j - 1], er = E[j + 1];
-                        n |= ec | (ec << 1) | (ec >> 1) | (el >> 31) | (er << 31);
-                    }
-                    uint32_t f = e | (c & n);
-                    for (;;) { const uint32_t f2 = f | (c & ((f << 1) | (f >> 1))); if (f2 == f) break; f = f2; }
-                    if (f != e) { E[idx] = f; changed = 1; }
+                // Sweep the strip down, then up, with the 3x3 word neighbourhood in a sliding register window: one step loads
+                // the three words of the incoming row and the candidate word (4 LDS; 11 before).  Words of the neighbouring
+                // columns are as old as the step that loaded them -- harmless for a monotone relaxation.  Inside a word the
+                // seeds are extended to whole runs of candidates with two carry chains instead of a shift-and-or loop.
+                auto spread = [](uint32_t l, uint32_t c, uint32_t r) { return c | (c << 1) | (c >> 1) | (l >> 31) | (r << 31); };
+                auto flood = [](uint32_t f, uint32_t c) {          // f subset of c: every seed grows to its run of ones of c
+                    const uint32_t up = ((c + f) ^ c) & c;
+                    const uint32_t cr = __brev(c), fr = __brev(f);
+                    return f | up | __brev(((cr + fr) ^ cr) & cr);
                 };
-                for (int y = ya; y < yb; ++y) visit(y);
-                for (int y = yb - 2; y >= ya; --y) visit(y);
+                typename HystPtr<GLOBAL_BITMAPS>::type Ev = E;
+                const uint32_t* Cv = C;                            // candidates are read-only in this phase
+                {   // down
+                    int idx = (ya + 1) * pitch + wx + 1;
+                    uint32_t sp = spread(Ev[idx - pitch - 1], Ev[idx - pitch], Ev[idx - pitch + 1]);
+                    uint32_t el = Ev[idx - 1], ec = Ev[idx], er = Ev[idx + 1];
+                    for (int y = ya; y < yb; ++y, idx += pitch) {
+                        const uint32_t nl = Ev[idx + pitch - 1], nc = Ev[idx + pitch], nr = Ev[idx + pitch + 1];
+                        const uint32_t c = Cv[idx];
+                        uint32_t f = ec;
+                        if (c != 0u && ec != c) {
+                            f = flood(ec | (c & (sp | spread(el, ec, er) | spread(nl, nc, nr))), c);
+                            if (f != ec) { Ev[idx] = f; changed = 1; }
+                        }
+                        sp = spread(el, f, er); el = nl; ec = nc; er = nr;
+                    }
+                }
+                {   // up
+                    int idx = yb * pitch + wx + 1;                 // row yb - 1
+                    uint32_t sp = spread(Ev[idx + pitch - 1], Ev[idx + pitch], Ev[idx + pitch + 1]);
+                    uint32_t el = Ev[idx - 1], ec = Ev[idx], er = Ev[idx + 1];
+                    for (int y = yb - 1; y >= ya; --y, idx -= pitch) {
+                        const uint32_t nl = Ev[idx - pitch - 1], nc = Ev[idx - pitch], nr = Ev[idx - pitch + 1];
+                        const uint32_t c = Cv[idx];
+                        uint32_t f = ec;
+                        if (c != 0u && ec != c) {
+                            f = flood(ec | (c & (sp | spread(el, ec, er) | spread(nl, nc, nr))), c);
+                            if (f != ec) { Ev[idx] = f; changed = 1; }
+                        }
+                        sp = spread(el, f, er); el = nl; ec = nc; er = nr;
+                    }
+                }
             }
             if (owner) s_chg[cur ^ 1][tid] = (unsigned char)changed;
             cur ^= 1;
@@ -325,7 +362,7 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     // ------------------------------------------------------------------ phase 3: edge bytes (0/255) + edge count
     const int nw = h * wd;
     {
-        uint8_t* eo = a.edge + (long long)b * a.P;
+        uint8_t* eo = a.edge[frame] + (long long)b * a.P;
         unsigned cnt = 0;
         const bool vec_ok = (w % 16 == 0) && ((reinterpret_cast<uintptr_t>(eo) & 15) == 0);
         for (int q = tid; q < nw; q += T) {
@@ -348,7 +385,7 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     }
 
     // ------------------------------------------------------------------ phase 4 (ref): selected = edge && depth > 100, in place
-    if (a.do_points) {
+    if (do_points) {
         const uint16_t* __restrict__ dep = a.depth + (long long)b * a.P;
         for (int q = tid; q < nw; q += T) {
             const int y = q / wd, wx = q - y * wd;
@@ -362,12 +399,12 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
         }
     }
     __syncthreads();
-    if (tid == 0) a.nedge[(long long)b * a.L] = s_cnt;
+    if (tid == 0) a.nedge[frame][(long long)b * a.L] = s_cnt;
 
     // ------------------------------------------------------------------ transpose E -> Et (into C's storage): Et[x * hwp + (y >> 5)], bit y & 31
     const int hw = (h + 31) >> 5, hwp = hw | 1;
     uint32_t* Et = C;
-    if (a.do_cols) {
+    if (do_cols) {
         const int nwarps = T >> 5;
         for (int blk = warp; blk < hw * wd; blk += nwarps) {
             const int wy = blk / wd, wx = blk - wy * wd;
@@ -384,7 +421,7 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     // ------------------------------------------------------------------ phase 4 (now): EDT phase 1 from the column bit strings
     // thread <-> column; per 32-row word the nearest edge above / below comes from clz / ffs on the masked word, with
     // carries (last edge row above the word, first edge row below it) tracked incrementally.
-    if (a.do_cols) {
+    if (do_cols) {
         uint16_t* gc = a.gcol + (long long)b * a.P;
         const int BIG = 1 << 20;
         for (int x = tid; x < w; x += T) {
@@ -420,7 +457,7 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     // horizontal contour then share 8 DRAM atoms inside one warp instruction.  Every sum over points is order
     // independent up to fp64 rounding; the pixel index of each point is kept so that the reference's order can be
     // restored wherever a per-point list is exposed (dvo_get_points, dvo_eval_normal_equations).
-    if (a.do_points) {
+    if (do_points) {
         const uint16_t* __restrict__ dep = a.depth + (long long)b * a.P;
         float* X = a.X + (long long)b * a.P; float* Y = a.Y + (long long)b * a.P; float* Z = a.Z + (long long)b * a.P;
         int* pix = a.pix + (long long)b * a.P;
@@ -469,6 +506,8 @@ static int canny_bitmap_words(int w, int h) {
 
 int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
     const PyrGeom& g = c->geom;
+    if (!(frames_mask & 3)) return DVO_OK;
+    if ((frames_mask & 1) && !c->depth[0]) { dvo_set_error("canny: reference depth missing"); return DVO_ERR_STATE; }
     for (int l = 0; l < g.L; ++l) {
         const int words = canny_bitmap_words(g.w[l], g.h[l]);
         const size_t smem = (size_t)2 * words * sizeof(uint32_t);
@@ -481,32 +520,37 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
         int S = 24 / nchunk; if (S < 1) S = 1;
         int warps = nchunk * S; if (warps > CANNY_MAX_WARPS) warps = CANNY_MAX_WARPS; if (warps < 4) warps = 4;
         const int T = warps * 32;
+        CannyArgs a;
         for (int f = 0; f < 2; ++f) {
-            if (!(frames_mask & (1 << f))) continue;
-            CannyArgs a;
-            a.gray = c->gray[f] + g.off[l]; a.edge = c->edge[f] + g.off[l];
-            a.depth = c->depth[f] ? c->depth[f] + g.off[l] : nullptr;
-            a.gcol = c->gcol + g.off[l];
-            a.X = c->ptsX + g.off[l]; a.Y = c->ptsY + g.off[l]; a.Z = c->ptsZ + g.off[l]; a.pix = c->ptsPix + g.off[l];
-            a.npts = c->npts + l; a.nedge = c->nedge + (size_t)f * g.Bmax * g.L + l;
-            a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L;
-            a.do_points = (f == DVO_FRAME_REF); a.do_cols = (f == DVO_FRAME_NOW);
-            if (a.do_points && !a.depth) { dvo_set_error("canny: reference depth missing"); return DVO_ERR_STATE; }
-            const float scaleFac = (float)ldexp(1.0, -l);                                  // src/SolveDVO.cpp:231
-            a.tmpfx = (float)(1. / (double)(scaleFac * c->K.fx));                          // :232
-            a.tmpfy = (float)(1. / (double)(scaleFac * c->K.fy));                          // :233
-            a.tmpcx = scaleFac * c->K.cx; a.tmpcy = scaleFac * c->K.cy;                    // :234-235
-            a.gscratch = use_global ? c->bitmap_scratch : nullptr;
-            a.gscratch_stride = (long long)c->bitmap_scratch_words;
-            a.first = first; a.low = 10000; a.high = 22500; a.bm_words = words; a.active = c->active;
-            const size_t dyn = use_global ? 0 : smem;
-            if (use_global) canny_kernel<true><<<count, T, 0, c->stream>>>(a);
-            else {
-                if (dyn > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(canny_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-                canny_kernel<false><<<count, T, dyn, c->stream>>>(a);
-            }
-            c->launches++;
+            a.gray[f] = c->gray[f] + g.off[l]; a.edge[f] = c->edge[f] + g.off[l];
+            a.nedge[f] = c->nedge + (size_t)f * g.Bmax * g.L + l;
         }
+        a.depth = c->depth[0] ? c->depth[0] + g.off[l] : nullptr;
+        a.gcol = c->gcol + g.off[l];
+        a.X = c->ptsX + g.off[l]; a.Y = c->ptsY + g.off[l]; a.Z = c->ptsZ + g.off[l]; a.pix = c->ptsPix + g.off[l];
+        a.npts = c->npts + l;
+        a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L;
+        const bool both = (frames_mask & 3) == 3;
+        a.frame0 = (frames_mask & 1) ? DVO_FRAME_REF : DVO_FRAME_NOW;
+        a.count = both ? count : 0x7fffffff;                                           // single frame: no block is "second"
+        const float scaleFac = (float)ldexp(1.0, -l);                                  // src/SolveDVO.cpp:231
+        a.tmpfx = (float)(1. / (double)(scaleFac * c->K.fx));                          // :232
+        a.tmpfy = (float)(1. / (double)(scaleFac * c->K.fy));                          // :233
+        a.tmpcx = scaleFac * c->K.cx; a.tmpcy = scaleFac * c->K.cy;                    // :234-235
+        a.gscratch = use_global ? c->bitmap_scratch : nullptr;
+        a.gscratch_stride = (long long)c->bitmap_scratch_words;
+        a.gscratch_frame_stride = (long long)c->bitmap_scratch_words * g.Bmax;
+        a.first = first; a.low = 10000; a.high = 22500; a.bm_words = words; a.active = c->active;
+        const int nblocks = both ? 2 * count : count;
+        if (use_global) canny_kernel<true><<<nblocks, T, 0, c->stream>>>(a);
+        else {
+            if (smem > 48 * 1024 && smem > c->canny_smem_optin) {                      // opt in once per size (not per launch)
+                DVO_CUDA(cudaFuncSetAttribute(canny_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                c->canny_smem_optin = smem;
+            }
+            canny_kernel<false><<<nblocks, T, smem, c->stream>>>(a);
+        }
+        c->launches++;
     }
     DVO_CUDA(cudaGetLastError());
     return DVO_OK;
@@ -830,6 +874,261 @@ int launch_pack(dvo_ctx* c, int first, int count) {
             c->launches++;
         }
     }
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}
+
+// =====================================================================================================
+// EDT rows + packed texels in one pass (texel_mode 1, the hot path).  edt_rows_*_kernel followed by pack_texel_kernel
+// writes the 32-bit d2 image (4 B/px) only to read it straight back (4 B/px + halo); here a CTA owns a band of R image
+// rows: its warps evaluate the R + 2 rows y0-1 .. y0+R with the same exact row routines (expanding window, or the
+// bisection for sparse images) into a 16-bit band buffer in shared memory, and the band's texels are assembled from
+// there and stored as whole 128-byte Morton tiles.  The two halo rows are evaluated twice ((R+2)/R of the row work).
+// The band holds min(d2, 65535); a texel whose stencil touches a saturated value is escaped (DVO_TEX_ESCAPE), and every
+// pixel with d2 >= DVO_D2_SPILL additionally writes its exact value to the 32-bit d2 image.  Neighbours of an escaped
+// texel are at most one pixel further from the edge set than a pixel with d >= 254.99, i.e. d2 >= 64 516 >
+// DVO_D2_SPILL, so every value the solver's escape path reads (stencil_from_d2) has been written.  The 32-bit image is
+// therefore SPARSE in this mode: inspection (dvo_get_level_buffer) takes d2 from the texel where it is not escaped.
+// =====================================================================================================
+#define DVO_D2_SPILL 64000
+
+struct EdtPackArgs { const uint16_t* gcol; int32_t* d2; uint2* tex8; unsigned* maxd2; int w, h, P, Pt, tw, th, L, first; };
+
+// expanding-window row routine of edt_rows_window_kernel for one warp; g2 = this warp's (w + 2)-int scratch + 1
+template <typename Emit>
+__device__ __forceinline__ void edt_row_window(const uint16_t* __restrict__ gr, int* g2, int w, int lane, Emit emit) {
+    for (int x = lane; x < w; x += 32) { const int gv = gr[x]; g2[x] = gv * gv; }
+    if (lane == 0) { g2[-1] = 0x3fffffff; g2[w] = 0x3fffffff; }
+    __syncwarp();
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        const int x = x0 + lane;
+        int best = (x < w) ? g2[x] : 0;
+        const int kint = min(x0, w - 32 - x0);
+        const int* gc = g2 + min(x, w - 1);
+        int k = 1, kk = 1;
+        while (k < w) {
+            if (__all_sync(0xffffffffu, kk >= best)) break;
+            if (k + 3 <= kint) {
+                const int a0 = min(gc[-k], gc[k]), a1 = min(gc[-k - 1], gc[k + 1]), a2 = min(gc[-k - 2], gc[k + 2]), a3 = min(gc[-k - 3], gc[k + 3]);
+                const int k1 = kk + 2 * k + 1, k2 = kk + 4 * k + 4, k3 = kk + 6 * k + 9;
+                best = min(min(best, a0 + kk), min(a1 + k1, min(a2 + k2, a3 + k3)));
+                kk += 8 * k + 16; k += 4;
+            } else {
+                const int vl = g2[min(max(x - k, -1), w)], vr = g2[min(x + k, w)];
+                best = min(best, min(vl, vr) + kk);
+                kk += 2 * k + 1; ++k;
+            }
+        }
+        if (x < w) emit(x, best);
+    }
+    __syncwarp();
+}
+
+// bisection row routine of edt_rows_kernel for one warp; dv / gs / arg = this warp's scratch
+template <typename Emit>
+__device__ __forceinline__ void edt_row_bisect(const uint16_t* __restrict__ gr, int* dv, unsigned short* gs, unsigned short* arg, int w, int lane, Emit emit) {
+    for (int x = lane; x < w; x += 32) gs[x] = gr[x];
+    __syncwarp();
+    constexpr int SOLO_MAX = 6;
+    int n = 1; while (n < w + 1) n <<= 1;
+    for (int step = n >> 1; step >= 1; step >>= 1) {
+        const int cnt = ((w / step) + 1) >> 1;
+        for (int j0 = 0; j0 < cnt; j0 += 32) {
+            const int j = j0 + lane;
+            const bool has = j < cnt;
+            int m = 0, lo = 0, hi = -1;
+            if (has) {
+                const int p = step * (2 * j + 1);
+                m = p - 1;
+                const int gm = gs[m];
+                lo = (p - step >= 1) ? (int)arg[p - step - 1] : 0;
+                hi = (p + step <= w) ? (int)arg[p + step - 1] : w - 1;
+                lo = max(lo, m - gm); hi = min(hi, m + gm);
+            }
+            const bool solo = has && (hi - lo < SOLO_MAX);
+            if (solo) {
+                int best = 0x7fffffff, bx = lo;
+                for (int xq = lo; xq <= hi; ++xq) {
+                    const int dxx = m - xq, gq = gs[xq]; const int v = gq * gq + dxx * dxx;
+                    if (v < best) { best = v; bx = xq; }
+                }
+                dv[m] = best; arg[m] = (unsigned short)bx;
+            }
+            unsigned longmask = __ballot_sync(0xffffffffu, has && !solo);
+            while (longmask) {
+                const int src = __ffs(longmask) - 1; longmask &= longmask - 1;
+                const int Lo = __shfl_sync(0xffffffffu, lo, src), Hi = __shfl_sync(0xffffffffu, hi, src), M = __shfl_sync(0xffffffffu, m, src);
+                int best = 0x7fffffff, bx = 0x7fffffff;
+                for (int xq = Lo + lane; xq <= Hi; xq += 32) {
+                    const int dxx = M - xq, gq = gs[xq]; const int v = gq * gq + dxx * dxx;
+                    if (v < best) { best = v; bx = xq; }
+                }
+                const int vmin = __reduce_min_sync(0xffffffffu, best);
+                const int xmin = __reduce_min_sync(0xffffffffu, best == vmin ? bx : 0x7fffffff);
+                if (lane == 0) { dv[M] = vmin; arg[M] = (unsigned short)xmin; }
+            }
+        }
+        __syncwarp();
+    }
+    for (int x = lane; x < w; x += 32) emit(x, dv[x]);
+    __syncwarp();
+}
+
+template <int WARPS, int R, bool SPARSE>
+__global__ void __launch_bounds__(WARPS * 32) edt_pack_kernel(EdtPackArgs a, const unsigned* __restrict__ nedge) {
+    extern __shared__ int smem_i32[];
+    static_assert(R % 4 == 0, "a band is a whole number of tile rows");
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = a.w, h = a.h;
+    const int b = a.first + blockIdx.y;
+    const unsigned ne = nedge[(long long)b * a.L];
+    const bool sparse = (ne != 0u) && ((unsigned long long)ne * DVO_EDT_SPARSE_DIV < (unsigned long long)a.P);
+    if (sparse != SPARSE) return;
+    const int y0 = blockIdx.x * R;
+    const int bp = (w + 1) & ~1;                                     // band pitch (u16), even
+    unsigned short* band = reinterpret_cast<unsigned short*>(smem_i32);
+    const int per_warp = SPARSE ? (w + bp) : (w + 2);
+    int* scratch = smem_i32 + ((R + 2) * bp) / 2 + warp * per_warp;
+    int32_t* __restrict__ d2g = a.d2 + (long long)b * a.P;
+    int mx = 0;
+    for (int r = warp; r < R + 2; r += WARPS) {
+        const int y = y0 - 1 + r;
+        if (y < 0 || y >= h) continue;                               // warp-uniform
+        unsigned short* brow = band + r * bp;
+        int32_t* grow = d2g + (long long)y * w;
+        auto emit = [&](int x, int v) {
+            brow[x] = (unsigned short)min(v, 65535);
+            if (v >= DVO_D2_SPILL) grow[x] = v;
+            mx = max(mx, v);
+        };
+        if (ne == 0u) {                                              // no edge pixel at all: d2 is the sentinel everywhere
+            for (int x = lane; x < w; x += 32) emit(x, DVO_EDT_INF);
+            continue;
+        }
+        const uint16_t* __restrict__ gr = a.gcol + (long long)b * a.P + (long long)y * w;
+        if (SPARSE) {
+            unsigned short* gs = reinterpret_cast<unsigned short*>(scratch + w);
+            edt_row_bisect(gr, scratch, gs, gs + bp, w, lane, emit);
+        } else {
+            edt_row_window(gr, scratch + 1, w, lane, emit);
+        }
+    }
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if (lane == 0 && mx > 0) atomicMax(&a.maxd2[(long long)b * a.L], (unsigned)mx);
+    __syncthreads();
+    // ---- texels of the band: rows y0 .. y0 + R - 1, tile row by tile row (16 * tw contiguous texels each).  A thread assembles
+    // one Morton quad = a 2x2 pixel block = 32 contiguous bytes: its 4x4 band neighbourhood takes eight shared-memory loads
+    // (the two middle rows: left, aligned pair, right; the outer rows: the pair), the four texels go out as two 16-byte stores.
+    uint2* __restrict__ out = a.tex8 + (long long)b * a.Pt;
+    const int row_quads = a.tw << 2;
+#pragma unroll 1
+    for (int tyl = 0; tyl < R / 4; ++tyl) {
+        const int ty = (y0 >> 2) + tyl;
+        if (ty >= a.th) break;
+        for (int q = threadIdx.x; q < row_quads; q += WARPS * 32) {
+            const int tx = q >> 2, sub = q & 3;
+            const int x = (tx << 2) | ((sub & 1) << 1), ly = (tyl << 2) | (sub & 2), y = y0 + ly;        // top-left pixel of the quad (x even)
+            uint2 t[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) t[k] = make_uint2(DVO_TEX_ESCAPE, 0u);
+            if (x < w && y < h) {
+                const unsigned short* br = band + (ly + 1) * bp + x;                                    // band row of image row y
+                // v[r][c]: rows y-1 .. y+2, columns x-1 .. x+2 (corners unused); out-of-image taps are never selected below
+                int v[4][4];
+                const bool has_r = (x + 1 < w), has_b = (y + 1 < h);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const unsigned short* p = br + (r - 1) * bp;
+                    const unsigned pr = *reinterpret_cast<const unsigned*>(p);                          // x is even and bp is even: 4-byte aligned
+                    v[r][1] = (int)(pr & 0xFFFFu); v[r][2] = (int)(pr >> 16);
+                    if (r == 1 || r == 2) { v[r][0] = (x > 0) ? (int)p[-1] : 0; v[r][3] = (x + 2 < w) ? (int)p[2] : 0; }
+                    else { v[r][0] = 0; v[r][3] = 0; }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int dy = k >> 1, dx = k & 1;
+                    const int px = x + dx, py = y + dy;
+                    if ((dx && !has_r) || (dy && !has_b)) continue;
+                    const int c = v[1 + dy][1 + dx];
+                    const bool bx = (px == 0 || px == w - 1), by = (py == 0 || py == h - 1);
+                    const int l = bx ? c : v[1 + dy][dx], r = bx ? c : v[1 + dy][2 + dx], u = by ? c : v[dy][1 + dx], d = by ? c : v[2 + dy][1 + dx];
+                    const int dl = l - c, dr = r - c, du = u - c, dd = d - c;
+                    const int lo = min(min(dl, dr), min(du, dd)), hi = max(max(dl, dr), max(du, dd));
+                    if (max(max(max(c, l), max(r, u)), d) < 65535 && lo >= -512 && hi <= 511) {
+                        t[k].x = (unsigned)c | (((unsigned)dl & 0x3FFu) << 16);
+                        t[k].y = ((unsigned)dr & 0x3FFu) | (((unsigned)du & 0x3FFu) << 10) | (((unsigned)dd & 0x3FFu) << 20);
+                    }
+                }
+            }
+            uint4* o = reinterpret_cast<uint4*>(out + (long long)ty * (row_quads << 2) + ((long long)q << 2));
+            o[0] = make_uint4(t[0].x, t[0].y, t[1].x, t[1].y);
+            o[1] = make_uint4(t[2].x, t[2].y, t[3].x, t[3].y);
+        }
+    }
+}
+
+// shared memory the fused kernel needs for a level of width w (the sparse variant is the larger one)
+static size_t edt_pack_smem(int warps, int R, int w, bool sparse) {
+    const int bp = (w + 1) & ~1;
+    return (size_t)(R + 2) * bp * sizeof(unsigned short) + (size_t)warps * (sparse ? (w + bp) : (w + 2)) * sizeof(int);
+}
+
+template <int WARPS, int R>
+static int launch_edt_pack_t(dvo_ctx* c, int first, int count) {
+    const PyrGeom& g = c->geom;
+    if (edt_pack_smem(WARPS, R, g.w[0], true) > c->smem_optin) {          // image too wide for a band in shared memory: unfused kernels
+        const int rc = launch_edt_rows(c, first, count);
+        return rc ? rc : launch_pack(c, first, count);
+    }
+    DVO_CUDA(cudaMemsetAsync(c->maxd2 + (size_t)first * g.L, 0, sizeof(unsigned) * (size_t)count * g.L, c->stream));
+    for (int l = 0; l < g.L; ++l) {
+        EdtPackArgs a; a.gcol = c->gcol + g.off[l]; a.d2 = c->d2 + g.off[l]; a.tex8 = c->tex8 + g.offt[l]; a.maxd2 = c->maxd2 + l;
+        a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.Pt = g.Pt[l]; a.tw = g.tw[l]; a.th = (g.h[l] + 3) >> 2; a.L = g.L; a.first = first;
+        const unsigned* ne = c->nedge + (size_t)DVO_FRAME_NOW * g.Bmax * g.L + l;
+        const int w = g.w[l], bp = (w + 1) & ~1;
+        dim3 grid((g.h[l] + R - 1) / R, count);
+        const size_t band = (size_t)(R + 2) * bp * sizeof(unsigned short);
+        const size_t smem_d = band + (size_t)WARPS * (w + 2) * sizeof(int), smem_s = band + (size_t)WARPS * (w + bp) * sizeof(int);
+        static size_t opted_d = 0, opted_s = 0;          // largest opt-in so far (per instantiation; one device per process)
+        if (smem_d > 48 * 1024 && smem_d > opted_d) { DVO_CUDA(cudaFuncSetAttribute(edt_pack_kernel<WARPS, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d)); opted_d = smem_d; }
+        if (smem_s > 48 * 1024 && smem_s > opted_s) { DVO_CUDA(cudaFuncSetAttribute(edt_pack_kernel<WARPS, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); opted_s = smem_s; }
+        edt_pack_kernel<WARPS, R, false><<<grid, WARPS * 32, smem_d, c->stream>>>(a, ne);
+        edt_pack_kernel<WARPS, R, true><<<grid, WARPS * 32, smem_s, c->stream>>>(a, ne);
+        c->launches += 2;
+    }
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}
+
+int launch_edt_pack(dvo_ctx* c, int first, int count) {
+    // band height: 24 rows (+2 halo, 13 warps x 2 rows: 3.83 ms per 1024 pairs at 640x480 against 3.85 / 3.92 / 4.00 for 20 / 28 / 12
+    // rows and 4.41 for the unfused kernels).  At 1280x720 a band costs twice the shared memory and the fused kernel is no faster
+    // than the unfused pair (2.46 ms per 148 pairs either way at best, 2.7 - 3.5 for the other band shapes): wide images stay unfused.
+    const int shape = c->edt_band ? c->edt_band : (c->geom.w[0] > 800 ? -1 : 24);
+    if (shape < 0) { const int rc = launch_edt_rows(c, first, count); return rc ? rc : launch_pack(c, first, count); }
+    if (shape == 12) return launch_edt_pack_t<7, 12>(c, first, count);
+    if (shape == 20) return launch_edt_pack_t<11, 20>(c, first, count);
+    if (shape == 24) return launch_edt_pack_t<13, 24>(c, first, count);
+    if (shape == 200) return launch_edt_pack_t<22, 20>(c, first, count);
+    if (shape == 160) return launch_edt_pack_t<9, 16>(c, first, count);
+    return launch_edt_pack_t<10, 28>(c, first, count);
+}
+
+// inspection (dvo_get_level_buffer D2 with the fused kernel): the dense d2 image of one slot / level from the packed texels
+// (centre value) and, where a texel is escaped, from the sparse 32-bit image
+__global__ void __launch_bounds__(256) d2_from_texels_kernel(const uint2* __restrict__ tex8, const int32_t* __restrict__ d2g, int32_t* __restrict__ out, int w, int h, int tw) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= w * h) return;
+    const int y = i / w, x = i - y * w;
+    const unsigned w0 = tex8[tex_index(x, y, tw)].x;
+    out[i] = ((int)w0 < 0) ? d2g[i] : (int)(w0 & 0xFFFFu);
+}
+
+int launch_d2_from_texels(dvo_ctx* c, int slot, int level, int32_t* d_out) {
+    const PyrGeom& g = c->geom;
+    d2_from_texels_kernel<<<(g.P[level] + 255) / 256, 256, 0, c->stream>>>(c->tex8 + tex_at(g, level, slot), c->d2 + lvl_at(g, level, slot), d_out,
+                                                                         g.w[level], g.h[level], g.tw[level]);
+    c->launches++;
     DVO_CUDA(cudaGetLastError());
     return DVO_OK;
 }
