@@ -329,7 +329,10 @@ def bench_config2(env, args):
         al.build_pyramids(B); al.prepare(B); al.run(B, params)
     stage = {k: v / nstage for k, v in al.stage_ms().items()}
     al.enable_timing(False)
-    stage["texels"] = stage.pop("normgrad")              # the stage slot of the old normalise+gradient pass now times pack_texel_kernel
+    stage["texels"] = stage.pop("normgrad")              # slot of the old normalise+gradient pass: pack_texel_kernel when it runs on its own
+    fused = stage["texels"] == 0.0                       # 640x480: EDT rows and texel packing are one kernel, timed in the edt_rows slot
+    if fused:
+        stage["edt_rows+texels"] = stage.pop("edt_rows"); stage.pop("texels")
     npts = np.array([[inf.npts[l] for l in range(LEVELS)] for inf in info], dtype=np.int64)
     itrun = np.array([[inf.iterations_run[l] for l in range(LEVELS)] for inf in info], dtype=np.int64)
     n_total = int(npts.sum())
@@ -338,6 +341,8 @@ def bench_config2(env, args):
     # the packed path moves 12), S5 points 3P + 12N, S6 24 * sum(I_L N_L)
     alg = {"pyramid": 4 * PIX * B, "canny": (4 + 3) * PIX * B + 12 * n_total, "edt_rows": 5 * PIX * B, "texels": 16 * PIX * B,
            "solve": 24 * iter_pts}
+    if fused:
+        alg["edt_rows+texels"] = alg.pop("edt_rows") + alg.pop("texels")
     bytes_pair = (32 * PIX * B + 12 * n_total + 24 * iter_pts) / B
     peak, peak_src = peaks()
     dom = "solve"
@@ -419,10 +424,39 @@ def bench_config3(env, args, pcie_peak):
         est.set_frames(dvo.FRAME_NOW, dev["now_bgr"].data_ptr(), None, count=B, device=True)
         solve()
 
+    # end to end: pinned host buffers, uploaded in 256-pair chunks on a copy stream into two staging sets so that chunk k+1 travels
+    # while chunk k is converted and solved; poses read back at the end of the pass
+    CH = min(256, B)
+    copy_stream = torch.cuda.Stream()
+    stage_buf = [{k: torch.empty((CH,) + tuple(v.shape[1:]), dtype=v.dtype, device="cuda") for k, v in pin.items()} for _ in range(2)]
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_used = [None, None]
+
     def step_host():
-        est.set_frames(dvo.FRAME_REF, pin["ref_bgr"].numpy(), pin["ref_depth"].numpy().view(np.uint16))
-        est.set_frames(dvo.FRAME_NOW, pin["now_bgr"].numpy(), None)
-        solve()
+        chunks = list(range(0, B, CH))
+
+        def upload(i):
+            c0 = chunks[i]; n = min(CH, B - c0); k = i & 1
+            if ev_used[k] is not None:
+                copy_stream.wait_event(ev_used[k])
+            with torch.cuda.stream(copy_stream):
+                for key in pin:
+                    stage_buf[k][key][:n].copy_(pin[key][c0:c0 + n], non_blocking=True)
+                ev_up[k].record(copy_stream)
+        copy_stream.wait_stream(env.stream)
+        upload(0)
+        for i, c0 in enumerate(chunks):
+            n = min(CH, B - c0); k = i & 1
+            if i + 1 < len(chunks):
+                upload(i + 1)
+            env.stream.wait_event(ev_up[k])
+            est.set_frames(dvo.FRAME_REF, stage_buf[k]["ref_bgr"].data_ptr(), stage_buf[k]["ref_depth"].data_ptr(), first=c0, count=n, device=True)
+            est.set_frames(dvo.FRAME_NOW, stage_buf[k]["now_bgr"].data_ptr(), None, first=c0, count=n, device=True)
+            ev_used[k] = torch.cuda.Event(); ev_used[k].record(env.stream)
+            est.prepare_ref(n, first=c0, compat=False)
+            est.set_pose(n, None, first=c0)
+            for l in (4, 3, 2, 1, 0):
+                est.estimate(n, l, iters=iters3, first=c0, compat=False, huber_k=hk, lambda0=lam)
         return est.get_poses(B)
 
     for _ in range(max(1, args.warmup - 1)):

@@ -778,8 +778,11 @@ inline void build_ref_level(const uint8_t* bgr, const uint16_t* depth, int W, in
                 X = Zmm / fx * ((double)r - sf * cx); Y = Zmm / fy * ((double)c - sf * cy);
                 X = X / 1000.; Y = Y / 1000.; Z = Zmm / 1000.;
             } else {
-                Z = Zmm / 1000.;
-                X = Z * ((double)c - sf * cx) / (sf * fx); Y = Z * ((double)r - sf * cy) / (sf * fy);
+                // corrected formulation (an extension, defined here): reciprocal focal lengths once per level, metres by a multiply --
+                // one rounding per operation in this order; the device evaluates exactly the same expressions
+                const double ifx = 1.0 / (sf * fx), ify = 1.0 / (sf * fy);
+                Z = Zmm * 1.0e-3;
+                X = (Z * ((double)c - sf * cx)) * ifx; Y = (Z * ((double)r - sf * cy)) * ify;
             }
             L.X[i] = X; L.Y[i] = Y; L.Z[i] = Z;
             const double egx = L.gx[i], egy = L.gy[i];
@@ -836,7 +839,8 @@ inline int warp_image(const RefLevel& L, Cam K, const double* Tr, bool compat, s
                 tR = (int)std::floor(u); tC = (int)std::floor(v);
             } else {
                 if (!(pz > 0.0)) continue;
-                const double uc = (sf * K.fx) * px / pz + sf * K.cx, vr = (sf * K.fy) * py / pz + sf * K.cy;
+                const double ipz = 1.0 / pz;                  // one division per point (corrected formulation)
+                const double uc = ((sf * K.fx) * px) * ipz + sf * K.cx, vr = ((sf * K.fy) * py) * ipz + sf * K.cy;
                 tC = (int)std::floor(uc); tR = (int)std::floor(vr);
             }
             if (tR >= 0 && tR < rows - 1 && tC >= 0 && tC < cols - 1) {

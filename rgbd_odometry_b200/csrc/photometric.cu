@@ -27,13 +27,14 @@
 struct PhGeom { int L, Bmax, W, H; int w[PH_MAX_LEVELS], h[PH_MAX_LEVELS], P[PH_MAX_LEVELS]; long long off[PH_MAX_LEVELS]; long long total; };
 __host__ __device__ inline long long ph_at(const PhGeom& g, int l, int b) { return g.off[l] + (long long)b * g.P[l]; }
 
-struct PhCam { double fx, fy, cx, cy; };
+struct PhCam { double fx, fy, cx, cy; double ifx, ify; };     // ifx / ify: 1 / (sf fx), 1 / (sf fy) of the level a launch works on
 
 // per-pair solver state (global memory)
 struct PhState {
     double Tr[16], accTr[16], accA[36], accb[6];
     double accE, lambda, sumsq_first, sumsq_last, visible;
     int have, status, iters_run, stop, nreproj;
+    int nreproj_last;      // nReprojected of the last warp an estimate() consumed (nreproj itself is the running counter)
 };
 
 struct dvo_photo_ctx {
@@ -61,8 +62,10 @@ __device__ __forceinline__ PixGeom ph_xyz(int r, int c, double Zmm, double sf, c
         double X = Zmm / K.fx * ((double)r - sf * K.cx), Y = Zmm / K.fy * ((double)c - sf * K.cy);
         o.X = X / 1000.; o.Y = Y / 1000.; o.Z = Zmm / 1000.;
     } else {
-        o.Z = Zmm / 1000.;
-        o.X = o.Z * ((double)c - sf * K.cx) / (sf * K.fx); o.Y = o.Z * ((double)r - sf * K.cy) / (sf * K.fy);
+        // corrected formulation (oracle photo::build_ref_level): reciprocal focal lengths once per level (K.ifx / K.ify are
+        // 1 / (sf fx), 1 / (sf fy) of THIS level, set by ph_args), metres by a multiply -- no division per pixel
+        o.Z = Zmm * 1.0e-3;
+        o.X = (o.Z * ((double)c - sf * K.cx)) * K.ifx; o.Y = (o.Z * ((double)r - sf * K.cy)) * K.ify;
     }
     return o;
 }
@@ -155,6 +158,7 @@ struct PhArgs {
     const uint8_t* gray_ref; const uint16_t* depth_ref; const uint8_t* gray_now;   // level regions (slot 0)
     int* winner; double* partial; double* A; PhState* st;
     int level, rows, cols, P, first, compat, nblk, maxblk; double huber_k, lambda0;
+    int reset_winner;      // ph_accum_kernel hands the winner map back cleared (the estimate loop then needs no clear pass per iteration)
 };
 
 // A = J^T J over the reference level (setPyramidalImages :229)
@@ -225,7 +229,8 @@ __global__ void __launch_bounds__(256) ph_splat_kernel(PhArgs a) {
                 const double u = a.K.fx * px / pz + a.sf * a.K.cx, v = a.K.fy * py / pz + a.sf * a.K.cy;
                 if (u > -1.0e9 && u < 1.0e9 && v > -1.0e9 && v < 1.0e9) { tR = (int)floor(u); tC = (int)floor(v); }
             } else if (pz > 0.0) {
-                const double uc = (a.sf * a.K.fx) * px / pz + a.sf * a.K.cx, vr = (a.sf * a.K.fy) * py / pz + a.sf * a.K.cy;
+                const double ipz = 1.0 / pz;
+                const double uc = ((a.sf * a.K.fx) * px) * ipz + a.sf * a.K.cx, vr = ((a.sf * a.K.fy) * py) * ipz + a.sf * a.K.cy;
                 if (uc > -1.0e9 && uc < 1.0e9 && vr > -1.0e9 && vr < 1.0e9) { tC = (int)floor(uc); tR = (int)floor(vr); }
             }
             if (tR >= 0 && tR < rows - 1 && tC >= 0 && tC < cols - 1) {
@@ -245,18 +250,24 @@ __global__ void __launch_bounds__(256) ph_splat_kernel(PhArgs a) {
 __global__ void __launch_bounds__(PH_THREADS) ph_accum_kernel(PhArgs a) {
     const int b = a.first + blockIdx.y;
     PhState& S = a.st[b];
+    // Huber weights: the residual is a difference of two 8-bit intensities, so |e| is an integer in 0..255 and k / |e| takes 256
+    // values -- one IEEE division per table entry instead of one per pixel, same values as the oracle's huber_w
+    __shared__ double s_hw[256];
+    s_hw[threadIdx.x] = (a.huber_k > 0.0 && (double)threadIdx.x > a.huber_k) ? a.huber_k / (double)threadIdx.x : 1.0;
+    __syncthreads();
     double acc[PH_NACC];
 #pragma unroll
     for (int k = 0; k < PH_NACC; ++k) acc[k] = 0.0;
     if (!S.stop) {
         const uint8_t* g = a.gray_ref + (long long)b * a.P; const uint16_t* d = a.depth_ref + (long long)b * a.P;
         const uint8_t* gn = a.gray_now + (long long)b * a.P;
-        const int* wn = a.winner + (long long)b * a.g.P[0];
+        int* wn = a.winner + (long long)b * a.g.P[0];
         const int rows = a.rows, cols = a.cols;
         for (int k = blockIdx.x * PH_THREADS + threadIdx.x; k < a.P; k += gridDim.x * PH_THREADS) {
             if (a.compat) {
                 // flattened index k: eps is row-major (cell k), J row k is the column-major pixel k (quirk 5); holes give -I_now
                 const int wk = wn[k];
+                if (a.reset_winner) wn[k] = -1;
                 const double cv = (wk >= 0) ? (double)g[(wk % rows) * cols + (wk / rows)] : 0.0;
                 const double e = cv - (double)gn[k];
                 const int r = k % rows, c = k / rows;
@@ -267,10 +278,10 @@ __global__ void __launch_bounds__(PH_THREADS) ph_accum_kernel(PhArgs a) {
             } else {
                 const int wk = wn[k];
                 if (wk < 0) continue;
+                if (a.reset_winner) wn[k] = -1;
                 const int rs = wk % rows, cs = wk / rows;     // source pixel that owns this cell
                 const double e = (double)g[rs * cols + cs] - (double)gn[k];
-                const double ae = fabs(e);
-                const double w = (a.huber_k > 0.0) ? (ae <= a.huber_k ? 1.0 : a.huber_k / ae) : 1.0;
+                const double w = s_hw[(int)fabs(e)];
                 double J[6]; ph_jrow(g, d, rows, cols, rs, cs, a.sf, a.K, false, J);
                 int idx = 8;
 #pragma unroll
@@ -339,6 +350,7 @@ __global__ void __launch_bounds__(64) ph_solve_kernel(PhArgs a, int itr) {
     if (threadIdx.x != 0) return;
     const double sumsq = tot[6];
     S.visible = (double)S.nreproj / ((double)a.rows * (double)a.cols);
+    S.nreproj_last = S.nreproj; S.nreproj = 0;               // the next splat counts from zero
     if (itr == 0) S.sumsq_first = sumsq;
     S.sumsq_last = sumsq; S.iters_run = itr + 1;
     double Aev[36];
@@ -395,7 +407,7 @@ __global__ void ph_init_state_kernel(PhState* st, int first, int count, const do
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) S.Tr[4 * r + c] = p[3 * r + c]; S.Tr[4 * r + 3] = p[9 + r]; }
         S.Tr[12] = S.Tr[13] = S.Tr[14] = 0.0; S.Tr[15] = 1.0;
     }
-    S.have = 0; S.status = 0; S.iters_run = 0; S.stop = 0; S.nreproj = 0; S.lambda = lambda0; S.accE = 0.0;
+    S.have = 0; S.status = 0; S.iters_run = 0; S.stop = 0; S.nreproj = 0; S.nreproj_last = 0; S.lambda = lambda0; S.accE = 0.0;
     S.sumsq_first = S.sumsq_last = 0.0; S.visible = 0.0;
 }
 
@@ -445,11 +457,12 @@ bool ph_range_ok(dvo_photo_ctx* c, int first, int count) { return c && first >= 
 PhArgs ph_args(dvo_photo_ctx* c, int level, int first, int compat, double huber_k, double lambda0) {
     PhArgs a;
     a.g = c->g; a.K = c->K; a.sf = ldexp(1.0, -level);
+    a.K.ifx = 1.0 / (a.sf * a.K.fx); a.K.ify = 1.0 / (a.sf * a.K.fy);
     a.gray_ref = c->gray[0] + c->g.off[level]; a.depth_ref = c->depth[0] + c->g.off[level]; a.gray_now = c->gray[1] + c->g.off[level];
     a.winner = c->winner; a.partial = c->partial; a.A = c->A; a.st = c->st;
     a.level = level; a.rows = c->g.h[level]; a.cols = c->g.w[level]; a.P = c->g.P[level]; a.first = first; a.compat = compat;
     int nblk = (a.P + PH_THREADS * 8 - 1) / (PH_THREADS * 8); if (nblk < 1) nblk = 1; if (nblk > c->maxblk) nblk = c->maxblk;
-    a.nblk = nblk; a.maxblk = c->maxblk; a.huber_k = huber_k; a.lambda0 = lambda0;
+    a.nblk = nblk; a.maxblk = c->maxblk; a.huber_k = huber_k; a.lambda0 = lambda0; a.reset_winner = 0;
     return a;
 }
 template <typename T> int ph_alloc(T** p, size_t n) {
@@ -603,12 +616,15 @@ int dvo_photo_estimate(dvo_photo_ctx* c, int first, int count, int level, int it
     ph_init_state_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(c->st, first, count, nullptr, lambda0);
     c->launches++;
     const dim3 gpix((a.P + 255) / 256, count);
+    // the winner map is cleared once; every accumulation pass hands it back cleared (cells of stopped pairs are never written)
+    a.reset_winner = 1;
+    ph_clear_kernel<<<gpix, 256, 0, c->stream>>>(a);
+    c->launches++;
     for (int itr = 0; itr < iters; ++itr) {
-        ph_clear_kernel<<<gpix, 256, 0, c->stream>>>(a);
         ph_splat_kernel<<<gpix, 256, 0, c->stream>>>(a);
         ph_accum_kernel<<<dim3(a.nblk, count), PH_THREADS, 0, c->stream>>>(a);
         ph_solve_kernel<<<count, 64, 0, c->stream>>>(a, itr);
-        c->launches += 4;
+        c->launches += 3;
     }
     ph_finish_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(c->st, first, count, compat);
     c->launches++;
@@ -624,7 +640,7 @@ int dvo_photo_get_poses(dvo_photo_ctx* c, int first, int count, double* R9T3, dv
     for (int i = 0; i < count; ++i) {
         if (R9T3) { double* p = R9T3 + 12 * (size_t)i; for (int r = 0; r < 3; ++r) { for (int q = 0; q < 3; ++q) p[3 * r + q] = st[i].Tr[4 * r + q]; p[9 + r] = st[i].Tr[4 * r + 3]; } }
         if (info) {
-            info[i].status = st[i].status; info[i].iters_run = st[i].iters_run; info[i].nreproj = st[i].nreproj;
+            info[i].status = st[i].status; info[i].iters_run = st[i].iters_run; info[i].nreproj = st[i].nreproj_last;
             info[i].sumsq_first = st[i].sumsq_first; info[i].sumsq_last = st[i].sumsq_last; info[i].visible = st[i].visible;
             memcpy(info[i].A, st[i].accA, sizeof(double) * 36); memcpy(info[i].b, st[i].accb, sizeof(double) * 6);
         }

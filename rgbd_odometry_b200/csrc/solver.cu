@@ -10,6 +10,22 @@
 namespace {
 
 constexpr int EVAL_THREADS = 256;     // inspection kernel
+// compile-time experiment knobs (tools/solve_variants.sh rebuilds with -D...): measured per 1024 pairs, GN 10 it / SUBGRAD 50 it:
+//   escape path out of line + run-time weight mode 4.06 / 17.96 ms; escape path inline 4.07 / 17.43; + weight mode specialised 4.01 / 17.19
+#ifndef DVO_GN_THREADS_PER_SM
+#define DVO_GN_THREADS_PER_SM 512     // resident threads per SM the 29-accumulator kernel is compiled for (768 = 85 registers, spills)
+#endif
+#ifndef DVO_ESCAPE_INLINE
+#define DVO_ESCAPE_INLINE 1
+#endif
+#if DVO_ESCAPE_INLINE
+#define DVO_ESCAPE_ATTR __device__ __forceinline__
+#else
+#define DVO_ESCAPE_ATTR __device__ __noinline__
+#endif
+#ifndef DVO_WMODE_SPECIALIZE
+#define DVO_WMODE_SPECIALIZE 1
+#endif
 
 // ------------------------------------------------------------------ fp64 3x3 / SE(3) helpers (device)
 __device__ __forceinline__ void m3_mul(const double* A, const double* B, double* C) {
@@ -189,7 +205,7 @@ __device__ __forceinline__ bool unpack_texel(const uint2 t, Stencil& s) {
     s.d = s.c + ((int)(t.y << 2) >> 22);
     return (int)t.x >= 0;
 }
-__device__ __noinline__ void stencil_from_d2(const int32_t* __restrict__ d2, int w, int h, int x, int y, Stencil& s) {
+DVO_ESCAPE_ATTR void stencil_from_d2(const int32_t* __restrict__ d2, int w, int h, int x, int y, Stencil& s) {
     const int32_t* d = d2 + y * w + x;
     s.c = __ldg(d);
     const bool bx = (x == 0 || x == w - 1), by = (y == 0 || y == h - 1);
@@ -256,9 +272,10 @@ __device__ __forceinline__ Proj project_point(float Xp, float Yp, float Zp, cons
 }
 
 // Jacobian row, residual and weight from the gathered texel {DTn, gx, gy, getWeightOf(DTn)} (:383-406, :446-450).
-template <int ARITH, int JAC>
+template <int ARITH, int JAC, int WMODE>
 __device__ __forceinline__ void finish_point(const Proj& q, const float4 t, const PoseF& P, const LevelCam& cam,
-                                             int weight_mode, float huber_k, float* Jr, float& e, float& wgt) {
+                                             int weight_mode_rt, float huber_k, float* Jr, float& e, float& wgt) {
+    const int weight_mode = (WMODE >= 0) ? WMODE : weight_mode_rt;
     typedef Ar<ARITH> A;
     const float* R = P.R;
     const float G0 = t.y, G1 = t.z;
@@ -351,17 +368,19 @@ template <bool NEED_H> struct AccN { static constexpr int N = NEED_H ? 29 : 8; }
 
 // Software-pipelined sweep over a thread's points: the coordinates are loaded two points ahead and the (random)
 // texel gather of the next point is in flight while the current point's Jacobian / fp64 accumulation executes.
-template <int ARITH, int JAC, bool NEED_H, int THREADS, bool OUT, int RES, int TEX>
+// (A counted loop with unconditional look-ahead loads into slack behind the arrays, unrolled by 1 / 2 / 3, was measured slower:
+// 4.51 / 4.32 / 4.84 ms per 1024 pairs against 4.01 for this guarded form -- DESIGN.md "measured and rejected".)
+template <int ARITH, int JAC, bool NEED_H, int THREADS, bool OUT, int RES, int TEX, int WMODE>
 __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, const float* __restrict__ Y,
                                                   const float* __restrict__ Z, int N, const PoseF& P, const LevelCam& cam,
-                                                  const TexSrc& S, int weight_mode, float huber_k,
+                                                  const TexSrc& S, int weight_mode_rt, float huber_k,
                                                   double* acc, int& nvis, float* o_eps, float* o_w, float* o_u, float* o_v,
                                                   float* o_J) {
     constexpr int stride = THREADS;
-    const int start = threadIdx.x;
     typedef Ar<ARITH> A;
     typedef Texel<TEX> TX;
-    int i = start;
+    const int weight_mode = (WMODE >= 0) ? WMODE : weight_mode_rt;
+    int i = threadIdx.x;
     if (i >= N) return;
     float cx = __ldg(X + i), cy = __ldg(Y + i), cz = __ldg(Z + i);
     Proj q = project_point<TEX>(cx, cy, cz, P, cam);
@@ -380,7 +399,7 @@ __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, c
         float Jr[6], e = 0.f, wgt = 0.f;
         if (q.idx >= 0) {
             const float4 tv = TX::resolve(S, cam, q, t);
-            finish_point<ARITH, JAC>(q, tv, P, cam, weight_mode, huber_k, Jr, e, wgt);
+            finish_point<ARITH, JAC, WMODE>(q, tv, P, cam, weight_mode_rt, huber_k, Jr, e, wgt);
             if (RES == DVO_RESIDUAL_DT_INTERP) {                                     // :443-444, weight from the interpolated value (:450)
                 e = interpolate_dt<TEX>(S, cam, q, tv.x);
                 if (weight_mode == DVO_WEIGHT_REF_CAUCHY) wgt = A::weight_ref(e);
@@ -599,8 +618,8 @@ __global__ void __launch_bounds__(1024) solve_order_kernel(const int* __restrict
 // pair's points over 2/4/8 CTAs and combined partial sums through distributed shared memory was measured slower --
 // 4.29 ms -> 4.58 / 5.53 / 8.62 ms per 1024 pairs -- and removed; so was a cp.async shared-memory ring that kept 2..8
 // texel gathers in flight per thread: 4.56 .. 4.72 ms.  See DESIGN.md "measured and rejected".)
-template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX>
-__global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve_kernel(SolveArgs a) {
+template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX, int WMODE>
+__global__ void __launch_bounds__(THREADS, (NEED_H ? DVO_GN_THREADS_PER_SM : 768) / THREADS) solve_kernel(SolveArgs a) {
     extern __shared__ float s_lut[];          // TEX 1: 2 * LUT_N floats
     constexpr int NACC = AccN<NEED_H>::N;
     constexpr int SOLVE_WARPS = THREADS / 32;
@@ -661,7 +680,7 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? 512 : 768) / THREADS) solve
 #pragma unroll
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
             int nvis = 0;
-            accumulate_points<ARITH, JAC, NEED_H, THREADS, false, RES, TEX>(X, Y, Z, N, P, cam, src, a.prm.weight, a.prm.huber_k, acc, nvis,
+            accumulate_points<ARITH, JAC, NEED_H, THREADS, false, RES, TEX, WMODE>(X, Y, Z, N, P, cam, src, a.prm.weight, a.prm.huber_k, acc, nvis,
                                                   nullptr, nullptr, nullptr, nullptr, nullptr);
             block_reduce<NACC, THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
             if (lead) {
@@ -730,7 +749,7 @@ __global__ void __launch_bounds__(EVAL_THREADS) eval_kernel(EvalArgs a) {
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
     int nvis = 0;
-    accumulate_points<ARITH, JAC, true, EVAL_THREADS, true, RES, TEX>(a.X + base, a.Y + base, a.Z + base, N, P, cam, src, a.weight, a.huber_k,
+    accumulate_points<ARITH, JAC, true, EVAL_THREADS, true, RES, TEX, -1>(a.X + base, a.Y + base, a.Z + base, N, P, cam, src, a.weight, a.huber_k,
                                         acc, nvis, a.eps, a.w, a.u, a.v, a.J);
     block_reduce<NACC, EVAL_THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
     if (threadIdx.x == 0) {
@@ -799,14 +818,23 @@ static cudaError_t optin_lut_smem(int device) {
     return e;
 }
 
-template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX>
-static cudaError_t launch_solve_inst(dvo_ctx* c, const SolveArgs& a, int count) {
+template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX, int WMODE>
+static cudaError_t launch_solve_w(dvo_ctx* c, const SolveArgs& a, int count) {
     if (TEX) {
-        const cudaError_t e = optin_lut_smem<SolveArgs, solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX>>(c->cfg.device);
+        const cudaError_t e = optin_lut_smem<SolveArgs, solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX, WMODE>>(c->cfg.device);
         if (e != cudaSuccess) return e;
     }
-    solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX><<<count, THREADS, TEX ? LUT_BYTES : 0, c->stream>>>(a);
+    solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX, WMODE><<<count, THREADS, TEX ? LUT_BYTES : 0, c->stream>>>(a);
     return cudaGetLastError();
+}
+
+// the shipped weight (getWeightOf, REF_CAUCHY) on the shipped residual gets its own instantiation with the weight mode fixed at
+// compile time; every other combination takes the generic kernel that branches on the run-time value
+template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX>
+static cudaError_t launch_solve_inst(dvo_ctx* c, const SolveArgs& a, int count) {
+    if (DVO_WMODE_SPECIALIZE && TEX == 1 && ARITH == DVO_ARITH_EXACT && RES == DVO_RESIDUAL_DT_FLOOR && a.prm.weight == DVO_WEIGHT_REF_CAUCHY)
+        return launch_solve_w<ARITH, JAC, NEED_H, THREADS, RES, TEX, (TEX == 1 && ARITH == DVO_ARITH_EXACT && RES == DVO_RESIDUAL_DT_FLOOR) ? DVO_WEIGHT_REF_CAUCHY : -1>(c, a, count);
+    return launch_solve_w<ARITH, JAC, NEED_H, THREADS, RES, TEX, -1>(c, a, count);
 }
 
 template <int ARITH, int JAC, int TEX>
