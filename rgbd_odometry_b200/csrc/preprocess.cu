@@ -246,42 +246,59 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
             loadrow(vn, ven);                                         // y0+2, prefetched one row ahead
             const int c0 = 30 * k, sh = c0 & 31;
             uint32_t* Bm = (lane == 0 ? C : E) + (y0 + 1) * pitch + (c0 >> 5) + 1;   // lane 0 merges candidates, lane 1 the strong set
+            // The row step is branch-free up to the bitmap merge: every select below is a predicated move, so the warp stays
+            // converged for the shuffles and ballots (the nested ifs of the first version cost a third of the loop in
+            // BSSY / BSYNC / BRA.DIV bookkeeping).  halo lanes and out-of-image columns carry m == 0 and never pass m > low.
+            const int lowt = halo ? 0x7fffffff : low;
             const bool writer = lane < 2;
-            for (int y = y0; y < y1; ++y) {
+            // One row step.  Arguments are passed by role so that the caller can rotate the roles instead of the registers:
+            // (sA, bA), (sB, bB) = horizontal Sobel sums of gray rows y, y+1 -> (sC, bC) receives row y+2; the magnitude rows
+            // P / C hold y-1, y -> N receives y+1.  The step is branch-free up to the bitmap merge: every select is a
+            // predicated move, so the warp stays converged for the shuffles and ballots (the nested ifs of the first version
+            // cost a third of the loop in BSSY / BSYNC / BRA.DIV bookkeeping).  Halo lanes never pass m > lowt.
+            auto row_step = [&](int y, int sA, int bA, int sB, int bB, int& sC, int& bC, int pL, int pC, int pR, int cL, int cC, int cR,
+                                int& nL, int& nC, int& nR, int dx0, int dy0, int& dx1, int& dy1) {
                 v = vn; ve = ven;
                 loadrow(vn, ven);                                     // gray row y+3
-                hsA = hsB; hbA = hbB; hsB = hsC; hbB = hbC;
-                sums(v, ve, hsC, hbC);                                // gray row y+2
-                const int dxN = hsA + 2 * hsB + hsC, dyN = hbC - hbA; // gradient at row y+1
-                const int mNC = (incol && y + 1 < h) ? dxN * dxN + dyN * dyN : 0;
-                const int mNL = __shfl_up_sync(0xffffffffu, mNC, 1), mNR = __shfl_down_sync(0xffffffffu, mNC, 1);
-                bool cand = false, strong = false;
-                const int m = mCC;
-                if (m > low && !halo) {                               // m == 0 outside the image
-                    const int ax = abs(dxC), ay = abs(dyC) << 15;
-                    const int tg22x = ax * TG22;
-                    bool keep;
-                    if (ay < tg22x) keep = (m > mCL) && (m >= mCR);
-                    else {
-                        const int tg67x = tg22x + (ax << 16);
-                        if (ay > tg67x) keep = (m > mPC) && (m >= mNC);
-                        else { const bool neg = ((dxC ^ dyC) < 0); keep = (m > (neg ? mPR : mPL)) && (m > (neg ? mNL : mNR)); }
-                    }
-                    cand = keep; strong = keep && (m > high);
-                }
+                sums(v, ve, sC, bC);                                  // gray row y+2
+                dx1 = sA + 2 * sB + sC; dy1 = bC - bA;                // gradient at row y+1
+                nC = (incol && y + 1 < h) ? dx1 * dx1 + dy1 * dy1 : 0;
+                nL = __shfl_up_sync(0xffffffffu, nC, 1); nR = __shfl_down_sync(0xffffffffu, nC, 1);
+                const int m = cC;
+                const int ax = abs(dx0), ays = abs(dy0) << 15;
+                const int tg22x = ax * TG22;
+                const bool horiz = ays < tg22x, vert = ays > tg22x + (ax << 16);
+                const bool neg = (dx0 ^ dy0) < 0;
+                const int da = neg ? pR : pL, db = neg ? nL : nR;                     // the two diagonal neighbours
+                const int na = horiz ? cL : (vert ? pC : da);
+                const int nb = horiz ? cR : (vert ? nC : db);
+                // horizontal / vertical: m > na && m >= nb; diagonal: m > na && m > nb
+                const bool keep = (m > na) && (m + ((horiz || vert) ? 1 : 0) > nb);
+                const bool cand = keep && (m > lowt);
+                const bool strong = cand && (m > high);
                 const uint32_t cb = __ballot_sync(0xffffffffu, cand);
-                if (cb) {                                             // warp-uniform
-                    const uint32_t sb = __ballot_sync(0xffffffffu, strong);
-                    if (writer) {
-                        const uint32_t bits = ((lane == 0 ? cb : sb) >> 1) & 0x3fffffffu;
-                        if (bits) {
-                            atomicOr(Bm, bits << sh);
-                            const uint32_t hi = (sh > 2) ? bits >> (32 - sh) : 0u;
-                            if (hi) atomicOr(Bm + 1, hi);
-                        }
-                    }
+                const uint32_t sb = __ballot_sync(0xffffffffu, strong);
+                const uint32_t bits = ((lane == 0 ? cb : sb) >> 1) & 0x3fffffffu;
+                if (writer && bits) {
+                    atomicOr(Bm, bits << sh);
+                    const uint32_t hi = (sh > 2) ? bits >> (32 - sh) : 0u;
+                    if (hi) atomicOr(Bm + 1, hi);
                 }
                 Bm += pitch;
+            };
+            // roles on entry: sums A = row y0, B = row y0+1 (hsB / hsC of the prologue), magnitudes P = y0-1, C = y0
+            int s0 = hsB, b0 = hbB, s1 = hsC, b1 = hbC, s2 = 0, b2 = 0;
+            int mNL = 0, mNC = 0, mNR = 0, dxN = 0, dyN = 0;
+            int y = y0;
+            for (; y + 3 <= y1; y += 3) {             // three steps = one full rotation of the sums and of the magnitude rows
+                row_step(y, s0, b0, s1, b1, s2, b2, mPL, mPC, mPR, mCL, mCC, mCR, mNL, mNC, mNR, dxC, dyC, dxN, dyN);
+                row_step(y + 1, s1, b1, s2, b2, s0, b0, mCL, mCC, mCR, mNL, mNC, mNR, mPL, mPC, mPR, dxN, dyN, dxC, dyC);
+                row_step(y + 2, s2, b2, s0, b0, s1, b1, mNL, mNC, mNR, mPL, mPC, mPR, mCL, mCC, mCR, dxC, dyC, dxN, dyN);
+                dxC = dxN; dyC = dyN;                 // the gradient pair has period two: one move per three rows
+            }
+            for (; y < y1; ++y) {                     // remainder: plain step, roles rotated by moves
+                row_step(y, s0, b0, s1, b1, s2, b2, mPL, mPC, mPR, mCL, mCC, mCR, mNL, mNC, mNR, dxC, dyC, dxN, dyN);
+                s0 = s1; b0 = b1; s1 = s2; b1 = b2;
                 mPL = mCL; mPC = mCC; mPR = mCR; mCL = mNL; mCC = mNC; mCR = mNR; dxC = dxN; dyC = dyN;
             }
         }
