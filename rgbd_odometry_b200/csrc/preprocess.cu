@@ -153,6 +153,9 @@ __device__ __forceinline__ void row_sums(const uint8_t* __restrict__ grow, int w
 }
 
 constexpr int CANNY_MAX_WARPS = 24;
+#ifndef DVO_CANNY_STOP_AFTER
+#define DVO_CANNY_STOP_AFTER 0
+#endif
 
 // The hysteresis sweep is a chaotic relaxation on purpose: within a round a thread reads neighbouring words their owners may be
 // updating (bits only ever get set, every word has one writer, the loop ends after a round without changes).  In shared memory
@@ -305,6 +308,9 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     }
     __syncthreads();
 
+#if DVO_CANNY_STOP_AFTER == 1
+    return;        // phase timing probe (tools/prepare_variants.sh); never defined in a shipped build
+#endif
     // ------------------------------------------------------------------ phase 2: hysteresis closure
     {
         const int Hs = max(1, min(h, min(T, 768) / wd));    // row strips
@@ -376,6 +382,9 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
         }
     }
 
+#if DVO_CANNY_STOP_AFTER == 2
+    return;        // phase timing probe (tools/prepare_variants.sh); never defined in a shipped build
+#endif
     // ------------------------------------------------------------------ phase 3: edge bytes (0/255) + edge count
     const int nw = h * wd;
     {
@@ -401,6 +410,9 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
         if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
     }
 
+#if DVO_CANNY_STOP_AFTER == 3
+    return;        // phase timing probe (tools/prepare_variants.sh); never defined in a shipped build
+#endif
     // ------------------------------------------------------------------ phase 4 (ref): selected = edge && depth > 100, in place
     if (do_points) {
         const uint16_t* __restrict__ dep = a.depth + (long long)b * a.P;

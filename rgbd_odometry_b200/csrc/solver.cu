@@ -15,6 +15,13 @@ constexpr int EVAL_THREADS = 256;     // inspection kernel
 #ifndef DVO_GN_THREADS_PER_SM
 #define DVO_GN_THREADS_PER_SM 512     // resident threads per SM the 29-accumulator kernel is compiled for (768 = 85 registers, spills)
 #endif
+#ifndef DVO_SOLVE_PIPE_GN
+#define DVO_SOLVE_PIPE_GN 4           // ring depth of the shipped configuration's sweep, 29-accumulator kernel (0 = register pipeline, one gather ahead)
+#endif
+#ifndef DVO_SOLVE_PIPE_SG
+#define DVO_SOLVE_PIPE_SG 2           // same, 8-accumulator (sub-gradient) kernel
+#endif
+
 #ifndef DVO_ESCAPE_INLINE
 #define DVO_ESCAPE_INLINE 1
 #endif
@@ -169,6 +176,7 @@ struct LevelCam { float M00, M02, M11, M12; int w, h; float wf, hf, M00_lo, M11_
 //                      point more than 63 pixels from every edge) are evaluated directly with the same operations.
 //   TEX = 0: legacy float4 texels {DTn, gx, gy, w} written by normgrad_kernel.
 constexpr int LUT_N = 4096;
+constexpr int LUT_BYTES = 2 * LUT_N * (int)sizeof(float);
 struct TexSrc {
     const float4* tex;       // TEX 0: level / slot base
     const uint2* tex8;       // TEX 1: level / slot base
@@ -435,6 +443,74 @@ __device__ __forceinline__ void accumulate_points(const float* __restrict__ X, c
     }
 }
 
+// ---- sweep with a shared-memory ring (PIPE = ring depth D): the shipped configuration only (EXACT arithmetic, reference Jacobian,
+// floor residual, packed texels, getWeightOf weights).  A point is projected D-1 steps before it is consumed; its normalised
+// coordinates, reprojection and texel index go to the thread's own ring slot and the 8-byte texel follows with cp.async (no
+// destination register, no scoreboard wait), so up to D-1 gathers per thread are in flight instead of one.  With 16-byte row-major
+// texels the sweep was bound by DRAM transactions and a deeper ring did not pay (round 1); with packed Morton texels DRAM runs at
+// 20 % and the first use of a gathered texel is the top stall.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int JAC, bool NEED_H, int THREADS, int D>
+__device__ __forceinline__ void accumulate_points_ring(const float* __restrict__ X, const float* __restrict__ Y, const float* __restrict__ Z, int N,
+                                                       const PoseF& P, const LevelCam& cam, const TexSrc& S, double* acc, int& nvis,
+                                                       unsigned char* ring) {
+    static_assert((D & (D - 1)) == 0 && D >= 2, "ring depth must be a power of two");
+    typedef Ar<DVO_ARITH_EXACT> A;
+    float4* ringP = reinterpret_cast<float4*>(ring);                               // [D][THREADS] {X, Y, Z, texel index}
+    float2* ringUV = reinterpret_cast<float2*>(ring + D * THREADS * 16);            // [D][THREADS] reprojection (escape path only)
+    uint2* ringT = reinterpret_cast<uint2*>(ring + D * THREADS * 24);               // [D][THREADS] texel, filled by cp.async
+    const int tid = threadIdx.x;
+    if (tid >= N) return;
+    const int n_iter = (N - tid + THREADS - 1) / THREADS;
+    const float* __restrict__ px = X + tid; const float* __restrict__ py = Y + tid; const float* __restrict__ pz = Z + tid;
+    float cx = __ldg(px), cy = __ldg(py), cz = __ldg(pz);
+    auto issue = [&](int k) {                      // project point k (coordinates in cx, cy, cz), start its gather, fetch the next coordinates
+        const int slot = (k & (D - 1)) * THREADS + tid;
+        const Proj q = project_point<1>(cx, cy, cz, P, cam);
+        ringP[slot] = make_float4(q.X, q.Y, q.Z, __int_as_float(q.idx));
+        ringUV[slot] = make_float2(q.u, q.v);
+        if (q.idx >= 0) cp_async8(&ringT[slot], S.tex8 + q.idx);
+        if (k + 1 < n_iter) { px += THREADS; py += THREADS; pz += THREADS; cx = __ldg(px); cy = __ldg(py); cz = __ldg(pz); }
+    };
+#pragma unroll
+    for (int k = 0; k < D - 1; ++k) { if (k < n_iter) issue(k); cp_async_commit(); }
+    for (int k = 0; k < n_iter; ++k) {
+        if (k + D - 1 < n_iter) issue(k + D - 1);
+        cp_async_commit();
+        cp_async_wait<D - 1>();                    // the group of point k has landed
+        const int slot = (k & (D - 1)) * THREADS + tid;
+        const float4 pr = ringP[slot];
+        Proj q; q.X = pr.x; q.Y = pr.y; q.Z = pr.z; q.idx = __float_as_int(pr.w);
+        if (q.idx >= 0) {
+            const float2 uv = ringUV[slot]; q.u = uv.x; q.v = uv.y;
+            const float4 tv = Texel<1>::resolve(S, cam, q, ringT[slot]);
+            float Jr[6], e, wgt;
+            finish_point<DVO_ARITH_EXACT, JAC, DVO_WEIGHT_REF_CAUCHY>(q, tv, P, cam, DVO_WEIGHT_REF_CAUCHY, 0.f, Jr, e, wgt);
+            ++nvis;
+            const double de = (double)e;
+            acc[6] = fma(de, de, acc[6]);
+            acc[7] += de;
+            double Jw[6];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) { Jw[c] = (double)A::mul(Jr[c], wgt); acc[c] = fma(Jw[c], de, acc[c]); }
+            if (NEED_H) {
+                int idx = 8;
+#pragma unroll
+                for (int r = 0; r < 6; ++r)
+#pragma unroll
+                    for (int c = r; c < 6; ++c) { acc[idx] = fma(Jw[r], (double)Jr[c], acc[idx]); ++idx; }
+            }
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // Deterministic block reduction of NACC fp64 accumulators per thread.
 // Stage 1 (per warp).  TRANSPOSED (the 29-accumulator Gauss-Newton case): eight accumulators at a time are parked
 // in a [8][36] shared tile (row = accumulator, column = lane); lane (r, q) = (lane / 4, lane % 4) sums columns
@@ -618,7 +694,7 @@ __global__ void __launch_bounds__(1024) solve_order_kernel(const int* __restrict
 // pair's points over 2/4/8 CTAs and combined partial sums through distributed shared memory was measured slower --
 // 4.29 ms -> 4.58 / 5.53 / 8.62 ms per 1024 pairs -- and removed; so was a cp.async shared-memory ring that kept 2..8
 // texel gathers in flight per thread: 4.56 .. 4.72 ms.  See DESIGN.md "measured and rejected".)
-template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX, int WMODE>
+template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX, int WMODE, int PIPE>
 __global__ void __launch_bounds__(THREADS, (NEED_H ? DVO_GN_THREADS_PER_SM : 768) / THREADS) solve_kernel(SolveArgs a) {
     extern __shared__ float s_lut[];          // TEX 1: 2 * LUT_N floats
     constexpr int NACC = AccN<NEED_H>::N;
@@ -680,8 +756,11 @@ __global__ void __launch_bounds__(THREADS, (NEED_H ? DVO_GN_THREADS_PER_SM : 768
 #pragma unroll
             for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
             int nvis = 0;
-            accumulate_points<ARITH, JAC, NEED_H, THREADS, false, RES, TEX, WMODE>(X, Y, Z, N, P, cam, src, a.prm.weight, a.prm.huber_k, acc, nvis,
-                                                  nullptr, nullptr, nullptr, nullptr, nullptr);
+            if constexpr (PIPE > 0 && JAC == DVO_JAC_REFERENCE)
+                accumulate_points_ring<JAC, NEED_H, THREADS, PIPE>(X, Y, Z, N, P, cam, src, acc, nvis, reinterpret_cast<unsigned char*>(s_lut) + LUT_BYTES);
+            else
+                accumulate_points<ARITH, JAC, NEED_H, THREADS, false, RES, TEX, WMODE>(X, Y, Z, N, P, cam, src, a.prm.weight, a.prm.huber_k, acc, nvis,
+                                                      nullptr, nullptr, nullptr, nullptr, nullptr);
             block_reduce<NACC, THREADS>(acc, nvis, s_scr, s_red, s_nv, s_tot, &s_nvtot);
             if (lead) {
                 double* tr = nullptr;
@@ -807,24 +886,26 @@ __global__ void gop_kernel(int nseq, int nframes, const int* __restrict__ kind, 
 
 // Kernels that use the lookup tables need 32 KB of dynamic shared memory on top of their static reduction scratch:
 // opt in once per kernel and device.
-constexpr int LUT_BYTES = 2 * LUT_N * (int)sizeof(float);
 template <typename KArgs, void (*KERN)(KArgs)>
-static cudaError_t optin_lut_smem(int device) {
+static cudaError_t optin_lut_smem(int device, int bytes = LUT_BYTES) {
     static unsigned long long done = 0ull;
     const unsigned long long bit = 1ull << (device & 63);
     if (done & bit) return cudaSuccess;
-    const cudaError_t e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, LUT_BYTES);
+    const cudaError_t e = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess) done |= bit;
     return e;
 }
 
 template <int ARITH, int JAC, bool NEED_H, int THREADS, int RES, int TEX, int WMODE>
 static cudaError_t launch_solve_w(dvo_ctx* c, const SolveArgs& a, int count) {
-    if (TEX) {
-        const cudaError_t e = optin_lut_smem<SolveArgs, solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX, WMODE>>(c->cfg.device);
+    // the shipped configuration (reference Jacobian, getWeightOf weights, packed texels) takes the ring sweep
+    constexpr int PIPE = (WMODE == DVO_WEIGHT_REF_CAUCHY && JAC == DVO_JAC_REFERENCE && TEX == 1) ? (NEED_H ? DVO_SOLVE_PIPE_GN : DVO_SOLVE_PIPE_SG) : 0;
+    constexpr int SMEM = (TEX ? LUT_BYTES : 0) + PIPE * THREADS * 32;
+    if (SMEM > 0) {
+        const cudaError_t e = optin_lut_smem<SolveArgs, solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX, WMODE, PIPE>>(c->cfg.device, SMEM);
         if (e != cudaSuccess) return e;
     }
-    solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX, WMODE><<<count, THREADS, TEX ? LUT_BYTES : 0, c->stream>>>(a);
+    solve_kernel<ARITH, JAC, NEED_H, THREADS, RES, TEX, WMODE, PIPE><<<count, THREADS, SMEM, c->stream>>>(a);
     return cudaGetLastError();
 }
 
