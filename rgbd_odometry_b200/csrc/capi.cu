@@ -145,15 +145,12 @@ int dvo_create(const dvo_config* cfg, dvo_ctx** out) {
     A(dalloc(&c->pose0, B * 12)); A(dalloc(&c->pose, B * 12)); A(dalloc(&c->info, B));
     if (cfg->trace_iters > 0) A(dalloc(&c->trace, B * g.L * cfg->trace_iters * DVO_TRACE_DOUBLES));
     A(dalloc(&c->energy, B * g.L * DVO_ENERGY_ITERS));
-    // hysteresis bitmaps that do not fit in shared memory live in a global scratch (one pair of bitmaps per CTA)
-    {
-        const int wd = (g.w[0] + 31) >> 5;
-        size_t wa = (size_t)(wd + 2) * (g.h[0] + 2), wt = (size_t)(wd << 5) * (((g.h[0] + 31) >> 5) | 1);
-        const size_t words = 2 * (wa > wt ? wa : wt);
-        if (words * 4 + 8192 > c->smem_optin) { c->bitmap_scratch_words = words; A(dalloc(&c->bitmap_scratch, words * B * 2)); }
-    }
+    // candidate / edge bitmaps: sobel_nms_kernel -> canny_kernel (which keeps working in them when they do not fit in shared memory)
+    canny_scratch_layout(g, c->bm_off, c->bm_words, &c->bitmap_scratch_words);
+    A(dalloc(&c->bitmap_scratch, c->bitmap_scratch_words * B * 2));
     if (rc != DVO_OK) { dvo_destroy(c); return rc; }
     CREATE_CUDA(cudaMemsetAsync(c->npts, 0, sizeof(int) * B * g.L, c->stream));
+    CREATE_CUDA(cudaMemsetAsync(c->bitmap_scratch, 0, sizeof(uint32_t) * c->bitmap_scratch_words * B * 2, c->stream));   // the bitmaps' zero borders are never written
     CREATE_CUDA(cudaMemsetAsync(c->nedge, 0, sizeof(unsigned) * 2 * B * g.L, c->stream));
     CREATE_CUDA(cudaMemsetAsync(c->maxd2, 0, sizeof(unsigned) * B * g.L, c->stream));
     CREATE_CUDA(cudaMemsetAsync(c->info, 0, sizeof(dvo_pair_info) * B, c->stream));

@@ -93,8 +93,10 @@ struct dvo_ctx {
     dvo_pair_info* info;     // [Bmax]
     double* trace;           // [Bmax][L][trace_iters][56] or null
     float* energy;           // [Bmax][L][DVO_ENERGY_ITERS] ||eps|| of every executed iteration of the last solve
-    uint32_t* bitmap_scratch;    // hysteresis bitmaps for images too large for shared memory, or null
+    uint32_t* bitmap_scratch;    // candidate / edge bitmaps of every (frame, slot, level): written by sobel_nms_kernel, consumed by canny_kernel
     size_t bitmap_scratch_words; // per slot and frame (the scratch holds 2 x Bmax of them: reference and now CTAs run in one launch)
+    long long bm_off[DVO_MAX_LEVELS];   // level region inside a (slot, frame) image of the scratch, in words
+    int bm_words[DVO_MAX_LEVELS];       // words per bitmap at the level (the region holds two)
     size_t canny_smem_optin;     // largest dynamic shared-memory opt-in made for canny_kernel so far
 
     // device staging of dvo_set_frames_raw with host buffers (allocated on first use)
@@ -124,6 +126,7 @@ void dvo_set_error(const char* fmt, ...);
 // ---- stage launchers (each defined next to its kernels) ----
 int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask);
 int launch_canny(dvo_ctx* c, int first, int count, int frames_mask);
+void canny_scratch_layout(const PyrGeom& g, long long* bm_off, int* bm_words, size_t* words_per_image);
 int launch_edt_rows(dvo_ctx* c, int first, int count);
 int launch_normgrad(dvo_ctx* c, int first, int count);
 int launch_pack(dvo_ctx* c, int first, int count);

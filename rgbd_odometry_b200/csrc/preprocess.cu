@@ -121,7 +121,6 @@ struct CannyArgs {
     uint32_t* gscratch;    // null -> shared memory bitmaps
     long long gscratch_stride;
     int first;
-    int low, high;         // squared thresholds (10000, 22500)
     int bm_words;          // words per bitmap region
     const unsigned char* active;   // optional per-slot mask
 };
@@ -150,6 +149,232 @@ __device__ __forceinline__ void row_sums(const uint8_t* __restrict__ grow, int w
     if (lane == 31) r = (x + 1 < w) ? (int)grow[x + 1] : v;
     if (x + 1 >= w) r = v;
     hs = r - l; hb = l + 2 * v + r;
+}
+
+// =====================================================================================================
+// Canny phase 1: Sobel + non-maximum suppression + double threshold, every pyramid level and both frames in ONE launch.
+// Output: the candidate bitmap (m > low, local maximum along the gradient) and the strong bitmap (candidate and m > high) of
+// every image, in the padded layout canny_kernel works on (word (y + 1) * pitch + wx + 1), in the bitmap scratch.
+//
+// Warp task = (image, 128-column chunk, NMS_ROWS-row strip).  A lane owns FOUR adjacent columns (one aligned 32-bit load per
+// row), so three of the four horizontal neighbours of a pixel are already in the lane's registers and a row costs 4 shuffles
+// instead of 16; the chunk's two outside columns are carried by lanes 0 / 31 as one extra (halo) column each, so chunks are
+// word aligned and the bitmap words are plain stores.  The arithmetic is fp32 on purpose: every value (gray <= 255, Sobel
+// sums <= 1020, squared magnitude <= 2 080 800, tan(22.5) products < 2^24) is an integer that fp32 represents exactly, so
+// the result is bit-identical to OpenCV's integer code, but adds / multiplies run on the FMA pipe and |x| is a free operand
+// modifier -- on sm_100 the integer ALU pipe (half rate) was the limiter of the integer version (ncu: 70 % ALU pipe).
+//   OpenCV:  horizontal  <=>  |dy| * 2^15 <  |dx| * 13573            <=>  |dy| < |dx| * (13573 / 2^15)
+//            vertical    <=>  |dy| * 2^15 >  |dx| * (13573 + 2^16)   <=>  |dy| - 2 |dx| > |dx| * (13573 / 2^15)
+//   (13573 / 2^15 is a dyadic rational: the products are exact.)  "m >= nb" on integers is "m > nb - 0.5".
+// =====================================================================================================
+#ifndef DVO_NMS_L2_AHEAD
+#define DVO_NMS_L2_AHEAD 4           // rows prefetched into L2 ahead of the register prefetch (0 = off)
+#endif
+#ifndef DVO_NMS_MIN_BLOCKS
+#define DVO_NMS_MIN_BLOCKS 2
+#endif
+#ifndef DVO_NMS_ROWS
+#define DVO_NMS_ROWS 48
+#endif
+#ifndef DVO_NMS_WARPS
+#define DVO_NMS_WARPS 8
+#endif
+constexpr int NMS_ROWS = DVO_NMS_ROWS, NMS_WARPS = DVO_NMS_WARPS;
+struct NmsArgs {
+    const uint8_t* gray[2];
+    uint32_t* scratch;                 // bitmap scratch: [slot][frame] regions of slot_stride / frame_stride words
+    long long slot_stride, frame_stride;
+    long long off[DVO_MAX_LEVELS];     // gray: level offset
+    long long bm_off[DVO_MAX_LEVELS];  // scratch: level offset inside a (slot, frame) region
+    int w[DVO_MAX_LEVELS], h[DVO_MAX_LEVELS], P[DVO_MAX_LEVELS], bm_words[DVO_MAX_LEVELS];
+    int chunks[DVO_MAX_LEVELS], strips[DVO_MAX_LEVELS], task_end[DVO_MAX_LEVELS];   // warp tasks of levels 0..l
+    int L, first, count, frame0;
+    float low, high;                   // squared thresholds (10000, 22500)
+    const unsigned char* active;
+};
+struct NmsSums { float s[4], b[4], sH, bH; };     // horizontal Sobel sums of one gray row: s = g(x+1) - g(x-1), b = g(x-1) + 2 g(x) + g(x+1); H = halo column
+struct NmsMags { float m[4], L, R; };             // squared gradient magnitudes of one row: own four columns, left and right neighbour
+struct NmsGrad { float dx[4], dy[4]; };
+
+template <bool VEC>       // VEC: width a multiple of 4 and 4-byte aligned rows -> one 32-bit load per lane and row
+__global__ void __launch_bounds__(NMS_WARPS * 32, DVO_NMS_MIN_BLOCKS) sobel_nms_kernel(NmsArgs a) {
+    const int lane = threadIdx.x & 31;
+    int task = blockIdx.x * NMS_WARPS + (threadIdx.x >> 5);
+    int l = 0;
+    while (l < a.L && task >= a.task_end[l]) ++l;
+    if (l >= a.L) return;
+    if (l) task -= a.task_end[l - 1];
+    const int chunks = a.chunks[l], strips = a.strips[l];
+    const int chunk = task % chunks, t2 = task / chunks, strip = t2 % strips, img = t2 / strips;
+    const int second = (img >= a.count) ? 1 : 0;
+    const int frame = second ? DVO_FRAME_NOW : a.frame0;
+    const int b = a.first + img - second * a.count;
+    if (a.active && !a.active[b]) return;
+    const int w = a.w[l], h = a.h[l];
+    const int wd = (w + 31) >> 5, pitch = wd + 2;
+    const uint8_t* __restrict__ g = a.gray[frame] + a.off[l] + (long long)b * a.P[l];
+    uint32_t* Cb = a.scratch + (long long)b * a.slot_stride + (long long)frame * a.frame_stride + a.bm_off[l];
+    const int bmw = a.bm_words[l];
+    const int c0 = chunk << 7, xb = c0 + (lane << 2);
+    const int y0 = strip * NMS_ROWS, y1 = min(h, y0 + NMS_ROWS);
+    const bool first_lane = (lane == 0), last_lane = (lane == 31);
+    const bool halo_valid = first_lane ? (c0 > 0) : (last_lane && c0 + 128 < w);        // the halo column lies inside the image
+    const bool self_left = (xb == 0), self_right = (xb + 4 >= w);                       // BORDER_REPLICATE at the image border
+    const int hx0 = first_lane ? c0 - 2 : c0 + 128;                                      // the two halo bytes: columns hx0, hx0 + 1
+    const uint32_t sel_near = 0x7440u + (first_lane ? 1u : 0u), sel_far = 0x7440u + (first_lane ? 0u : 1u);
+    const float lowt = (xb < w) ? a.low : 3.0e38f, high = a.high;
+    const float K = 13573.0f / 32768.0f;
+
+    // raw gray row r (clamped to the image): the lane's four bytes + the two halo bytes
+    const bool in_image = (xb < w);
+    const uint8_t* __restrict__ gx = g + (in_image ? xb : 0);
+    const uint8_t* __restrict__ gh = g + (halo_valid ? hx0 : 0);
+    const unsigned roff_max = (unsigned)((h - 1) * w);
+    auto load_row = [&](unsigned roff, uint32_t& wv, uint32_t& hv) {      // roff = clamped row * w
+        if (VEC) {
+            wv = in_image ? *reinterpret_cast<const uint32_t*>(gx + roff) : 0u;
+            hv = halo_valid ? (uint32_t)*reinterpret_cast<const uint16_t*>(gh + roff) : 0u;
+        } else {
+            const uint8_t* __restrict__ row = g + roff;
+            wv = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) wv |= (uint32_t)row[min(xb + j, w - 1)] << (8 * j);
+            hv = halo_valid ? ((uint32_t)row[hx0] | ((uint32_t)row[min(hx0 + 1, w - 1)] << 8)) : 0u;
+        }
+    };
+    auto byte_f = [](uint32_t wv, uint32_t sel) { return __uint_as_float(__byte_perm(wv, 0x4B000000u, sel)) - 8388608.0f; };
+    auto sums = [&](uint32_t wv, uint32_t hv, NmsSums& S) {
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = byte_f(wv, 0x7440u + j);
+        const float hn = byte_f(hv, sel_near), hf = byte_f(hv, sel_far);
+        float lft = __shfl_up_sync(0xffffffffu, v[3], 1), rgt = __shfl_down_sync(0xffffffffu, v[0], 1);
+        if (first_lane) lft = hn;
+        if (last_lane) rgt = hn;
+        if (self_left) lft = v[0];
+        if (self_right) rgt = v[3];
+        S.s[0] = v[1] - lft;  S.s[1] = v[2] - v[0]; S.s[2] = v[3] - v[1]; S.s[3] = rgt - v[2];
+        S.b[0] = fmaf(2.0f, v[0], lft) + v[1];  S.b[1] = fmaf(2.0f, v[1], v[0]) + v[2];
+        S.b[2] = fmaf(2.0f, v[2], v[1]) + v[3]; S.b[3] = fmaf(2.0f, v[3], v[2]) + rgt;
+        const float gm1 = first_lane ? hf : v[3], gp1 = first_lane ? v[0] : hf;          // halo column's left / right neighbour
+        S.sH = gp1 - gm1; S.bH = fmaf(2.0f, hn, gm1) + gp1;
+    };
+    // gradient and squared magnitude of an image row from the sums of the gray rows above (A), on (B) and below it (Cs); a row
+    // outside the image (inside == false, warp-uniform) has magnitude zero
+    auto grad_mag = [&](bool inside, const NmsSums& A, const NmsSums& B, const NmsSums& Cs, NmsGrad& G, NmsMags& M) {
+        float mH;
+        if (inside) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                G.dx[j] = fmaf(2.0f, B.s[j], A.s[j]) + Cs.s[j]; G.dy[j] = Cs.b[j] - A.b[j];
+                M.m[j] = fmaf(G.dx[j], G.dx[j], G.dy[j] * G.dy[j]);
+            }
+            const float dxH = fmaf(2.0f, B.sH, A.sH) + Cs.sH, dyH = Cs.bH - A.bH;
+            mH = halo_valid ? fmaf(dxH, dxH, dyH * dyH) : 0.0f;
+            if (!VEC) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (xb + j >= w) M.m[j] = 0.0f;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { G.dx[j] = 0.0f; G.dy[j] = 0.0f; M.m[j] = 0.0f; }
+            mH = 0.0f;
+        }
+        M.L = __shfl_up_sync(0xffffffffu, M.m[3], 1); M.R = __shfl_down_sync(0xffffffffu, M.m[0], 1);
+        if (first_lane) M.L = mH;
+        if (last_lane) M.R = mH;
+        if (self_right) M.R = 0.0f;
+    };
+
+    uint32_t wv, hv;
+    NmsSums S0, S1, S2;
+    NmsMags M0, M1, M2;
+    NmsGrad G0, G1;
+    auto row_off = [&](int r) { return min((unsigned)max(r, 0) * (unsigned)w, roff_max); };
+    load_row(row_off(y0 - 2), wv, hv); sums(wv, hv, S0);
+    load_row(row_off(y0 - 1), wv, hv); sums(wv, hv, S1);
+    load_row(row_off(y0), wv, hv);     sums(wv, hv, S2);
+    grad_mag(y0 > 0, S0, S1, S2, G0, M0);                                               // magnitude row y0 - 1
+    load_row(row_off(y0 + 1), wv, hv); sums(wv, hv, S0);                                 // S0 <- gray row y0 + 1
+    grad_mag(true, S1, S2, S0, G0, M1);                                                  // magnitude row y0, its gradient in G0
+    uint32_t wvn, hvn;
+    load_row(row_off(y0 + 2), wvn, hvn);                                                 // one row ahead in registers ...
+    unsigned roff_next = row_off(y0 + 3);
+    unsigned roff_l2 = row_off(y0 + 3 + DVO_NMS_L2_AHEAD);                               // ... and DVO_NMS_L2_AHEAD more rows ahead into L2
+
+    const int widx = (c0 >> 5) + (lane >> 3);
+    const bool writer = ((lane & 7) == 0) && widx < wd;
+    uint32_t* Cp = Cb + (long long)(y0 + 1) * pitch + 1 + widx;
+    const int sh = (lane & 3) << 2;
+
+    // non-maximum suppression + thresholds of one row (magnitude rows P above, C on, N below; Gc = gradient on the row) -> bitmap words
+    auto nms_row = [&](const NmsMags& P, const NmsMags& C, const NmsMags& N, const NmsGrad& Gc) {
+        float crm[4], ncm[4];                       // "m >= nb" on integers is "m > nb - 0.5"
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { crm[j] = ((j < 3) ? C.m[j < 3 ? j + 1 : 3] : C.R) - 0.5f; ncm[j] = N.m[j] - 0.5f; }
+        uint32_t bits = 0u;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float m = C.m[j];
+            const float cl = j ? C.m[j > 0 ? j - 1 : 0] : C.L;
+            const float pl = j ? P.m[j > 0 ? j - 1 : 0] : P.L, pr = (j < 3) ? P.m[j < 3 ? j + 1 : 3] : P.R;
+            const float nl = j ? N.m[j > 0 ? j - 1 : 0] : N.L, nr = (j < 3) ? N.m[j < 3 ? j + 1 : 3] : N.R;
+            const float adx = fabsf(Gc.dx[j]), ady = fabsf(Gc.dy[j]);
+            const float t = adx * K, u = fmaf(adx, -2.0f, ady);
+            const bool horiz = ady < t, vert = u > t;
+            const bool neg = Gc.dx[j] * Gc.dy[j] < 0.0f;                                 // only read in the diagonal case, where dx, dy != 0
+            const float da = neg ? pr : pl, db = neg ? nl : nr;
+            const float na = horiz ? cl : (vert ? P.m[j] : da);
+            const float nb = horiz ? crm[j] : (vert ? ncm[j] : db);
+            const bool cand = (m > na) && (m > nb) && (m > lowt);
+            const bool strong = cand && (m > high);
+            bits |= (cand ? (1u << j) : 0u) | (strong ? (0x10000u << j) : 0u);
+        }
+        // candidate nibbles of a lane quad -> low half-word, strong nibbles -> high half-word; two quads make the 32-bit words
+        bits <<= sh;
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+        bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+        const uint32_t hi = __shfl_down_sync(0xffffffffu, bits, 4);
+        if (writer) {
+            Cp[0] = __byte_perm(bits, hi, 0x5410);
+            Cp[bmw] = __byte_perm(bits, hi, 0x7632);
+        }
+        Cp += pitch;
+    };
+    // One row: roles are passed by reference so that the caller rotates names, not registers.  A, B = sums of gray rows y, y+1;
+    // Cs receives row y+2.  P, C = magnitude rows y-1, y; N receives y+1.  Gc = gradient at row y, Gn receives row y+1.
+    auto row_step = [&](const NmsSums& A, const NmsSums& B, NmsSums& Cs, const NmsMags& P, const NmsMags& C, NmsMags& N,
+                        const NmsGrad& Gc, NmsGrad& Gn) {
+        wv = wvn; hv = hvn;
+        load_row(roff_next, wvn, hvn); roff_next = min(roff_next + (unsigned)w, roff_max);   // gray row y + 3
+        if (DVO_NMS_L2_AHEAD > 0) {
+            if (in_image) asm volatile("prefetch.global.L2 [%0];" :: "l"(gx + roff_l2));
+            roff_l2 = min(roff_l2 + (unsigned)w, roff_max);
+        }
+        sums(wv, hv, Cs);                                                                // gray row y + 2
+        grad_mag(true, A, B, Cs, Gn, N);
+        nms_row(P, C, N, Gc);
+    };
+    // rows whose lower neighbour row lies inside the image; the image's last row is done after the loops
+    const int yend = (y1 == h) ? y1 - 1 : y1;
+    // roles on entry: sums A = row y0 (S2), B = row y0 + 1 (S0), free = S1; magnitudes P = M0, C = M1, free = M2
+    int y = y0;
+    for (; y + 6 <= yend; y += 6) {               // six steps = a whole number of rotations of the sums / magnitudes (3) and of the gradient pair (2)
+        row_step(S2, S0, S1, M0, M1, M2, G0, G1);
+        row_step(S0, S1, S2, M1, M2, M0, G1, G0);
+        row_step(S1, S2, S0, M2, M0, M1, G0, G1);
+        row_step(S2, S0, S1, M0, M1, M2, G1, G0);
+        row_step(S0, S1, S2, M1, M2, M0, G0, G1);
+        row_step(S1, S2, S0, M2, M0, M1, G1, G0);
+    }
+    for (; y < yend; ++y) {                        // remainder: plain step, roles rotated by moves
+        row_step(S2, S0, S1, M0, M1, M2, G0, G1);
+        S2 = S0; S0 = S1; M0 = M1; M1 = M2; G0 = G1;
+    }
+    if (y1 == h) {                                 // last image row: the magnitude row below it is the zero padding
+        grad_mag(false, S2, S0, S1, G1, M2);
+        nms_row(M0, M1, M2, G0);
+    }
 }
 
 constexpr int CANNY_MAX_WARPS = 24;
@@ -185,127 +410,25 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     const int nwords = a.bm_words;
     // bitmaps: shared memory (LDS/STS/ATOMS) or, for images too large for it, a global scratch
     // (the global scratch is indexed by SLOT, not by block: launches on different streams own disjoint slot ranges)
-    uint32_t* C = GLOBAL_BITMAPS ? a.gscratch + (long long)b * a.gscratch_stride + (long long)frame * a.gscratch_frame_stride : smem_u32;
+    uint32_t* C = GLOBAL_BITMAPS ? a.gscratch + (long long)b * a.gscratch_stride + (long long)frame * a.gscratch_frame_stride : smem_u32;   // gscratch already points at this level's region
     uint32_t* E = C + nwords;
-    const uint8_t* __restrict__ g = a.gray[frame] + (long long)b * a.P;
 
-    for (int i = tid; i < 2 * nwords; i += T) C[i] = 0u;
-    if (tid == 0) { s_cnt = 0u; s_base = 0; }
-    __syncthreads();
-
-    // ------------------------------------------------------------------ phase 1: Sobel + NMS
-    // Warp task = (30-column chunk, row strip).  Lane j holds column 30*chunk + j - 1, so lanes 1..30 produce output
-    // and lanes 0 / 31 are halo columns (they load one extra gray value each); warps never synchronise with each
-    // other.  Rows are swept top to bottom: one (prefetched) byte load per pixel, separable Sobel row sums, the 3x3
-    // magnitude neighbourhood in registers, horizontal neighbours by shuffle.  Ballots are merged into the 32-bit
-    // aligned bitmap words with shared-memory atomicOr.
-    {
-        const int TG22 = 13573;   // (int)(0.4142135623730950488016887242097 * (1 << 15) + 0.5)
-        const int nchunk = (w + 29) / 30;
-        const int nwarps = T >> 5;
-        const int S = max(1, nwarps / nchunk);
-        const int R = (h + S - 1) / S;
-        const bool halo = (lane == 0 || lane == 31);
-        for (int task = warp; task < nchunk * S; task += nwarps) {
-            const int k = task % nchunk, st = task / nchunk;
-            const int y0 = st * R, y1 = min(h, y0 + R);
-            if (y0 >= y1) continue;                                   // warp-uniform
-            const int x = 30 * k + lane - 1;
-            const bool incol = (x >= 0 && x < w);
-            const int xc = min(max(x, 0), w - 1);                     // BORDER_REPLICATE
-            const int de = min(max(lane == 0 ? x - 1 : x + 1, 0), w - 1) - xc;
-            const int low = a.low, high = a.high;
-            // row pointer that follows r = clamp(row, 0, h-1) incrementally
-            const uint8_t* __restrict__ pr = g + min(max(y0 - 2, 0), h - 1) * w + xc;
-            int rr = y0 - 2;
-            auto loadrow = [&](int& v, int& ve) {                     // loads row rr (clamped), then advances rr
-                v = pr[0]; ve = halo ? (int)pr[de] : 0;
-                if (rr >= 0 && rr < h - 1) pr += w;
-                ++rr;
-            };
-            auto sums = [&](int v, int ve, int& hs, int& hb) {
-                int l = __shfl_up_sync(0xffffffffu, v, 1), r = __shfl_down_sync(0xffffffffu, v, 1);
-                if (lane == 0) l = ve;
-                if (lane == 31) r = ve;
-                hs = r - l; hb = l + 2 * v + r;
-            };
-            int hsA, hbA, hsB, hbB, hsC, hbC, v, ve, vn, ven;
-            int mPL, mPC, mPR, mCL, mCC, mCR, dxC, dyC;
-            loadrow(v, ve); sums(v, ve, hsA, hbA);                    // gray row y0-2
-            loadrow(v, ve); sums(v, ve, hsB, hbB);                    // y0-1
-            loadrow(v, ve); sums(v, ve, hsC, hbC);                    // y0
-            {   // magnitude row y0-1 (zero outside the image)
-                const int dx = hsA + 2 * hsB + hsC, dy = hbC - hbA;
-                mPC = (incol && y0 - 1 >= 0) ? dx * dx + dy * dy : 0;
-                mPL = __shfl_up_sync(0xffffffffu, mPC, 1); mPR = __shfl_down_sync(0xffffffffu, mPC, 1);
-            }
-            hsA = hsB; hbA = hbB; hsB = hsC; hbB = hbC;
-            loadrow(v, ve); sums(v, ve, hsC, hbC);                    // y0+1
-            {   // magnitude row y0
-                dxC = hsA + 2 * hsB + hsC; dyC = hbC - hbA;
-                mCC = incol ? dxC * dxC + dyC * dyC : 0;
-                mCL = __shfl_up_sync(0xffffffffu, mCC, 1); mCR = __shfl_down_sync(0xffffffffu, mCC, 1);
-            }
-            loadrow(vn, ven);                                         // y0+2, prefetched one row ahead
-            const int c0 = 30 * k, sh = c0 & 31;
-            uint32_t* Bm = (lane == 0 ? C : E) + (y0 + 1) * pitch + (c0 >> 5) + 1;   // lane 0 merges candidates, lane 1 the strong set
-            // The row step is branch-free up to the bitmap merge: every select below is a predicated move, so the warp stays
-            // converged for the shuffles and ballots (the nested ifs of the first version cost a third of the loop in
-            // BSSY / BSYNC / BRA.DIV bookkeeping).  halo lanes and out-of-image columns carry m == 0 and never pass m > low.
-            const int lowt = halo ? 0x7fffffff : low;
-            const bool writer = lane < 2;
-            // One row step.  Arguments are passed by role so that the caller can rotate the roles instead of the registers:
-            // (sA, bA), (sB, bB) = horizontal Sobel sums of gray rows y, y+1 -> (sC, bC) receives row y+2; the magnitude rows
-            // P / C hold y-1, y -> N receives y+1.  The step is branch-free up to the bitmap merge: every select is a
-            // predicated move, so the warp stays converged for the shuffles and ballots (the nested ifs of the first version
-            // cost a third of the loop in BSSY / BSYNC / BRA.DIV bookkeeping).  Halo lanes never pass m > lowt.
-            auto row_step = [&](int y, int sA, int bA, int sB, int bB, int& sC, int& bC, int pL, int pC, int pR, int cL, int cC, int cR,
-                                int& nL, int& nC, int& nR, int dx0, int dy0, int& dx1, int& dy1) {
-                v = vn; ve = ven;
-                loadrow(vn, ven);                                     // gray row y+3
-                sums(v, ve, sC, bC);                                  // gray row y+2
-                dx1 = sA + 2 * sB + sC; dy1 = bC - bA;                // gradient at row y+1
-                nC = (incol && y + 1 < h) ? dx1 * dx1 + dy1 * dy1 : 0;
-                nL = __shfl_up_sync(0xffffffffu, nC, 1); nR = __shfl_down_sync(0xffffffffu, nC, 1);
-                const int m = cC;
-                const int ax = abs(dx0), ays = abs(dy0) << 15;
-                const int tg22x = ax * TG22;
-                const bool horiz = ays < tg22x, vert = ays > tg22x + (ax << 16);
-                const bool neg = (dx0 ^ dy0) < 0;
-                const int da = neg ? pR : pL, db = neg ? nL : nR;                     // the two diagonal neighbours
-                const int na = horiz ? cL : (vert ? pC : da);
-                const int nb = horiz ? cR : (vert ? nC : db);
-                // horizontal / vertical: m > na && m >= nb; diagonal: m > na && m > nb
-                const bool keep = (m > na) && (m + ((horiz || vert) ? 1 : 0) > nb);
-                const bool cand = keep && (m > lowt);
-                const bool strong = cand && (m > high);
-                const uint32_t cb = __ballot_sync(0xffffffffu, cand);
-                const uint32_t sb = __ballot_sync(0xffffffffu, strong);
-                const uint32_t bits = ((lane == 0 ? cb : sb) >> 1) & 0x3fffffffu;
-                if (writer && bits) {
-                    atomicOr(Bm, bits << sh);
-                    const uint32_t hi = (sh > 2) ? bits >> (32 - sh) : 0u;
-                    if (hi) atomicOr(Bm + 1, hi);
-                }
-                Bm += pitch;
-            };
-            // roles on entry: sums A = row y0, B = row y0+1 (hsB / hsC of the prologue), magnitudes P = y0-1, C = y0
-            int s0 = hsB, b0 = hbB, s1 = hsC, b1 = hbC, s2 = 0, b2 = 0;
-            int mNL = 0, mNC = 0, mNR = 0, dxN = 0, dyN = 0;
-            int y = y0;
-            for (; y + 3 <= y1; y += 3) {             // three steps = one full rotation of the sums and of the magnitude rows
-                row_step(y, s0, b0, s1, b1, s2, b2, mPL, mPC, mPR, mCL, mCC, mCR, mNL, mNC, mNR, dxC, dyC, dxN, dyN);
-                row_step(y + 1, s1, b1, s2, b2, s0, b0, mCL, mCC, mCR, mNL, mNC, mNR, mPL, mPC, mPR, dxN, dyN, dxC, dyC);
-                row_step(y + 2, s2, b2, s0, b0, s1, b1, mNL, mNC, mNR, mPL, mPC, mPR, mCL, mCC, mCR, dxC, dyC, dxN, dyN);
-                dxC = dxN; dyC = dyN;                 // the gradient pair has period two: one move per three rows
-            }
-            for (; y < y1; ++y) {                     // remainder: plain step, roles rotated by moves
-                row_step(y, s0, b0, s1, b1, s2, b2, mPL, mPC, mPR, mCL, mCC, mCR, mNL, mNC, mNR, dxC, dyC, dxN, dyN);
-                s0 = s1; b0 = b1; s1 = s2; b1 = b2;
-                mPL = mCL; mPC = mCC; mPR = mCR; mCL = mNL; mCC = mNC; mCR = mNR; dxC = dxN; dyC = dyN;
-            }
+    // phase 1 (Sobel + NMS) ran in sobel_nms_kernel: it left the candidate and the strong bitmap of this image in the scratch.
+    if (GLOBAL_BITMAPS) {      // bitmaps stay where they are; the transposed layout of the previous pass may have touched the border
+        for (int i = tid; i < pitch; i += T) { C[i] = 0u; E[i] = 0u; C[(h + 1) * pitch + i] = 0u; E[(h + 1) * pitch + i] = 0u; }
+        for (int y = tid; y < h; y += T) {
+            C[(y + 1) * pitch] = 0u; E[(y + 1) * pitch] = 0u; C[(y + 1) * pitch + wd + 1] = 0u; E[(y + 1) * pitch + wd + 1] = 0u;
+        }
+    } else {
+        const uint32_t* __restrict__ src = a.gscratch + (long long)b * a.gscratch_stride + (long long)frame * a.gscratch_frame_stride;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0 && (nwords & 1) == 0) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src); uint4* d4 = reinterpret_cast<uint4*>(C);
+            for (int i = tid; i < (nwords >> 1); i += T) d4[i] = s4[i];
+        } else {
+            for (int i = tid; i < 2 * nwords; i += T) C[i] = src[i];
         }
     }
+    if (tid == 0) { s_cnt = 0u; s_base = 0; }
     __syncthreads();
 
 #if DVO_CANNY_STOP_AFTER == 1
@@ -533,21 +656,51 @@ static int canny_bitmap_words(int w, int h) {
     return a > t ? a : t;
 }
 
+// Bitmap scratch geometry (context creation): per (slot, frame) one region per level holding the candidate and the edge bitmap.
+void canny_scratch_layout(const PyrGeom& g, long long* bm_off, int* bm_words, size_t* words_per_image) {
+    long long o = 0;
+    for (int l = 0; l < g.L; ++l) { bm_off[l] = o; bm_words[l] = canny_bitmap_words(g.w[l], g.h[l]); o += 2LL * ((bm_words[l] + 3) & ~3); }
+    *words_per_image = (size_t)o;
+}
+
 int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
     const PyrGeom& g = c->geom;
     if (!(frames_mask & 3)) return DVO_OK;
     if ((frames_mask & 1) && !c->depth[0]) { dvo_set_error("canny: reference depth missing"); return DVO_ERR_STATE; }
+    if (!c->bitmap_scratch) { dvo_set_error("canny: bitmap scratch missing"); return DVO_ERR_STATE; }
+    const bool both = (frames_mask & 3) == 3;
+    const int frame0 = (frames_mask & 1) ? DVO_FRAME_REF : DVO_FRAME_NOW;
+    const long long slot_stride = (long long)c->bitmap_scratch_words, frame_stride = slot_stride * g.Bmax;
+    {   // phase 1 of every level and frame: one launch
+        NmsArgs n;
+        n.gray[0] = c->gray[0]; n.gray[1] = c->gray[1];
+        n.scratch = c->bitmap_scratch; n.slot_stride = slot_stride; n.frame_stride = frame_stride;
+        long long tasks = 0;
+        for (int l = 0; l < g.L; ++l) {
+            n.off[l] = g.off[l]; n.bm_off[l] = c->bm_off[l]; n.w[l] = g.w[l]; n.h[l] = g.h[l]; n.P[l] = g.P[l]; n.bm_words[l] = c->bm_words[l];
+            n.chunks[l] = (g.w[l] + 127) >> 7; n.strips[l] = (g.h[l] + NMS_ROWS - 1) / NMS_ROWS;
+            tasks += (long long)n.chunks[l] * n.strips[l] * count * (both ? 2 : 1);
+            if (tasks > 0x7fffffff - NMS_WARPS) { dvo_set_error("canny: too many tiles in one launch"); return DVO_ERR_ARG; }
+            n.task_end[l] = (int)tasks;
+        }
+        n.L = g.L; n.first = first; n.count = both ? count : 0x7fffffff; n.frame0 = frame0;
+        n.low = 10000.0f; n.high = 22500.0f; n.active = c->active;
+        bool vec = true;          // every level: width a multiple of 4, rows 4-byte aligned (level offsets and image sizes are then multiples of 4 too)
+        for (int l = 0; l < g.L; ++l) vec = vec && (g.w[l] % 4 == 0) && (g.off[l] % 4 == 0) && (g.P[l] % 4 == 0);
+        const unsigned grid = (unsigned)((tasks + NMS_WARPS - 1) / NMS_WARPS);
+        if (vec) sobel_nms_kernel<true><<<grid, NMS_WARPS * 32, 0, c->stream>>>(n);
+        else sobel_nms_kernel<false><<<grid, NMS_WARPS * 32, 0, c->stream>>>(n);
+        c->launches++;
+    }
     for (int l = 0; l < g.L; ++l) {
-        const int words = canny_bitmap_words(g.w[l], g.h[l]);
+        const int words = c->bm_words[l];
         const size_t smem = (size_t)2 * words * sizeof(uint32_t);
         const bool use_global = smem + 8192 > c->smem_optin;
-        if (use_global && (!c->bitmap_scratch || (size_t)2 * words > c->bitmap_scratch_words)) {
-            dvo_set_error("canny: bitmap scratch missing for %dx%d", g.w[l], g.h[l]); return DVO_ERR_STATE;
-        }
-        // warps = (30-column chunks) x (row strips), up to 24 warps per CTA (two CTAs per SM)
-        const int nchunk = (g.w[l] + 29) / 30;
-        int S = 24 / nchunk; if (S < 1) S = 1;
-        int warps = nchunk * S; if (warps > CANNY_MAX_WARPS) warps = CANNY_MAX_WARPS; if (warps < 4) warps = 4;
+        // hysteresis: thread <-> (word column, row strip), up to 24 warps per CTA (two CTAs per SM); the column pass wants a thread per column
+        const int wdl = (g.w[l] + 31) >> 5;
+        int strips = (CANNY_MAX_WARPS * 32) / wdl; if (strips > g.h[l]) strips = g.h[l]; if (strips < 1) strips = 1;
+        int threads = wdl * strips; if (threads < g.w[l]) threads = g.w[l];
+        int warps = (threads + 31) / 32; if (warps > CANNY_MAX_WARPS) warps = CANNY_MAX_WARPS; if (warps < 4) warps = 4;
         const int T = warps * 32;
         CannyArgs a;
         for (int f = 0; f < 2; ++f) {
@@ -559,17 +712,16 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
         a.X = c->ptsX + g.off[l]; a.Y = c->ptsY + g.off[l]; a.Z = c->ptsZ + g.off[l]; a.pix = c->ptsPix + g.off[l];
         a.npts = c->npts + l;
         a.w = g.w[l]; a.h = g.h[l]; a.P = g.P[l]; a.L = g.L;
-        const bool both = (frames_mask & 3) == 3;
-        a.frame0 = (frames_mask & 1) ? DVO_FRAME_REF : DVO_FRAME_NOW;
+        a.frame0 = frame0;
         a.count = both ? count : 0x7fffffff;                                           // single frame: no block is "second"
         const float scaleFac = (float)ldexp(1.0, -l);                                  // src/SolveDVO.cpp:231
         a.tmpfx = (float)(1. / (double)(scaleFac * c->K.fx));                          // :232
         a.tmpfy = (float)(1. / (double)(scaleFac * c->K.fy));                          // :233
         a.tmpcx = scaleFac * c->K.cx; a.tmpcy = scaleFac * c->K.cy;                    // :234-235
-        a.gscratch = use_global ? c->bitmap_scratch : nullptr;
-        a.gscratch_stride = (long long)c->bitmap_scratch_words;
-        a.gscratch_frame_stride = (long long)c->bitmap_scratch_words * g.Bmax;
-        a.first = first; a.low = 10000; a.high = 22500; a.bm_words = words; a.active = c->active;
+        a.gscratch = c->bitmap_scratch + c->bm_off[l];                                 // this level's region of slot 0, reference frame
+        a.gscratch_stride = slot_stride;
+        a.gscratch_frame_stride = frame_stride;
+        a.first = first; a.bm_words = words; a.active = c->active;
         const int nblocks = both ? 2 * count : count;
         if (use_global) canny_kernel<true><<<nblocks, T, 0, c->stream>>>(a);
         else {
@@ -677,32 +829,22 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_kernel(EdtArgs a, const u
 // edge maps the loop length is the largest distance inside the 32-pixel segment (a dozen steps at 640x480), every
 // step is two conflict-free shared-memory loads and two min's for all 32 lanes -- no divergence, no stack.
 // Images with very few edge pixels (loop length ~ image width) are left to the bisection kernel below.
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) edt_rows_window_kernel(EdtArgs a, const unsigned* __restrict__ nedge) {
-    extern __shared__ int smem_i32[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = a.w;
-    const int row = blockIdx.x * WARPS + warp;
-    const int b = a.first + blockIdx.y;
-    if (row >= a.h) return;
-    const unsigned ne = nedge[(long long)b * a.L];
-    if (ne != 0u && (unsigned long long)ne * DVO_EDT_SPARSE_DIV < (unsigned long long)a.P) return;   // sparse image: other kernel
-    int32_t* out = a.d2 + (long long)b * a.P + (long long)row * w;
-    if (ne == 0u) {                                  // no edge pixel at all: d2 is the sentinel everywhere
-        for (int x = lane; x < w; x += 32) out[x] = DVO_EDT_INF;
-        if (lane == 0) atomicMax(&a.maxd2[(long long)b * a.L], (unsigned)DVO_EDT_INF);
-        return;
-    }
-    int* g2 = smem_i32 + (size_t)warp * (w + 2) + 1;  // g2[-1] and g2[w] are sentinels
-    const uint16_t* __restrict__ gr = a.gcol + (long long)b * a.P + (long long)row * w;
+constexpr int EDT16_G = 170, EDT16_PAD = 192, EDT16_BIG = 30000;
+#ifndef DVO_EDT_PACKED16
+#define DVO_EDT_PACKED16 1
+#endif
+// per-warp scratch of the window routines in ints: the 32-bit row (w + 2) or the two padded 16-bit copies
+__host__ __device__ inline int edt_window_scratch_ints(int w) { return DVO_EDT_PACKED16 ? (w + 2 * EDT16_PAD + 2) : (w + 2); }
+
+// expanding-window row routine of edt_rows_window_kernel for one warp; g2 = this warp's (w + 2)-int scratch + 1
+template <typename Emit>
+__device__ __forceinline__ void edt_row_window(const uint16_t* __restrict__ gr, int* g2, int w, int lane, Emit emit) {
     for (int x = lane; x < w; x += 32) { const int gv = gr[x]; g2[x] = gv * gv; }
     if (lane == 0) { g2[-1] = 0x3fffffff; g2[w] = 0x3fffffff; }
     __syncwarp();
-    int mx = 0;
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
         int best = (x < w) ? g2[x] : 0;
-        // while the whole 32-pixel segment +- k stays inside the row no index clamping is needed: 4 steps per exit test
         const int kint = min(x0, w - 32 - x0);
         const int* gc = g2 + min(x, w - 1);
         int k = 1, kk = 1;
@@ -719,8 +861,102 @@ __global__ void __launch_bounds__(WARPS * 32) edt_rows_window_kernel(EdtArgs a, 
                 kk += 2 * k + 1; ++k;
             }
         }
-        if (x < w) { out[x] = best; mx = max(mx, best); }
+        if (x < w) emit(x, best);
     }
+    __syncwarp();
+}
+
+// The same expanding window on PACKED 16-bit lanes: a lane owns two adjacent pixels and every step is one per-halfword
+// min and one per-halfword add-min (VIMNMX.U16x2 / VIADDMNMX.U16x2), i.e. two instructions for two pixels instead of two per
+// pixel.  The row lives in shared memory twice -- A[i] = (g2[2i], g2[2i+1]) and B[i] = (g2[2i+1], g2[2i+2]) -- so that the
+// pair at any offset is one aligned 32-bit load.  Column distances are clamped to EDT16_G before squaring and both copies
+// carry EDT16_PAD halfwords of EDT16_BIG on either side: every sum stays below 2^16 (g2 <= 28 900, k <= 173 + 3, BIG + k^2 <=
+// 60 976).  A result below EDT16_G^2 was produced by an unclamped candidate and is therefore the exact minimum; the routine
+// returns false if any pixel of the row reached EDT16_G^2, and the caller redoes that row with the 32-bit routine.
+// H = this warp's scratch as halfwords: copy A at H[0 ..), copy B at H[EDT16_PAD + w + EDT16_PAD ..); w is even.
+__device__ __forceinline__ void edt16_fill_pads(unsigned short* H, int w, int lane) {
+    const int n = w + 2 * EDT16_PAD;
+    for (int i = lane; i < EDT16_PAD; i += 32) { H[i] = EDT16_BIG; H[EDT16_PAD + w + i] = EDT16_BIG; H[n + i] = EDT16_BIG; H[n + EDT16_PAD + w + i] = EDT16_BIG; }
+    __syncwarp();
+}
+template <typename Emit2>
+__device__ __forceinline__ bool edt_row_window16(const uint16_t* __restrict__ gr, unsigned short* H, int w, int lane, Emit2 emit2) {
+    const int n = w + 2 * EDT16_PAD;                       // halfwords per copy (even)
+    uint32_t* A = reinterpret_cast<uint32_t*>(H);
+    uint32_t* B = reinterpret_cast<uint32_t*>(H + n);
+    const uint32_t* __restrict__ gr2 = reinterpret_cast<const uint32_t*>(gr);
+    for (int p = lane; 2 * p < w; p += 32) {
+        const uint32_t gv = gr2[p];
+        const uint32_t g0 = min(gv & 0xFFFFu, (uint32_t)EDT16_G), g1 = min(gv >> 16, (uint32_t)EDT16_G);
+        A[(EDT16_PAD >> 1) + p] = (g0 * g0) | ((g1 * g1) << 16);
+    }
+    __syncwarp();
+    for (int p = lane - 1; 2 * p < w; p += 32) {          // B[i] = (H[2i+1], H[2i+2]): from p = -1 (left pad | g2[0]) to the last pair (g2[w-1] | right pad)
+        const int i = (EDT16_PAD >> 1) + p;
+        B[i] = __byte_perm(A[i], A[i + 1], 0x5432);
+    }
+    __syncwarp();
+    bool exact = true;
+    for (int x0 = 0; x0 < w; x0 += 64) {
+        const int x = x0 + 2 * lane;
+        const int i0 = (EDT16_PAD + min(x, w - 2)) >> 1;
+        uint32_t best = (x < w) ? A[i0] : 0u;
+        const uint32_t* a = A + i0;
+        const uint32_t* b = B + i0;
+        int k = 1;
+        uint32_t kk = 0x00010001u;                         // k^2 in both halfwords
+        for (;;) {
+            const uint32_t bmax = max(best & 0xFFFFu, best >> 16);
+            if (__all_sync(0xffffffffu, (kk & 0xFFFFu) >= bmax)) break;
+            // offsets k .. k+3 with k odd: pairs at odd offsets come from copy B, even offsets from copy A
+            const int m = k >> 1;
+            const uint32_t c0 = __vminu2(b[m], b[-m - 1]), c1 = __vminu2(a[m + 1], a[-m - 1]);
+            const uint32_t c2 = __vminu2(b[m + 1], b[-m - 2]), c3 = __vminu2(a[m + 2], a[-m - 2]);
+            const uint32_t k1 = kk + (uint32_t)(2 * k + 1) * 0x00010001u, k2 = kk + (uint32_t)(4 * k + 4) * 0x00010001u, k3 = kk + (uint32_t)(6 * k + 9) * 0x00010001u;
+            best = __viaddmin_u16x2(c0, kk, best); best = __viaddmin_u16x2(c1, k1, best);
+            best = __viaddmin_u16x2(c2, k2, best); best = __viaddmin_u16x2(c3, k3, best);
+            kk += (uint32_t)(8 * k + 16) * 0x00010001u; k += 4;
+        }
+        if (x < w) {
+            emit2(x, best);
+            if (max(best & 0xFFFFu, best >> 16) >= (uint32_t)(EDT16_G * EDT16_G)) exact = false;
+        }
+    }
+    __syncwarp();
+    return __all_sync(0xffffffffu, exact);
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) edt_rows_window_kernel(EdtArgs a, const unsigned* __restrict__ nedge) {
+    extern __shared__ int smem_i32[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = a.w;
+    const int row = blockIdx.x * WARPS + warp;
+    const int b = a.first + blockIdx.y;
+    if (row >= a.h) return;
+    const unsigned ne = nedge[(long long)b * a.L];
+    if (ne != 0u && (unsigned long long)ne * DVO_EDT_SPARSE_DIV < (unsigned long long)a.P) return;   // sparse image: other kernel
+    int32_t* out = a.d2 + (long long)b * a.P + (long long)row * w;
+    if (ne == 0u) {                                  // no edge pixel at all: d2 is the sentinel everywhere
+        for (int x = lane; x < w; x += 32) out[x] = DVO_EDT_INF;
+        if (lane == 0) atomicMax(&a.maxd2[(long long)b * a.L], (unsigned)DVO_EDT_INF);
+        return;
+    }
+    int* scratch = smem_i32 + (size_t)warp * edt_window_scratch_ints(w);
+    const uint16_t* __restrict__ gr = a.gcol + (long long)b * a.P + (long long)row * w;
+    int mx = 0;
+    auto emit = [&](int x, int v) { out[x] = v; mx = max(mx, v); };
+    const bool packed16 = DVO_EDT_PACKED16 && (w % 2 == 0) && ((reinterpret_cast<uintptr_t>(gr) & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+    bool done = false;
+    if (packed16) {
+        edt16_fill_pads(reinterpret_cast<unsigned short*>(scratch), w, lane);
+        auto emit2 = [&](int x, uint32_t v2) {
+            *reinterpret_cast<int2*>(out + x) = make_int2((int)(v2 & 0xFFFFu), (int)(v2 >> 16));
+            mx = max(mx, (int)max(v2 & 0xFFFFu, v2 >> 16));
+        };
+        done = edt_row_window16(gr, reinterpret_cast<unsigned short*>(scratch), w, lane, emit2);
+    }
+    if (!done) edt_row_window(gr, scratch + 1, w, lane, emit);     // odd width, or a pixel further than EDT16_G from every edge
     mx = __reduce_max_sync(0xffffffffu, mx);
     if (lane == 0) atomicMax(&a.maxd2[(long long)b * a.L], (unsigned)mx);
 }
@@ -736,7 +972,7 @@ int launch_edt_rows(dvo_ctx* c, int first, int count) {
         const int w = g.w[l];
         dim3 grid((g.h[l] + WARPS - 1) / WARPS, count);
         {   // dense images: expanding-window kernel
-            const size_t smem = (size_t)WARPS * (w + 2) * sizeof(int);
+            const size_t smem = (size_t)WARPS * edt_window_scratch_ints(w) * sizeof(int);
             if (smem > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(edt_rows_window_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             edt_rows_window_kernel<WARPS><<<grid, WARPS * 32, smem, c->stream>>>(a, ne);
             c->launches++;
@@ -923,36 +1159,6 @@ int launch_pack(dvo_ctx* c, int first, int count) {
 
 struct EdtPackArgs { const uint16_t* gcol; int32_t* d2; uint2* tex8; unsigned* maxd2; int w, h, P, Pt, tw, th, L, first; };
 
-// expanding-window row routine of edt_rows_window_kernel for one warp; g2 = this warp's (w + 2)-int scratch + 1
-template <typename Emit>
-__device__ __forceinline__ void edt_row_window(const uint16_t* __restrict__ gr, int* g2, int w, int lane, Emit emit) {
-    for (int x = lane; x < w; x += 32) { const int gv = gr[x]; g2[x] = gv * gv; }
-    if (lane == 0) { g2[-1] = 0x3fffffff; g2[w] = 0x3fffffff; }
-    __syncwarp();
-    for (int x0 = 0; x0 < w; x0 += 32) {
-        const int x = x0 + lane;
-        int best = (x < w) ? g2[x] : 0;
-        const int kint = min(x0, w - 32 - x0);
-        const int* gc = g2 + min(x, w - 1);
-        int k = 1, kk = 1;
-        while (k < w) {
-            if (__all_sync(0xffffffffu, kk >= best)) break;
-            if (k + 3 <= kint) {
-                const int a0 = min(gc[-k], gc[k]), a1 = min(gc[-k - 1], gc[k + 1]), a2 = min(gc[-k - 2], gc[k + 2]), a3 = min(gc[-k - 3], gc[k + 3]);
-                const int k1 = kk + 2 * k + 1, k2 = kk + 4 * k + 4, k3 = kk + 6 * k + 9;
-                best = min(min(best, a0 + kk), min(a1 + k1, min(a2 + k2, a3 + k3)));
-                kk += 8 * k + 16; k += 4;
-            } else {
-                const int vl = g2[min(max(x - k, -1), w)], vr = g2[min(x + k, w)];
-                best = min(best, min(vl, vr) + kk);
-                kk += 2 * k + 1; ++k;
-            }
-        }
-        if (x < w) emit(x, best);
-    }
-    __syncwarp();
-}
-
 // bisection row routine of edt_rows_kernel for one warp; dv / gs / arg = this warp's scratch
 template <typename Emit>
 __device__ __forceinline__ void edt_row_bisect(const uint16_t* __restrict__ gr, int* dv, unsigned short* gs, unsigned short* arg, int w, int lane, Emit emit) {
@@ -1016,10 +1222,13 @@ __global__ void __launch_bounds__(WARPS * 32) edt_pack_kernel(EdtPackArgs a, con
     const int y0 = blockIdx.x * R;
     const int bp = (w + 1) & ~1;                                     // band pitch (u16), even
     unsigned short* band = reinterpret_cast<unsigned short*>(smem_i32);
-    const int per_warp = SPARSE ? (w + bp) : (w + 2);
+    const int per_warp = SPARSE ? (w + bp) : edt_window_scratch_ints(w);
     int* scratch = smem_i32 + ((R + 2) * bp) / 2 + warp * per_warp;
     int32_t* __restrict__ d2g = a.d2 + (long long)b * a.P;
     int mx = 0;
+    const bool packed16 = !SPARSE && DVO_EDT_PACKED16 && (w % 2 == 0) && ne != 0u &&
+                          ((reinterpret_cast<uintptr_t>(a.gcol + (long long)b * a.P) & 3) == 0);     // block-uniform; rows are read as 32-bit pairs
+    if (packed16) edt16_fill_pads(reinterpret_cast<unsigned short*>(scratch), w, lane);
     for (int r = warp; r < R + 2; r += WARPS) {
         const int y = y0 - 1 + r;
         if (y < 0 || y >= h) continue;                               // warp-uniform
@@ -1038,6 +1247,13 @@ __global__ void __launch_bounds__(WARPS * 32) edt_pack_kernel(EdtPackArgs a, con
         if (SPARSE) {
             unsigned short* gs = reinterpret_cast<unsigned short*>(scratch + w);
             edt_row_bisect(gr, scratch, gs, gs + bp, w, lane, emit);
+        } else if (packed16) {
+            unsigned* brow2 = reinterpret_cast<unsigned*>(brow);
+            auto emit2 = [&](int x, uint32_t v2) { brow2[x >> 1] = v2; mx = max(mx, (int)max(v2 & 0xFFFFu, v2 >> 16)); };   // both values < DVO_D2_SPILL
+            if (!edt_row_window16(gr, reinterpret_cast<unsigned short*>(scratch), w, lane, emit2)) {
+                edt_row_window(gr, scratch + 1, w, lane, emit);                          // a pixel further than EDT16_G from every edge: exact 32-bit redo
+                edt16_fill_pads(reinterpret_cast<unsigned short*>(scratch), w, lane);   // the redo used the scratch
+            }
         } else {
             edt_row_window(gr, scratch + 1, w, lane, emit);
         }
@@ -1099,7 +1315,7 @@ __global__ void __launch_bounds__(WARPS * 32) edt_pack_kernel(EdtPackArgs a, con
 // shared memory the fused kernel needs for a level of width w (the sparse variant is the larger one)
 static size_t edt_pack_smem(int warps, int R, int w, bool sparse) {
     const int bp = (w + 1) & ~1;
-    return (size_t)(R + 2) * bp * sizeof(unsigned short) + (size_t)warps * (sparse ? (w + bp) : (w + 2)) * sizeof(int);
+    return (size_t)(R + 2) * bp * sizeof(unsigned short) + (size_t)warps * (sparse ? (w + bp) : edt_window_scratch_ints(w)) * sizeof(int);
 }
 
 template <int WARPS, int R>
@@ -1117,7 +1333,7 @@ static int launch_edt_pack_t(dvo_ctx* c, int first, int count) {
         const int w = g.w[l], bp = (w + 1) & ~1;
         dim3 grid((g.h[l] + R - 1) / R, count);
         const size_t band = (size_t)(R + 2) * bp * sizeof(unsigned short);
-        const size_t smem_d = band + (size_t)WARPS * (w + 2) * sizeof(int), smem_s = band + (size_t)WARPS * (w + bp) * sizeof(int);
+        const size_t smem_d = band + (size_t)WARPS * edt_window_scratch_ints(w) * sizeof(int), smem_s = band + (size_t)WARPS * (w + bp) * sizeof(int);
         static size_t opted_d = 0, opted_s = 0;          // largest opt-in so far (per instantiation; one device per process)
         if (smem_d > 48 * 1024 && smem_d > opted_d) { DVO_CUDA(cudaFuncSetAttribute(edt_pack_kernel<WARPS, R, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d)); opted_d = smem_d; }
         if (smem_s > 48 * 1024 && smem_s > opted_s) { DVO_CUDA(cudaFuncSetAttribute(edt_pack_kernel<WARPS, R, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s)); opted_s = smem_s; }

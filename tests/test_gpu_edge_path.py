@@ -404,6 +404,39 @@ def test_edt_sparse_images_take_the_bisection_kernel():
     al.close()
 
 
+def test_edt_packed_rows_redo_far_pixels_exactly():
+    """The dense-image EDT rows run on packed 16-bit lanes with column distances clamped to 170 pixels; a row holding a
+    pixel further than that from every edge must be redone by the 32-bit routine.  A textured patch in one corner (dense
+    enough for the window kernels, nedge * 2048 >= P) leaves most of a 640x480 image 170..600 pixels from the nearest edge;
+    a second image puts a single column of edges at x = 171 / 170 / 169 so that distances sit right on the switch."""
+    rng = np.random.default_rng(11)
+    W, H = 640, 480
+    a = np.full((H, W), 40, np.uint8)
+    a[:96, :128] = (rng.integers(0, 2, (12, 16)) * 180 + 40).astype(np.uint8).repeat(8, 0).repeat(8, 1)
+    b = np.full((H, W), 40, np.uint8); b[:, :171] = 220; b[200:, :170] = 220; b[400:, :169] = 220
+    b[:, 600:] = (rng.integers(0, 2, (60, 5)) * 180 + 40).astype(np.uint8).repeat(8, 0).repeat(8, 1)
+    gray = np.stack([a, b])
+    al = dvo.BatchAligner(W, H, 2, max_batch=2)
+    al.set_frames(dvo.FRAME_REF, gray, np.full((2, H, W), 1000, np.uint16))
+    al.set_frames(dvo.FRAME_NOW, gray, None)
+    al.build_pyramids(2)
+    al.prepare(2)
+    for i in range(2):
+        for l in range(2):
+            edge = al.get_level_buffer(i, 1, l, "edge")
+            assert np.array_equal(edge, O.canny(O.pyr_nearest(gray[i], l)))
+            n = int((edge > 0).sum())
+            assert n * 2048 >= edge.size, (i, l, n)                     # dense: the window kernels, not the bisection
+            d2 = al.get_level_buffer(i, 1, l, "d2")
+            o = O.edt_d2(edge)
+            assert np.array_equal(d2, o), mismatch(d2, o)
+            if l == 0:
+                assert o.max() > 170 * 170 and (o < 170 * 170).any()
+            dtn, _ = O.dt_normalize(d2)
+            assert bits_equal(al.get_level_buffer(i, 1, l, "dtn"), dtn)
+    al.close()
+
+
 def test_gop_compose_matches_oracle():
     rng = np.random.default_rng(5)
     nseq, nframes = 5, 23

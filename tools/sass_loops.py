@@ -28,5 +28,5 @@ for i, (a, ins) in enumerate(body):
                 toks = s.split()
                 op = toks[1] if toks[0].startswith("@") else toks[0]
                 ops[op.split(".")[0]] += 1
-            if ops.get("DFMA", 0) >= 6:
+            if len(seg) >= int(sys.argv[2]) if len(sys.argv) > 2 else ops.get("DFMA", 0) >= 6:
                 print(f"loop {t:#x}..{a:#x}: {len(seg)} instr;", ", ".join(f"{k} {v}" for k, v in ops.most_common(14)))
