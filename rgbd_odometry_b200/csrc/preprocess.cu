@@ -543,9 +543,14 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
             const int y = q / wd, wx = q - y * wd;
             const int idx = (y + 1) * pitch + wx + 1;
             uint32_t e = E[idx], sel = 0u;
-            while (e) {
-                const int i = __ffs(e) - 1; e &= e - 1;
-                if (dep[(long long)y * w + (wx << 5) + i] > 100) sel |= (1u << i);
+            const uint16_t* __restrict__ dr = dep + (long long)y * w + (wx << 5);
+            while (e) {                               // four edge pixels per round: their depth loads are in flight together
+                const int i0 = __ffs(e) - 1; e &= e - 1;
+                const int i1 = e ? __ffs(e) - 1 : i0; e &= e - 1;        // 0 & (0 - 1) == 0: an exhausted word repeats i0
+                const int i2 = e ? __ffs(e) - 1 : i0; e &= e - 1;
+                const int i3 = e ? __ffs(e) - 1 : i0; e &= e - 1;
+                const unsigned d0 = dr[i0], d1 = dr[i1], d2 = dr[i2], d3 = dr[i3];
+                sel |= (d0 > 100u ? 1u << i0 : 0u) | (d1 > 100u ? 1u << i1 : 0u) | (d2 > 100u ? 1u << i2 : 0u) | (d3 > 100u ? 1u << i3 : 0u);
             }
             E[idx] = sel;
         }
@@ -634,15 +639,28 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
         for (int q = q0; q < q1; ++q) {
             const int y = q / wd, wx = q - y * wd;
             uint32_t v = E[(y + 1) * pitch + wx + 1];
-            while (v) {
-                const int x = (wx << 5) + __ffs(v) - 1; v &= v - 1;
-                const float d = (float)dep[(long long)y * w + x];
-                const float z = __fdiv_rn(d, 1000.0f);                                          // :248
-                X[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)x, a.tmpcx)), a.tmpfx);          // :249
-                Y[off] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)y, a.tmpcy)), a.tmpfy);          // :250
-                Z[off] = z;
-                pix[off] = y * w + x;
-                ++off;
+            const uint16_t* __restrict__ dr = dep + (long long)y * w;
+            while (v) {                               // four points per round: their depth loads are in flight together
+                int xs[4], n = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (v) { xs[k] = (wx << 5) + __ffs(v) - 1; v &= v - 1; n = k + 1; } else xs[k] = xs[0];
+                }
+                unsigned dv[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) dv[k] = dr[xs[k]];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (k < n) {
+                        const int x = xs[k];
+                        const float z = __fdiv_rn((float)dv[k], 1000.0f);                                    // :248
+                        X[off + k] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)x, a.tmpcx)), a.tmpfx);        // :249
+                        Y[off + k] = __fmul_rn(__fmul_rn(z, __fsub_rn((float)y, a.tmpcy)), a.tmpfy);        // :250
+                        Z[off + k] = z;
+                        pix[off + k] = y * w + x;
+                    }
+                }
+                off += n;
             }
         }
         if (tid == 0) a.npts[(long long)b * a.L] = s_scan[CANNY_MAX_WARPS];
@@ -1228,11 +1246,24 @@ __global__ void __launch_bounds__(WARPS * 32) edt_pack_kernel(EdtPackArgs a, con
     int mx = 0;
     const bool packed16 = !SPARSE && DVO_EDT_PACKED16 && (w % 2 == 0) && ne != 0u &&
                           ((reinterpret_cast<uintptr_t>(a.gcol + (long long)b * a.P) & 3) == 0);     // block-uniform; rows are read as 32-bit pairs
+    __shared__ int s_next_row;
+    if (threadIdx.x == 0) s_next_row = WARPS;
+    if (ne != 0u) {      // the band's column distances (contiguous rows y0-1 .. y0+R) towards L2 while the first rows are being set up
+        const int ya = max(y0 - 1, 0), yb = min(y0 + R + 1, h);
+        const char* base = reinterpret_cast<const char*>(a.gcol + (long long)b * a.P + (long long)ya * w);
+        const int nbytes = (yb - ya) * w * 2;
+        for (int o = threadIdx.x * 128; o < nbytes; o += WARPS * 32 * 128) asm volatile("prefetch.global.L2 [%0];" :: "l"(base + o));
+    }
     if (packed16) edt16_fill_pads(reinterpret_cast<unsigned short*>(scratch), w, lane);
-    for (int r = warp; r < R + 2; r += WARPS) {
-        const int y = y0 - 1 + r;
+    __syncthreads();
+    // rows are handed out dynamically (their cost follows the distance to the nearest edge): first one per warp, then first come first served
+    for (int r = warp; r < R + 2; ) {
+        const int rcur = r;
+        if (lane == 0) r = atomicAdd(&s_next_row, 1);
+        r = __shfl_sync(0xffffffffu, r, 0);
+        const int y = y0 - 1 + rcur;
         if (y < 0 || y >= h) continue;                               // warp-uniform
-        unsigned short* brow = band + r * bp;
+        unsigned short* brow = band + rcur * bp;
         int32_t* grow = d2g + (long long)y * w;
         auto emit = [&](int x, int v) {
             brow[x] = (unsigned short)min(v, 65535);
