@@ -719,6 +719,19 @@ int launch_canny(dvo_ctx* c, int first, int count, int frames_mask) {
         int strips = (CANNY_MAX_WARPS * 32) / wdl; if (strips > g.h[l]) strips = g.h[l]; if (strips < 1) strips = 1;
         int threads = wdl * strips; if (threads < g.w[l]) threads = g.w[l];
         int warps = (threads + 31) / 32; if (warps > CANNY_MAX_WARPS) warps = CANNY_MAX_WARPS; if (warps < 4) warps = 4;
+        {   // smaller levels: smaller CTAs, more of them per SM (their phases are short and barrier-separated); DVO_CANNY_WARPS="24,12,8,4" overrides
+            static int cap[DVO_MAX_LEVELS] = {-1};
+            if (cap[0] < 0) {
+                const int dflt[DVO_MAX_LEVELS] = {24, 12, 8, 4, 4, 4};      // 640x480, 1024 pairs: 4.14 ms with 24 warps everywhere, 3.95 ms so
+                for (int i = 0; i < DVO_MAX_LEVELS; ++i) cap[i] = dflt[i];
+                if (const char* e = getenv("DVO_CANNY_WARPS")) {
+                    int i = 0;
+                    for (const char* q = e; *q && i < DVO_MAX_LEVELS; ++i) { cap[i] = atoi(q); while (*q && *q != ',') ++q; if (*q == ',') ++q; }
+                    for (int k = 0; k < DVO_MAX_LEVELS; ++k) if (cap[k] < 4 || cap[k] > CANNY_MAX_WARPS) cap[k] = dflt[k];
+                }
+            }
+            if (warps > cap[l]) warps = cap[l];
+        }
         const int T = warps * 32;
         CannyArgs a;
         for (int f = 0; f < 2; ++f) {
