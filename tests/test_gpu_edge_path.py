@@ -317,10 +317,11 @@ def test_blank_and_degenerate_inputs():
     al.close()
 
 
-@pytest.mark.parametrize("W,H,L", [(100, 75, 3), (82, 61, 2), (1280, 720, 5), (320, 240, 4), (2112, 96, 2)])
+@pytest.mark.parametrize("W,H,L", [(100, 75, 3), (82, 61, 2), (1280, 720, 5), (320, 240, 4), (2112, 96, 2), (200, 152, 2), (132, 100, 1)])
 def test_ragged_and_large_sizes(W, H, L):
     """Odd sizes (cvRound half-to-even level dims, non-multiple-of-32 widths), 1280x720x5 (BASELINE config 4;
-    hysteresis bitmaps exceed shared memory -> global scratch path) and a very wide image (EDT bisection fallback)."""
+    hysteresis bitmaps exceed shared memory -> global scratch path), a very wide image (EDT bisection fallback) and widths
+    that are a multiple of 4 but not of 32 / 128 (the vector path of sobel_nms_kernel with a partial last chunk and word)."""
     K = (525.0 * W / 640, 525.0 * W / 640, (W - 1) / 2.0, (H - 1) / 2.0)
     d = O.synth_pair(7, W, H, K)
     al = dvo.BatchAligner(W, H, L, max_batch=1, intrinsics=K)
