@@ -370,7 +370,7 @@ def bench_config2(env, args):
         n_e2e = max(2, min(args.steps, 5))
         ems = env.timed(lambda: al.align_batch(hp["ref_gray"], hp["ref_depth"], hp["now_gray"], params, want_info=False), n_e2e)
         e2e = e2e_block(env, world * B / (ems * 1e-3), ems, B * W * H * 4, B * 96, pcie_peak,
-                        note="uploads in 256-pair chunks on a copy stream, chunk k+1's copy overlaps chunk k's kernels; the pass is bound by the host link")
+                        note="uploads in 128-pair chunks on a copy stream, chunk k+1's copy overlaps chunk k's kernels; the pass is bound by the host link")
         del pin, hp
 
     # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the box's host cores, bounded sample

@@ -560,16 +560,16 @@ int run_sequences_core(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, c
         if (rc != DVO_OK) return;
         uint8_t* dg = c->gray[frame] + lvl_at(c->geom, 0, 0); uint16_t* dd = c->depth[frame] + lvl_at(c->geom, 0, 0);
         if (frame == DVO_FRAME_NOW && c->now_valid[0]) {                                     // setRcvdFrameAsNowFrame keeps the outgoing now frame (:594-600)
-            fail(cudaMemcpyAsync(c->prev_gray, dg, P0 * nseq, cudaMemcpyDeviceToDevice, c->stream));
-            fail(cudaMemcpyAsync(c->prev_depth, dd, P0 * nseq * 2, cudaMemcpyDeviceToDevice, c->stream));
+            if (rc == DVO_OK) rc = launch_copy_bytes(c, c->prev_gray, dg, P0 * nseq);
+            if (rc == DVO_OK) rc = launch_copy_bytes(c, c->prev_depth, dd, P0 * nseq * 2);
             for (int s2 = 0; s2 < nseq; ++s2) c->prev_valid[s2] = 1;
         }
         if (frame == DVO_FRAME_NOW) for (int s2 = 0; s2 < nseq; ++s2) c->now_valid[s2] = 1;
         if (host_in) {
             const int k = t & 1;
             fail(cudaStreamWaitEvent(c->stream, ev_ready[k], 0));
-            fail(cudaMemcpyAsync(dg, stage_g[k], P0 * nseq, cudaMemcpyDeviceToDevice, c->stream));
-            fail(cudaMemcpyAsync(dd, stage_d[k], P0 * nseq * 2, cudaMemcpyDeviceToDevice, c->stream));
+            if (rc == DVO_OK) rc = launch_copy_bytes(c, dg, stage_g[k], P0 * nseq);          // a kernel, not a D2D memcpy: the copy engines stay with the uploads
+            if (rc == DVO_OK) rc = launch_copy_bytes(c, dd, stage_d[k], P0 * nseq * 2);
             fail(cudaEventRecord(ev_free[k], c->stream));
         } else {
             fail(cudaMemcpy2DAsync(dg, P0, gray + (size_t)t * P0, (size_t)nframes * P0, P0, nseq, cudaMemcpyDeviceToDevice, c->stream));

@@ -142,6 +142,7 @@ int launch_eval(dvo_ctx* c, int slot, int level, const double* d_pose12, int jac
 int launch_gop(dvo_ctx* c, int nseq, int nframes, const int* d_kind, const double* d_rel, double* d_out);
 int launch_promote(dvo_ctx* c, int first, int count);
 int launch_ingest_raw(dvo_ctx* c, int frame, int first, int count, const uint8_t* d_bgr, const float* d_depth_m);
+int launch_copy_bytes(dvo_ctx* c, void* dst, const void* src, size_t n);
 
 // ---- arithmetic policies for the per-point fp32 math ----
 // EXACT: one IEEE rounding per written operation, never contracted -> bit-identical to the oracle compiled with

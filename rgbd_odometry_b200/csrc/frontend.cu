@@ -142,3 +142,26 @@ int launch_ingest_raw(dvo_ctx* c, int frame, int first, int count, const uint8_t
     DVO_CUDA(cudaGetLastError());
     return DVO_OK;
 }
+
+// Device-to-device byte copy as a kernel.  The sequence pipeline moves a staged frame into the level-0 regions while the next
+// frame's host-to-device copy is in flight: a cudaMemcpyAsync D2D can be scheduled on the same copy engine as that upload (the
+// end-to-end sequence rate then varied 3x between runs); a kernel leaves the copy engines to the host link.
+__global__ void __launch_bounds__(256) copy_bytes_kernel(uint8_t* __restrict__ dst, const uint8_t* __restrict__ src, size_t n16, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = (n16 << 4) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+int launch_copy_bytes(dvo_ctx* c, void* dst, const void* src, size_t n) {
+    if (n == 0) return DVO_OK;
+    const bool vec = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+    const size_t n16 = vec ? (n >> 4) : 0;
+    size_t blocks = ((vec ? n16 : n) + 255) / 256;
+    const size_t cap = (size_t)c->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    copy_bytes_kernel<<<(unsigned)blocks, 256, 0, c->stream>>>(static_cast<uint8_t*>(dst), static_cast<const uint8_t*>(src), n16, n);
+    c->launches++;
+    DVO_CUDA(cudaGetLastError());
+    return DVO_OK;
+}
