@@ -169,6 +169,12 @@ int dvo_destroy(dvo_ctx* c) {
     for (int f = 0; f < 2; ++f) { cudaFree(c->gray[f]); cudaFree(c->depth[f]); cudaFree(c->edge[f]); }
     cudaFree(c->gcol); cudaFree(c->d2); cudaFree(c->texel); cudaFree(c->tex8); cudaFree(c->ptsX); cudaFree(c->ptsY); cudaFree(c->ptsZ); cudaFree(c->ptsPix);
     cudaFree(c->npts); cudaFree(c->solve_order); cudaFree(c->seq_mask); cudaFree(c->seq_state); cudaFree(c->nedge); cudaFree(c->maxd2); cudaFree(c->pose0); cudaFree(c->pose); cudaFree(c->info);
+    cudaFree(c->seq_rel); cudaFree(c->seq_kind); cudaFree(c->seq_reason); cudaFree(c->seq_glob);
+    for (int k = 0; k < 2; ++k) {
+        cudaFree(c->seq_stage_g[k]); cudaFree(c->seq_stage_d[k]);
+        if (c->seq_ev_ready[k]) cudaEventDestroy(c->seq_ev_ready[k]);
+        if (c->seq_ev_free[k]) cudaEventDestroy(c->seq_ev_free[k]);
+    }
     cudaFree(c->trace); cudaFree(c->energy); cudaFree(c->bitmap_scratch); cudaFree(c->prev_gray); cudaFree(c->prev_depth); cudaFree(c->raw_bgr); cudaFree(c->raw_depth);
     free(c->now_valid); free(c->prev_valid);
     if (c->h_pose) cudaFreeHost(c->h_pose);
@@ -524,21 +530,26 @@ int run_sequences_core(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, c
     int rc = DVO_OK;
     auto fail = [&](cudaError_t e) { if (e != cudaSuccess && rc == DVO_OK) { dvo_set_error("%s: %s", who, cudaGetErrorString(e)); rc = DVO_ERR_CUDA; } return rc != DVO_OK; };
 
-    // ---- buffers: record of the run (device), staging for the uploads
-    double* d_rel = nullptr; int* d_kind = nullptr; int* d_reason = nullptr; double* d_glob = nullptr;
-    uint8_t* stage_g[2] = {nullptr, nullptr}; uint16_t* stage_d[2] = {nullptr, nullptr};
-    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-    auto cleanup = [&]() {
-        cudaFree(d_rel); cudaFree(d_kind); cudaFree(d_reason); cudaFree(d_glob);
-        for (int k = 0; k < 2; ++k) { cudaFree(stage_g[k]); cudaFree(stage_d[k]); if (ev_ready[k]) cudaEventDestroy(ev_ready[k]); if (ev_free[k]) cudaEventDestroy(ev_free[k]); }
-    };
-    fail(cudaMalloc((void**)&d_rel, sizeof(double) * 12 * n)); fail(cudaMalloc((void**)&d_kind, sizeof(int) * n)); fail(cudaMalloc((void**)&d_reason, sizeof(int) * n));
-    if (host_in)
+    // ---- buffers: record of the run (device), staging for the uploads -- owned by the context, grown on demand, reused across calls
+    if (c->seq_rec_n < n) {
+        cudaFree(c->seq_rel); cudaFree(c->seq_kind); cudaFree(c->seq_reason); c->seq_rel = nullptr; c->seq_kind = nullptr; c->seq_reason = nullptr; c->seq_rec_n = 0;
+        fail(cudaMalloc((void**)&c->seq_rel, sizeof(double) * 12 * n)); fail(cudaMalloc((void**)&c->seq_kind, sizeof(int) * n)); fail(cudaMalloc((void**)&c->seq_reason, sizeof(int) * n));
+        if (rc == DVO_OK) c->seq_rec_n = n;
+    }
+    if (host_in && c->seq_stage_slots < (size_t)nseq) {
+        for (int k = 0; k < 2; ++k) { cudaFree(c->seq_stage_g[k]); cudaFree(c->seq_stage_d[k]); c->seq_stage_g[k] = nullptr; c->seq_stage_d[k] = nullptr; }
+        c->seq_stage_slots = 0;
         for (int k = 0; k < 2 && rc == DVO_OK; ++k) {
-            fail(cudaMalloc((void**)&stage_g[k], P0 * nseq)); fail(cudaMalloc((void**)&stage_d[k], P0 * nseq * sizeof(uint16_t)));
-            fail(cudaEventCreateWithFlags(&ev_ready[k], cudaEventDisableTiming)); fail(cudaEventCreateWithFlags(&ev_free[k], cudaEventDisableTiming));
+            fail(cudaMalloc((void**)&c->seq_stage_g[k], P0 * nseq)); fail(cudaMalloc((void**)&c->seq_stage_d[k], P0 * nseq * sizeof(uint16_t)));
+            if (!c->seq_ev_ready[k]) fail(cudaEventCreateWithFlags(&c->seq_ev_ready[k], cudaEventDisableTiming));
+            if (!c->seq_ev_free[k]) fail(cudaEventCreateWithFlags(&c->seq_ev_free[k], cudaEventDisableTiming));
         }
-    if (rc != DVO_OK) { cleanup(); return rc; }
+        if (rc == DVO_OK) c->seq_stage_slots = (size_t)nseq;
+    }
+    if (rc != DVO_OK) return rc;
+    double* d_rel = c->seq_rel; int* d_kind = c->seq_kind; int* d_reason = c->seq_reason; double* d_glob = nullptr;
+    uint8_t* stage_g[2] = {c->seq_stage_g[0], c->seq_stage_g[1]}; uint16_t* stage_d[2] = {c->seq_stage_d[0], c->seq_stage_d[1]};
+    cudaEvent_t ev_ready[2] = {c->seq_ev_ready[0], c->seq_ev_ready[1]}, ev_free[2] = {c->seq_ev_free[0], c->seq_ev_free[1]};
     fail(cudaMemsetAsync(d_rel, 0, sizeof(double) * 12 * n, c->stream));
     fail(cudaMemsetAsync(d_kind, 0, sizeof(int) * n, c->stream));
     fail(cudaMemsetAsync(d_reason, 0, sizeof(int) * n, c->stream));
@@ -618,7 +629,12 @@ int run_sequences_core(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, c
     c->active = nullptr;
     c->timing = timing;
     if (rc == DVO_OK && global_poses) {
-        if (!fail(cudaMalloc((void**)&d_glob, sizeof(double) * 19 * n))) {
+        if (c->seq_glob_n < n) {
+            cudaFree(c->seq_glob); c->seq_glob = nullptr; c->seq_glob_n = 0;
+            if (!fail(cudaMalloc((void**)&c->seq_glob, sizeof(double) * 19 * n))) c->seq_glob_n = n;
+        }
+        d_glob = c->seq_glob;
+        if (rc == DVO_OK) {
             rc = launch_gop(c, nseq, nframes, d_kind, d_rel, d_glob);
             if (rc == DVO_OK) fail(cudaMemcpyAsync(global_poses, d_glob, sizeof(double) * 19 * n, cudaMemcpyDeviceToHost, c->stream));
         }
@@ -630,7 +646,6 @@ int run_sequences_core(dvo_ctx* c, int nseq, int nframes, const uint8_t* gray, c
     }
     cudaStreamSynchronize(c->copy_stream);
     if (cudaStreamSynchronize(c->stream) != cudaSuccess && rc == DVO_OK) { dvo_set_error("%s: %s", who, cudaGetErrorString(cudaGetLastError())); rc = DVO_ERR_CUDA; }
-    cleanup();
     return rc;
 }
 }  // namespace

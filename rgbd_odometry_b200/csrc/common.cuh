@@ -62,6 +62,11 @@ struct dvo_ctx {
     bool aux_pending;               // work is in flight on aux[] that the context stream has not joined yet
     int proc_first, proc_count;     // slot range of the dvo_process call that left that work in flight
     int e2e_chunk;           // frame pairs per upload/compute pipeline stage in dvo_align_batch
+    // sequence mode (run_sequences_core): staging for the pipelined uploads and the device record of a run, kept across calls
+    // (cudaMalloc / cudaFree of ~0.8 GB per call made the end-to-end sequence rate vary 8x between runs)
+    uint8_t* seq_stage_g[2]; uint16_t* seq_stage_d[2]; size_t seq_stage_slots;
+    cudaEvent_t seq_ev_ready[2], seq_ev_free[2];
+    double* seq_rel; int* seq_kind; int* seq_reason; double* seq_glob; size_t seq_rec_n, seq_glob_n;
     int sm_count;
     int solve_shape;         // threads per pair in solve_kernel: 512 when max_batch <= sm_count (one pair per SM at most), else 256
     size_t smem_optin;
