@@ -1390,10 +1390,12 @@ static int launch_edt_pack_t(dvo_ctx* c, int first, int count) {
 }
 
 int launch_edt_pack(dvo_ctx* c, int first, int count) {
-    // band height: 24 rows (+2 halo, 13 warps x 2 rows: 3.83 ms per 1024 pairs at 640x480 against 3.85 / 3.92 / 4.00 for 20 / 28 / 12
-    // rows and 4.41 for the unfused kernels).  At 1280x720 a band costs twice the shared memory and the fused kernel is no faster
-    // than the unfused pair (2.46 ms per 148 pairs either way at best, 2.7 - 3.5 for the other band shapes): wide images stay unfused.
-    const int shape = c->edt_band ? c->edt_band : (c->geom.w[0] > 800 ? -1 : 24);
+    // band height (640x480, 1024 pairs, packed 16-bit window): 20 rows + 2 halo with 11 warps (73 KB of shared memory, three CTAs per
+    // SM) 2.65 ms; 24 rows x 13 warps (86 KB, two CTAs per SM) 2.82; 12 x 7: 2.78; 16 x 9: 2.80; 28 x 10: 2.82; also 16 x 8: 2.70,
+    // 16 x 10: 2.76, 20 x 9 / 10 / 12 / 14: 2.83 / 2.73 / 2.96 / 3.10.  (With the 32-bit window 24 x 13 was best: 3.83 against 3.85 -
+    // 4.00, and 4.41 for the unfused kernels.)  At 1280x720 a band costs twice the shared memory and the fused kernel is no faster
+    // than the unfused pair: wide images stay unfused.
+    const int shape = c->edt_band ? c->edt_band : (c->geom.w[0] > 800 ? -1 : 20);
     if (shape < 0) { const int rc = launch_edt_rows(c, first, count); return rc ? rc : launch_pack(c, first, count); }
     if (shape == 12) return launch_edt_pack_t<7, 12>(c, first, count);
     if (shape == 20) return launch_edt_pack_t<11, 20>(c, first, count);
