@@ -78,12 +78,9 @@ __device__ __forceinline__ void ph_grad(const uint8_t* __restrict__ g, int rows,
     gy = (double)g[(rows > 1 ? r1 : r) * cols + c] - v;
 }
 
-// Jacobian row of pixel (r,c)  (:390-395, :415)
-__device__ __forceinline__ void ph_jrow(const uint8_t* __restrict__ g, const uint16_t* __restrict__ d, int rows, int cols, int r, int c,
-                                        double sf, const PhCam& K, bool compat, double* J) {
-    const double Zmm = (double)d[r * cols + c];
+// Jacobian row of pixel (r,c)  (:390-395, :415) from its depth and forward differences
+__device__ __forceinline__ void ph_jrow_vals(double Zmm, double egx, double egy, int r, int c, double sf, const PhCam& K, bool compat, double* J) {
     const PixGeom p = ph_xyz(r, c, Zmm, sf, K, compat);
-    double egx, egy; ph_grad(g, rows, cols, r, c, egx, egy);
     const double fx = K.fx, fy = K.fy, X = p.X, Y = p.Y, Z = p.Z;
     if (compat) {
         const double Z_inv = 1.0 / Z, Z2_inv = 1.0 / (Z * Z);
@@ -98,6 +95,11 @@ __device__ __forceinline__ void ph_jrow(const uint8_t* __restrict__ g, const uin
         const double J1 = fxs * egx * Z_inv, J2 = fys * egy * Z_inv, J3 = -(J1 * X + J2 * Y) * Z_inv;
         J[0] = J1; J[1] = J2; J[2] = J3; J[3] = J3 * Y - J2 * Z; J[4] = J1 * Z - J3 * X; J[5] = J2 * X - J1 * Y;
     } else { for (int k = 0; k < 6; ++k) J[k] = 0.0; }
+}
+__device__ __forceinline__ void ph_jrow(const uint8_t* __restrict__ g, const uint16_t* __restrict__ d, int rows, int cols, int r, int c,
+                                        double sf, const PhCam& K, bool compat, double* J) {
+    double egx, egy; ph_grad(g, rows, cols, r, c, egx, egy);
+    ph_jrow_vals((double)d[r * cols + c], egx, egy, r, c, sf, K, compat, J);
 }
 
 // deterministic block reduction of PH_NACC doubles into partial[blockIdx]
@@ -263,8 +265,9 @@ __global__ void __launch_bounds__(PH_THREADS) ph_accum_kernel(PhArgs a) {
         const uint8_t* gn = a.gray_now + (long long)b * a.P;
         int* wn = a.winner + (long long)b * a.g.P[0];
         const int rows = a.rows, cols = a.cols;
-        for (int k = blockIdx.x * PH_THREADS + threadIdx.x; k < a.P; k += gridDim.x * PH_THREADS) {
-            if (a.compat) {
+        const int stride = gridDim.x * PH_THREADS, k0 = blockIdx.x * PH_THREADS + threadIdx.x;
+        if (a.compat) {
+            for (int k = k0; k < a.P; k += stride) {
                 // flattened index k: eps is row-major (cell k), J row k is the column-major pixel k (quirk 5); holes give -I_now
                 const int wk = wn[k];
                 if (a.reset_winner) wn[k] = -1;
@@ -275,23 +278,46 @@ __global__ void __launch_bounds__(PH_THREADS) ph_accum_kernel(PhArgs a) {
 #pragma unroll
                 for (int q = 0; q < 6; ++q) acc[q] += J[q] * e;
                 acc[6] += e * e; acc[7] += 1.0;
-            } else {
-                const int wk = wn[k];
-                if (wk < 0) continue;
-                if (a.reset_winner) wn[k] = -1;
-                const int rs = wk % rows, cs = wk / rows;     // source pixel that owns this cell
-                const double e = (double)g[rs * cols + cs] - (double)gn[k];
-                const double w = s_hw[(int)fabs(e)];
-                double J[6]; ph_jrow(g, d, rows, cols, rs, cs, a.sf, a.K, false, J);
-                int idx = 8;
-#pragma unroll
-                for (int p = 0; p < 6; ++p) {
-                    const double jw = J[p] * w;
-                    acc[p] += jw * e;
-#pragma unroll
-                    for (int q = p; q < 6; ++q) { acc[idx] += jw * J[q]; ++idx; }
+            }
+        } else {
+            // Software pipeline over the thread's cells: the winner of cell k + 2 strides is loaded while the five gathers its
+            // predecessor's winner addresses (source intensity, two forward-difference taps, depth, now intensity) are in flight
+            // and the cell before that is accumulated -- two dependent memory latencies per cell are otherwise exposed at the
+            // two CTAs per SM that 29 fp64 accumulators leave.
+            struct Taps { int rs, cs; unsigned gv, gr, gd, gnv, dz; };
+            auto gather = [&](int wk, int k) {
+                Taps t; t.rs = -1; t.cs = 0; t.gv = t.gr = t.gd = t.gnv = t.dz = 0u;
+                if (wk >= 0) {
+                    const int rs = wk % rows, cs = wk / rows;      // source pixel that owns this cell
+                    const int c1 = (cs + 1 < cols) ? cs + 1 : cols - 2, r1 = (rs + 1 < rows) ? rs + 1 : rows - 2;   // ph_grad's REFLECT_101 taps
+                    t.rs = rs; t.cs = cs;
+                    t.gv = g[rs * cols + cs]; t.gr = g[rs * cols + (cols > 1 ? c1 : cs)]; t.gd = g[(rows > 1 ? r1 : rs) * cols + cs];
+                    t.dz = d[rs * cols + cs]; t.gnv = gn[k];
                 }
-                acc[6] += e * e; acc[7] += 1.0;
+                return t;
+            };
+            int wk1 = (k0 + stride < a.P) ? wn[k0 + stride] : -1;
+            Taps t0 = gather((k0 < a.P) ? wn[k0] : -1, k0);
+            for (int k = k0; k < a.P; k += stride) {
+                const int wk2 = (k + 2 * stride < a.P) ? wn[k + 2 * stride] : -1;
+                const Taps t1 = gather(wk1, k + stride);
+                if (t0.rs >= 0) {
+                    if (a.reset_winner) wn[k] = -1;
+                    const double v = (double)t0.gv;
+                    const double e = v - (double)t0.gnv;
+                    const double w = s_hw[(int)fabs(e)];
+                    double J[6]; ph_jrow_vals((double)t0.dz, (double)t0.gr - v, (double)t0.gd - v, t0.rs, t0.cs, a.sf, a.K, false, J);
+                    int idx = 8;
+#pragma unroll
+                    for (int p = 0; p < 6; ++p) {
+                        const double jw = J[p] * w;
+                        acc[p] += jw * e;
+#pragma unroll
+                        for (int q = p; q < 6; ++q) { acc[idx] += jw * J[q]; ++idx; }
+                    }
+                    acc[6] += e * e; acc[7] += 1.0;
+                }
+                t0 = t1; wk1 = wk2;
             }
         }
     }
