@@ -248,8 +248,11 @@ __global__ void __launch_bounds__(256) ph_splat_kernel(PhArgs a) {
     if ((threadIdx.x & 31) == 0 && m) atomicAdd(&S.nreproj, __popc(m));
 }
 
+#ifndef PH_ACCUM_MIN_BLOCKS
+#define PH_ACCUM_MIN_BLOCKS 2
+#endif
 // residual + normal equations (:176-182): partial sums per block
-__global__ void __launch_bounds__(PH_THREADS) ph_accum_kernel(PhArgs a) {
+__global__ void __launch_bounds__(PH_THREADS, PH_ACCUM_MIN_BLOCKS) ph_accum_kernel(PhArgs a) {
     const int b = a.first + blockIdx.y;
     PhState& S = a.st[b];
     // Huber weights: the residual is a difference of two 8-bit intensities, so |e| is an integer in 0..255 and k / |e| takes 256
