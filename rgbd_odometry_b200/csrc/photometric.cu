@@ -206,46 +206,55 @@ __global__ void __launch_bounds__(256) ph_clear_kernel(PhArgs a) {
 }
 
 // warpImage (:490-553): forward splat; "last writer wins" in column-major pixel order == max source index per cell.
+// PH_SPLAT_PX pixels per thread (256 apart, so every load and the sources of a warp stay coalesced): the depth loads of all of
+// them are issued before the first projection, and the pair's state and inverse transform are read once per thread.  With one
+// pixel per thread the kernel sat at 22 % of its issue slots with 80 % of the stall samples on those dependent loads.
+#ifndef PH_SPLAT_PX
+#define PH_SPLAT_PX 8
+#endif
 __global__ void __launch_bounds__(256) ph_splat_kernel(PhArgs a) {
     const int b = a.first + blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int base = blockIdx.x * (256 * PH_SPLAT_PX) + threadIdx.x;
     PhState& S = a.st[b];
     if (S.stop) return;
-    int hit = 0;
-    if (i < a.P) {
-        const int rows = a.rows, cols = a.cols;
+    const int rows = a.rows, cols = a.cols;
+    unsigned dzv[PH_SPLAT_PX];
+#pragma unroll
+    for (int j = 0; j < PH_SPLAT_PX; ++j) { const int i = base + j * 256; dzv[j] = (i < a.P) ? (unsigned)a.depth_ref[(long long)b * a.P + i] : 0u; }
+    // Tr^-1 = [R^T, -R^T t]
+    const double* Tr = S.Tr;
+    double Ti[12];
+    for (int u = 0; u < 3; ++u) for (int v = 0; v < 3; ++v) Ti[4 * u + v] = Tr[4 * v + u];
+    for (int u = 0; u < 3; ++u) Ti[4 * u + 3] = -((Ti[4 * u] * Tr[3] + Ti[4 * u + 1] * Tr[7]) + Ti[4 * u + 2] * Tr[11]);
+    int* wn = a.winner + (long long)b * a.g.P[0];
+    int hits = 0;
+#pragma unroll
+    for (int j = 0; j < PH_SPLAT_PX; ++j) {
+        const int i = base + j * 256;
+        if (i >= a.P || !(a.compat || dzv[j] > 0u)) continue;
         const int r = i / cols, c = i - r * cols;
-        const uint16_t dz = a.depth_ref[(long long)b * a.P + i];
-        if (a.compat || dz > 0) {
-            const PixGeom p = ph_xyz(r, c, (double)dz, a.sf, a.K, a.compat != 0);
-            // Tr^-1 = [R^T, -R^T t]
-            const double* Tr = S.Tr;
-            double Ti[12];
-            for (int u = 0; u < 3; ++u) for (int v = 0; v < 3; ++v) Ti[4 * u + v] = Tr[4 * v + u];
-            for (int u = 0; u < 3; ++u) Ti[4 * u + 3] = -((Ti[4 * u] * Tr[3] + Ti[4 * u + 1] * Tr[7]) + Ti[4 * u + 2] * Tr[11]);
-            const double px = ((Ti[0] * p.X + Ti[1] * p.Y) + Ti[2] * p.Z) + Ti[3] * 1.0;
-            const double py = ((Ti[4] * p.X + Ti[5] * p.Y) + Ti[6] * p.Z) + Ti[7] * 1.0;
-            const double pz = ((Ti[8] * p.X + Ti[9] * p.Y) + Ti[10] * p.Z) + Ti[11] * 1.0;
-            int tR = -1, tC = -1;
-            if (a.compat) {                               // :526-527: u is a ROW coordinate, fx unscaled
-                const double u = a.K.fx * px / pz + a.sf * a.K.cx, v = a.K.fy * py / pz + a.sf * a.K.cy;
-                if (u > -1.0e9 && u < 1.0e9 && v > -1.0e9 && v < 1.0e9) { tR = (int)floor(u); tC = (int)floor(v); }
-            } else if (pz > 0.0) {
-                const double ipz = 1.0 / pz;
-                const double uc = ((a.sf * a.K.fx) * px) * ipz + a.sf * a.K.cx, vr = ((a.sf * a.K.fy) * py) * ipz + a.sf * a.K.cy;
-                if (uc > -1.0e9 && uc < 1.0e9 && vr > -1.0e9 && vr < 1.0e9) { tC = (int)floor(uc); tR = (int)floor(vr); }
-            }
-            if (tR >= 0 && tR < rows - 1 && tC >= 0 && tC < cols - 1) {
-                hit = 1;
-                const int k = c * rows + r;               // column-major source index
-                int* wn = a.winner + (long long)b * a.g.P[0];
-                atomicMax(&wn[tR * cols + tC], k); atomicMax(&wn[tR * cols + tC + 1], k);
-                atomicMax(&wn[(tR + 1) * cols + tC], k); atomicMax(&wn[(tR + 1) * cols + tC + 1], k);
-            }
+        const PixGeom p = ph_xyz(r, c, (double)dzv[j], a.sf, a.K, a.compat != 0);
+        const double px = ((Ti[0] * p.X + Ti[1] * p.Y) + Ti[2] * p.Z) + Ti[3] * 1.0;
+        const double py = ((Ti[4] * p.X + Ti[5] * p.Y) + Ti[6] * p.Z) + Ti[7] * 1.0;
+        const double pz = ((Ti[8] * p.X + Ti[9] * p.Y) + Ti[10] * p.Z) + Ti[11] * 1.0;
+        int tR = -1, tC = -1;
+        if (a.compat) {                               // :526-527: u is a ROW coordinate, fx unscaled
+            const double u = a.K.fx * px / pz + a.sf * a.K.cx, v = a.K.fy * py / pz + a.sf * a.K.cy;
+            if (u > -1.0e9 && u < 1.0e9 && v > -1.0e9 && v < 1.0e9) { tR = (int)floor(u); tC = (int)floor(v); }
+        } else if (pz > 0.0) {
+            const double ipz = 1.0 / pz;
+            const double uc = ((a.sf * a.K.fx) * px) * ipz + a.sf * a.K.cx, vr = ((a.sf * a.K.fy) * py) * ipz + a.sf * a.K.cy;
+            if (uc > -1.0e9 && uc < 1.0e9 && vr > -1.0e9 && vr < 1.0e9) { tC = (int)floor(uc); tR = (int)floor(vr); }
+        }
+        if (tR >= 0 && tR < rows - 1 && tC >= 0 && tC < cols - 1) {
+            ++hits;
+            const int k = c * rows + r;               // column-major source index
+            atomicMax(&wn[tR * cols + tC], k); atomicMax(&wn[tR * cols + tC + 1], k);
+            atomicMax(&wn[(tR + 1) * cols + tC], k); atomicMax(&wn[(tR + 1) * cols + tC + 1], k);
         }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(&S.nreproj, __popc(m));
+    hits = __reduce_add_sync(0xffffffffu, hits);
+    if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&S.nreproj, hits);
 }
 
 #ifndef PH_ACCUM_MIN_BLOCKS
@@ -650,7 +659,7 @@ int dvo_photo_estimate(dvo_photo_ctx* c, int first, int count, int level, int it
     ph_clear_kernel<<<gpix, 256, 0, c->stream>>>(a);
     c->launches++;
     for (int itr = 0; itr < iters; ++itr) {
-        ph_splat_kernel<<<gpix, 256, 0, c->stream>>>(a);
+        ph_splat_kernel<<<dim3((a.P + 256 * PH_SPLAT_PX - 1) / (256 * PH_SPLAT_PX), count), 256, 0, c->stream>>>(a);
         ph_accum_kernel<<<dim3(a.nblk, count), PH_THREADS, 0, c->stream>>>(a);
         ph_solve_kernel<<<count, 64, 0, c->stream>>>(a, itr);
         c->launches += 3;
@@ -757,7 +766,7 @@ int dvo_photo_eval(dvo_photo_ctx* c, int slot, int level, const double* R9T3, in
     PhArgs a = ph_args(c, level, slot, compat, huber_k, 0.0);
     const dim3 gpix((a.P + 255) / 256, 1);
     ph_clear_kernel<<<gpix, 256, 0, c->stream>>>(a);
-    ph_splat_kernel<<<gpix, 256, 0, c->stream>>>(a);
+    ph_splat_kernel<<<dim3((a.P + 256 * PH_SPLAT_PX - 1) / (256 * PH_SPLAT_PX), 1), 256, 0, c->stream>>>(a);
     ph_accum_kernel<<<dim3(a.nblk, 1), PH_THREADS, 0, c->stream>>>(a);
     c->launches += 3;
     std::vector<double> part((size_t)a.nblk * PH_NACC);
