@@ -43,7 +43,7 @@ struct dvo_photo_ctx {
     uint8_t* bgr[2];      // full resolution, [Bmax][H][W][3]
     uint8_t* gray[2];     // AREA pyramid of the full-resolution gray
     uint16_t* depth[2];   // AREA pyramid of depth (now: stored for API completeness)
-    int* winner;          // [Bmax][P0]
+    int* winner;          // [Bmax][P0]: per target cell the winning source pixel as (column << 16) | row, -1 = hole
     double* partial;      // [Bmax][maxblk][PH_NACC]
     double* A;            // [Bmax][L][36]   J^T J of the reference frame
     PhState* st;          // [Bmax]
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) ph_splat_kernel(PhArgs a) {
         }
         if (tR >= 0 && tR < rows - 1 && tC >= 0 && tC < cols - 1) {
             ++hits;
-            const int k = c * rows + r;               // column-major source index
+            const int k = (c << 16) | r;              // column-major order of the source (c * rows + r) as a packed key: same maximum, no division to decode
             atomicMax(&wn[tR * cols + tC], k); atomicMax(&wn[tR * cols + tC + 1], k);
             atomicMax(&wn[(tR + 1) * cols + tC], k); atomicMax(&wn[(tR + 1) * cols + tC + 1], k);
         }
@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(PH_THREADS, PH_ACCUM_MIN_BLOCKS) ph_accum_kern
                 // flattened index k: eps is row-major (cell k), J row k is the column-major pixel k (quirk 5); holes give -I_now
                 const int wk = wn[k];
                 if (a.reset_winner) wn[k] = -1;
-                const double cv = (wk >= 0) ? (double)g[(wk % rows) * cols + (wk / rows)] : 0.0;
+                const double cv = (wk >= 0) ? (double)g[(wk & 0xFFFF) * cols + (wk >> 16)] : 0.0;
                 const double e = cv - (double)gn[k];
                 const int r = k % rows, c = k / rows;
                 double J[6]; ph_jrow(g, d, rows, cols, r, c, a.sf, a.K, true, J);
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(PH_THREADS, PH_ACCUM_MIN_BLOCKS) ph_accum_kern
             auto gather = [&](int wk, int k) {
                 Taps t; t.rs = -1; t.cs = 0; t.gv = t.gr = t.gd = t.gnv = t.dz = 0u;
                 if (wk >= 0) {
-                    const int rs = wk % rows, cs = wk / rows;      // source pixel that owns this cell
+                    const int rs = wk & 0xFFFF, cs = wk >> 16;     // source pixel that owns this cell
                     const int c1 = (cs + 1 < cols) ? cs + 1 : cols - 2, r1 = (rs + 1 < rows) ? rs + 1 : rows - 2;   // ph_grad's REFLECT_101 taps
                     t.rs = rs; t.cs = cs;
                     t.gv = g[rs * cols + cs]; t.gr = g[rs * cols + (cols > 1 ? c1 : cs)]; t.gd = g[(rows > 1 ? r1 : rs) * cols + cs];
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(256) ph_canvas_kernel(PhArgs a, double* __rest
     if (i >= a.P) return;
     const int b = a.first;
     const int wk = a.winner[(long long)b * a.g.P[0] + i];
-    out[i] = (wk >= 0) ? (double)a.gray_ref[(long long)b * a.P + (wk % a.rows) * a.cols + (wk / a.rows)] : 0.0;
+    out[i] = (wk >= 0) ? (double)a.gray_ref[(long long)b * a.P + (wk & 0xFFFF) * a.cols + (wk >> 16)] : 0.0;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -525,6 +525,7 @@ extern "C" {
 int dvo_photo_create(const dvo_photo_config* cfg, dvo_photo_ctx** out) {
     if (!cfg || !out) { dvo_set_error("dvo_photo_create: null argument"); return DVO_ERR_ARG; }
     if (cfg->levels < 1 || cfg->levels > PH_MAX_LEVELS || cfg->max_batch < 1 || cfg->max_batch > 65535 || cfg->width < 8 || cfg->height < 8 ||
+        cfg->width > 32767 || cfg->height > 65535 ||          /* the winner map packs (column << 16) | row into an int */
         (cfg->width % (1 << (cfg->levels - 1))) || (cfg->height % (1 << (cfg->levels - 1)))) {
         dvo_set_error("dvo_photo_create: bad config %dx%d levels=%d (dimensions must be divisible by 2^(levels-1))", cfg->width, cfg->height, cfg->levels);
         return DVO_ERR_ARG;
