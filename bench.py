@@ -424,9 +424,9 @@ def bench_config3(env, args, pcie_peak):
         est.set_frames(dvo.FRAME_NOW, dev["now_bgr"].data_ptr(), None, count=B, device=True)
         solve()
 
-    # end to end: pinned host buffers, uploaded in 256-pair chunks on a copy stream into two staging sets so that chunk k+1 travels
+    # end to end: pinned host buffers, uploaded in 128-pair chunks on a copy stream into two staging sets so that chunk k+1 travels
     # while chunk k is converted and solved; poses read back at the end of the pass
-    CH = min(256, B)
+    CH = min(int(os.environ.get("DVO_BENCH_C3_CHUNK", "128")), B)
     copy_stream = torch.cuda.Stream()
     stage_buf = [{k: torch.empty((CH,) + tuple(v.shape[1:]), dtype=v.dtype, device="cuda") for k, v in pin.items()} for _ in range(2)]
     ev_up = [torch.cuda.Event() for _ in range(2)]

@@ -436,7 +436,8 @@ __global__ void ph_finish_kernel(PhState* st, int first, int count, int compat) 
     if (S.have && !compat) for (int k = 0; k < 16; ++k) S.Tr[k] = S.accTr[k];
 }
 
-__global__ void ph_init_state_kernel(PhState* st, int first, int count, const double* pose12, double lambda0) {
+// pose12 != null: the given poses; identity != 0: the identity; neither: the pose is kept
+__global__ void ph_init_state_kernel(PhState* st, int first, int count, const double* pose12, double lambda0, int identity = 0) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= count) return;
     PhState& S = st[first + i];
@@ -444,6 +445,8 @@ __global__ void ph_init_state_kernel(PhState* st, int first, int count, const do
         const double* p = pose12 + 12 * (long long)i;
         for (int r = 0; r < 3; ++r) { for (int c = 0; c < 3; ++c) S.Tr[4 * r + c] = p[3 * r + c]; S.Tr[4 * r + 3] = p[9 + r]; }
         S.Tr[12] = S.Tr[13] = S.Tr[14] = 0.0; S.Tr[15] = 1.0;
+    } else if (identity) {
+        for (int k = 0; k < 16; ++k) S.Tr[k] = (k % 5 == 0) ? 1.0 : 0.0;
     }
     S.have = 0; S.status = 0; S.iters_run = 0; S.stop = 0; S.nreproj = 0; S.nreproj_last = 0; S.lambda = lambda0; S.accE = 0.0;
     S.sumsq_first = S.sumsq_last = 0.0; S.visible = 0.0;
@@ -629,12 +632,15 @@ int dvo_photo_prepare_ref(dvo_photo_ctx* c, int first, int count, int compat) {
 int dvo_photo_set_pose(dvo_photo_ctx* c, int first, int count, const double* R9T3) {
     if (!ph_range_ok(c, first, count)) return DVO_ERR_ARG;
     if (count == 0) return DVO_OK;
-    std::vector<double> id((size_t)12 * count, 0.0);
-    if (R9T3) memcpy(id.data(), R9T3, sizeof(double) * 12 * count);
-    else for (int i = 0; i < count; ++i) { id[12 * (size_t)i] = 1.0; id[12 * (size_t)i + 4] = 1.0; id[12 * (size_t)i + 8] = 1.0; }
+    if (!R9T3) {                                   // identity: set on the device, no copy and no synchronisation
+        ph_init_state_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(c->st, first, count, nullptr, 0.0, 1);
+        c->launches++;
+        DVO_CUDA(cudaGetLastError());
+        return DVO_OK;
+    }
     double* d = nullptr;
     DVO_CUDA(cudaMalloc((void**)&d, sizeof(double) * 12 * count));
-    cudaError_t e = cudaMemcpyAsync(d, id.data(), sizeof(double) * 12 * count, cudaMemcpyHostToDevice, c->stream);
+    cudaError_t e = cudaMemcpyAsync(d, R9T3, sizeof(double) * 12 * count, cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
         ph_init_state_kernel<<<(count + 127) / 128, 128, 0, c->stream>>>(c->st, first, count, d, 0.0);
         c->launches++;
