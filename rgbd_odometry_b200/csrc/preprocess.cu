@@ -59,13 +59,45 @@ __global__ void __launch_bounds__(256) pyramid_level1_vec4_kernel(PyrArgs a) {
     }
 }
 
+// Levels >= 2 when every width is a multiple of 4: a thread produces four consecutive pixels of one level row (four independent
+// loads, one 4-byte / one 8-byte store) instead of one pixel per thread -- the one-pixel kernel is latency-bound, not traffic-bound.
+__global__ void __launch_bounds__(256) pyramid_nearest_vec4_kernel(PyrArgs a) {
+    const int b = a.first + blockIdx.y;
+    if (a.active && !a.active[b]) return;
+    int q = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (q >= a.sub_total) return;
+    int l = a.l0;
+    while (l < a.g.L - 1 && q >= a.g.P[l]) { q -= a.g.P[l]; ++l; }
+    const int w = a.g.w[l], W0 = a.g.w[0], H0 = a.g.h[0];
+    const int y = q / w, x = q - y * w;
+    const int sy = min(y << l, H0 - 1);
+    const long long row = lvl_at(a.g, 0, b) + (long long)sy * W0;
+    const long long dst = lvl_at(a.g, l, b) + q;
+    int sx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) sx[j] = min((x + j) << l, W0 - 1);
+    uint32_t gv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) gv[j] = a.gray[row + sx[j]];
+    if (a.depth) {
+        uint32_t dv[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dv[j] = a.depth[row + sx[j]]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dv[j] = dv[j] ? dv[j] : 1u;
+        *reinterpret_cast<uint2*>(a.depth + dst) = make_uint2(dv[0] | (dv[1] << 16), dv[2] | (dv[3] << 16));
+    }
+    *reinterpret_cast<uint32_t*>(a.gray + dst) = gv[0] | (gv[1] << 8) | (gv[2] << 16) | (gv[3] << 24);
+}
+
 int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
     const PyrGeom& g = c->geom;
     if (g.L < 2) return DVO_OK;
     const bool vec1 = (g.w[0] == 2 * g.w[1]) && (g.w[1] % 4 == 0);
     const int l0 = vec1 ? 2 : 1;
     int sub = 0;
-    for (int l = l0; l < g.L; ++l) sub += g.P[l];
+    bool vec_rest = true;                                  // 4-pixel groups never straddle a row or a level, stores stay aligned
+    for (int l = l0; l < g.L; ++l) { sub += g.P[l]; vec_rest = vec_rest && (g.w[l] % 4 == 0) && (g.off[l] % 4 == 0) && (g.P[l] % 4 == 0); }
     for (int f = 0; f < 2; ++f) {
         if (!(frames_mask & (1 << f))) continue;
         PyrArgs a; a.g = g; a.gray = c->gray[f]; a.depth = c->depth[f]; a.first = first; a.sub_total = sub; a.l0 = l0; a.active = c->active;
@@ -74,7 +106,11 @@ int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
             pyramid_level1_vec4_kernel<<<grid1, 256, 0, c->stream>>>(a);
             c->launches++;
         }
-        if (sub > 0) {
+        if (sub > 0 && vec_rest) {
+            dim3 grid((sub / 4 + 255) / 256, count);
+            pyramid_nearest_vec4_kernel<<<grid, 256, 0, c->stream>>>(a);
+            c->launches++;
+        } else if (sub > 0) {
             dim3 grid((sub + 255) / 256, count);
             pyramid_nearest_kernel<<<grid, 256, 0, c->stream>>>(a);
             c->launches++;
