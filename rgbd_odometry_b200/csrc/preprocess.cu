@@ -59,6 +59,29 @@ __global__ void __launch_bounds__(256) pyramid_level1_vec4_kernel(PyrArgs a) {
     }
 }
 
+// The same with eight level-1 pixels per thread (w1 % 8 == 0): one 16-byte gray load, two 16-byte depth loads.
+__global__ void __launch_bounds__(256) pyramid_level1_vec8_kernel(PyrArgs a) {
+    const int b = a.first + blockIdx.y;
+    if (a.active && !a.active[b]) return;
+    const int w1 = a.g.w[1], W0 = a.g.w[0], H0 = a.g.h[0];
+    const int q8 = blockIdx.x * blockDim.x + threadIdx.x;          // group of 8 output pixels
+    if (q8 * 8 >= a.g.P[1]) return;
+    const int y = (q8 * 8) / w1, x = q8 * 8 - y * w1;
+    const int sy = min(2 * y, H0 - 1);
+    const long long src = lvl_at(a.g, 0, b) + (long long)sy * W0 + 2 * x;
+    const long long dst = lvl_at(a.g, 1, b) + (long long)q8 * 8;
+    const uint4 gv = *reinterpret_cast<const uint4*>(a.gray + src);
+    uint4 d0, d1;
+    if (a.depth) { d0 = *reinterpret_cast<const uint4*>(a.depth + src); d1 = *reinterpret_cast<const uint4*>(a.depth + src + 8); }
+    auto even_bytes = [](uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x6420); };                                 // bytes 0, 2 of lo and hi
+    *reinterpret_cast<uint2*>(a.gray + dst) = make_uint2(even_bytes(gv.x, gv.y), even_bytes(gv.z, gv.w));
+    if (a.depth) {
+        auto fix = [](uint32_t v) { v &= 0xFFFFu; return v ? v : 1u; };                                                     // element 0 of the pair, 0 -> 1
+        *reinterpret_cast<uint4*>(a.depth + dst) = make_uint4(fix(d0.x) | (fix(d0.y) << 16), fix(d0.z) | (fix(d0.w) << 16),
+                                                              fix(d1.x) | (fix(d1.y) << 16), fix(d1.z) | (fix(d1.w) << 16));
+    }
+}
+
 // Levels >= 2 when every width is a multiple of 4: a thread produces four consecutive pixels of one level row (four independent
 // loads, one 4-byte / one 8-byte store) instead of one pixel per thread -- the one-pixel kernel is latency-bound, not traffic-bound.
 __global__ void __launch_bounds__(256) pyramid_nearest_vec4_kernel(PyrArgs a) {
@@ -101,7 +124,11 @@ int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
     for (int f = 0; f < 2; ++f) {
         if (!(frames_mask & (1 << f))) continue;
         PyrArgs a; a.g = g; a.gray = c->gray[f]; a.depth = c->depth[f]; a.first = first; a.sub_total = sub; a.l0 = l0; a.active = c->active;
-        if (vec1) {
+        if (vec1 && g.w[1] % 8 == 0 && g.off[1] % 8 == 0 && g.P[1] % 8 == 0 && g.P[0] % 16 == 0) {
+            dim3 grid1((g.P[1] / 8 + 255) / 256, count);
+            pyramid_level1_vec8_kernel<<<grid1, 256, 0, c->stream>>>(a);
+            c->launches++;
+        } else if (vec1) {
             dim3 grid1((g.P[1] / 4 + 255) / 256, count);
             pyramid_level1_vec4_kernel<<<grid1, 256, 0, c->stream>>>(a);
             c->launches++;
