@@ -1183,7 +1183,10 @@ struct PackArgs { const int32_t* d2; uint2* tex8; int w, h, P, Pt, tw, th, first
 
 // One CTA = a 64x8-pixel region = 16x2 tiles: the d2 values (plus a one-pixel halo) are staged through shared memory with
 // row-contiguous loads, every thread assembles two texels, and each warp stores 256 contiguous bytes (two whole tiles).
-constexpr int PACK_RW = 64, PACK_RH = 8;
+#ifndef DVO_PACK_RH
+#define DVO_PACK_RH 32         // tile rows of pack_texel_kernel: 8 / 16 / 32 rows -> 63.1 / 62.5 / 62.1 ms per 148 x 8 frames of 1280x720 (config 4)
+#endif
+constexpr int PACK_RW = 64, PACK_RH = DVO_PACK_RH;
 __global__ void __launch_bounds__(256) pack_texel_kernel(PackArgs a) {
     __shared__ int tile[PACK_RH + 2][PACK_RW + 2 + 1];
     const int b = a.first + blockIdx.z;
