@@ -1067,14 +1067,16 @@ int launch_edt_rows(dvo_ctx* c, int first, int count) {
         dim3 grid((g.h[l] + WARPS - 1) / WARPS, count);
         {   // dense images: expanding-window kernel
             const size_t smem = (size_t)WARPS * edt_window_scratch_ints(w) * sizeof(int);
-            if (smem > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(edt_rows_window_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static size_t opted_w = 0;                      // largest opt-in so far (one device per process)
+            if (smem > 48 * 1024 && smem > opted_w) { DVO_CUDA(cudaFuncSetAttribute(edt_rows_window_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); opted_w = smem; }
             edt_rows_window_kernel<WARPS><<<grid, WARPS * 32, smem, c->stream>>>(a, ne);
             c->launches++;
         }
         {   // sparse images: bisection kernel (exits immediately for every other image)
             const int wp = (w + 1) & ~1;
             const size_t smem = (size_t)WARPS * (w + wp) * sizeof(int);
-            if (smem > 48 * 1024) DVO_CUDA(cudaFuncSetAttribute(edt_rows_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            static size_t opted_b = 0;
+            if (smem > 48 * 1024 && smem > opted_b) { DVO_CUDA(cudaFuncSetAttribute(edt_rows_kernel<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); opted_b = smem; }
             edt_rows_kernel<WARPS><<<grid, WARPS * 32, smem, c->stream>>>(a, ne);
             c->launches++;
         }
