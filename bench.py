@@ -79,9 +79,34 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.samples = index, False, []
+        self.nvml = self._init_nvml()        # before the timed region: nvmlInit can take longer than a short timed region lasts
+
+    def _init_nvml(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM); get_reasons(h)
+            return pynvml, h, mx, get_reasons
+        except Exception:
+            return None
+
+    def _sample_nvml(self):
+        pynvml, h, mx, get_reasons = self.nvml
+        bits = (0x8, 0x40, 0x20, 0x4)      # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
+        try:
+            r = int(get_reasons(h))
+            self.samples.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
+        except Exception:
+            pass
 
     def run(self):
-        if self._run_nvml():
+        if self.nvml is not None:
+            while not self.stop_flag:
+                self._sample_nvml()
+                time.sleep(0.005)
             return
         while not self.stop_flag:
             try:
@@ -93,29 +118,20 @@ class ClockSampler(threading.Thread):
                 pass
             time.sleep(0.1)
 
-    def _run_nvml(self):
-        try:
-            import pynvml
-            pynvml.nvmlInit()
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
-            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
-            bits = (0x8, 0x40, 0x20, 0x4)      # hw_slowdown, hw_thermal_slowdown, sw_thermal_slowdown, sw_power_cap
-            pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM); get_reasons(h)
-        except Exception:
-            return False
-        while not self.stop_flag:
-            try:
-                r = int(get_reasons(h))
-                self.samples.append([str(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)), str(mx)] + ["Active" if r & b else "Not Active" for b in bits])
-            except Exception:
-                pass
-            time.sleep(0.005)
-        return True
-
     def finish(self):
         self.stop_flag = True
         self.join(timeout=2)
+        if not self.samples:                 # region shorter than one sampling period: one reading right behind it
+            if self.nvml is not None:
+                self._sample_nvml()
+            else:
+                try:
+                    out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.samples.append([x.strip() for x in out.split(",")])
+                except Exception:
+                    pass
         return self.summary()
 
     def summary(self):
