@@ -217,7 +217,19 @@ class Env:
         torch.cuda.set_device(self.local)
         self.numa = bind_to_gpu_numa_node(self.local) if self.world > 1 else None    # host buffers of the e2e legs next to this rank's GPU
         if self.world > 1:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            # NCCL prints its version banner on stdout when the communicator is created; stdout carries the one JSON line, so
+            # file descriptor 1 points at stderr while the process group and its communicator come up
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+                dist.all_reduce(torch.zeros(1, device="cuda"))
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
         # a dedicated non-default stream shared by torch (events, NCCL) and the C-ABI contexts, so that the CUDA events are
         # recorded on the stream the kernels are launched on
         self.stream = torch.cuda.Stream()
