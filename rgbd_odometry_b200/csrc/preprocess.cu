@@ -1,5 +1,6 @@
-// preprocess.cu -- pyramid, Canny (+ fused EDT column pass / reference point list), EDT row pass,
-// normalise + gradient.  All integer stages are bit-exact against oracle/dvo_oracle.hpp.
+// preprocess.cu -- pyramid, Canny (Sobel + NMS kernel; hysteresis kernel with the fused EDT column pass / reference point list),
+// EDT row pass + packed distance texels, normalise + gradient (inspection only).  All stages are bit-exact against
+// oracle/dvo_oracle.hpp.
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -153,10 +154,8 @@ int launch_pyramid(dvo_ctx* c, int first, int count, int frames_mask) {
 // bit i of word wx <-> x = 32*wx + i) with a one-word / one-row zero border, in shared memory when they fit
 // (640x480: 2 x 42 KB) or in a global scratch otherwise.
 //
-//  phase 1  Sobel + NMS.  Thread <-> image column, rows are swept top to bottom with the 3x3 neighbourhood of
-//           gradient magnitudes kept in registers (separable Sobel: one byte load per pixel); horizontal
-//           neighbours come from warp shuffles, warp-edge lanes exchange through shared memory (one barrier per
-//           row).  `S` row strips run concurrently.  Ballots produce the bitmap words directly.
+//  phase 1  Sobel + NMS + double threshold: sobel_nms_kernel above (its own launch over every level and both frames); this
+//           kernel starts from the candidate and strong bitmaps it left in the scratch.
 //  phase 2  Hysteresis = monotone fixed point E <- C & dilate3x3(E) from E = strong.  Its closure equals the
 //           reference's stack traversal regardless of order, hence bit-exact.  Thread <-> (word column, row
 //           strip): each iteration sweeps the strip down and up so information crosses a whole strip per
@@ -181,7 +180,7 @@ struct CannyArgs {
     int count;             // blocks [count, 2 count) process the now frame of the same slots (one launch for both frames)
     long long gscratch_frame_stride;   // global bitmaps: offset of the now frame's scratch
     float tmpfx, tmpfy, tmpcx, tmpcy;
-    uint32_t* gscratch;    // null -> shared memory bitmaps
+    uint32_t* gscratch;    // this level's region of the bitmap scratch (slot 0, reference frame): source of the bitmaps, and their home when they do not fit in shared memory
     long long gscratch_stride;
     int first;
     int bm_words;          // words per bitmap region
