@@ -440,6 +440,9 @@ __global__ void __launch_bounds__(NMS_WARPS * 32, DVO_NMS_MIN_BLOCKS) sobel_nms_
 }
 
 constexpr int CANNY_MAX_WARPS = 24;
+#ifndef DVO_CANNY_INTERLEAVE
+#define DVO_CANNY_INTERLEAVE 1
+#endif
 #ifndef DVO_CANNY_STOP_AFTER
 #define DVO_CANNY_STOP_AFTER 0
 #endif
@@ -462,9 +465,18 @@ __global__ void __launch_bounds__(768, 2) canny_kernel(CannyArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // one launch covers the reference AND the now frame of every slot: 2 x count CTAs leave a much fuller last wave than two
     // launches of count CTAs each (1024 CTAs at 296 resident = 3.46 waves)
+#if DVO_CANNY_INTERLEAVE
+    // both frames in one launch (count < 0x7fffffff): even blocks take the reference frame, odd blocks the now frame of the same
+    // slot, so that every SM works on a mix of the two kinds of CTA (their last phases differ)
+    const bool both = a.count != 0x7fffffff;
+    const int second = both ? (int)(blockIdx.x & 1u) : 0;
+    const int frame = second ? DVO_FRAME_NOW : a.frame0;
+    const int b = a.first + (both ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
+#else
     const int second = (blockIdx.x >= (unsigned)a.count) ? 1 : 0;
     const int frame = second ? DVO_FRAME_NOW : a.frame0;
     const int b = a.first + (int)blockIdx.x - second * a.count;
+#endif
     const bool do_points = (frame == DVO_FRAME_REF), do_cols = (frame == DVO_FRAME_NOW);
     if (a.active && !a.active[b]) return;
     const int w = a.w, h = a.h;
